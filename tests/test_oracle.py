@@ -1,0 +1,249 @@
+"""Pin the CPU oracle: PRNG known answers + the reference tests' own identities.
+
+Each test names the reference test it restates (paths under /root/reference).
+"""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import prng, ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def kat():
+    with open(os.path.join(GOLD, "prng_kat.json")) as f:
+        return json.load(f)
+
+
+# ------------------------------------------------------------------ PRNG KATs
+
+
+def test_threefry_random123_kat(kat):
+    for case in kat["threefry2x32_20"]:
+        key = [int(x, 16) for x in case["key"]]
+        ctr = [int(x, 16) for x in case["ctr"]]
+        a, b = prng.threefry2x32(key, np.array([ctr[0]], np.uint32), np.array([ctr[1]], np.uint32))
+        assert [int(a[0]), int(b[0])] == [int(x, 16) for x in case["out"]]
+
+
+def test_jax_legacy_known_outputs(kat):
+    g = kat["jax_legacy"]
+    k0 = prng.prng_key(0)
+    assert prng.split(k0, mode="legacy").tolist() == g["split_key0"]
+    assert prng.uniform(k0, mode="legacy") == np.float32(g["uniform_key0"])
+    assert prng.normal(k0, mode="legacy") == np.float32(g["normal_key0"])
+    assert prng.normal(prng.prng_key(42), mode="legacy") == np.float32(g["normal_key42"])
+
+
+def test_jax_partitionable_known_outputs(kat):
+    g = kat["jax_partitionable"]
+    k0 = prng.prng_key(0)
+    assert prng.split(k0).tolist() == g["split_key0"]
+    assert int(prng.random_bits(k0, ())) == int(g["bits_key0"], 16)
+    assert np.float32(prng.uniform(k0)) == np.float32(g["uniform_key0"])
+    assert prng.normal(k0) == np.float32(g["normal_key0"])
+    assert prng.normal(prng.prng_key(42)) == np.float32(g["normal_key42"])
+    assert prng.rademacher(k0, ()) == g["rademacher_key0"]
+
+
+def test_offset_is_a_row_slice():
+    key = prng.prng_key(7)
+    full = prng.rademacher(key, (6, 11))
+    part = prng.rademacher(key, (2, 11), offset=3 * 11)
+    assert np.array_equal(full[3:5], part)
+    fulln = prng.normal(key, (6, 11))
+    partn = prng.normal(key, (2, 11), offset=3 * 11)
+    assert np.array_equal(fulln[3:5], partn)
+
+
+def test_counter_high_word_is_live():
+    key = prng.prng_key(1)
+    a = prng.random_bits(key, (4,), offset=(1 << 32) + 5)
+    hi = np.full(4, 1, np.uint32)
+    lo = np.arange(5, 9, dtype=np.uint32)
+    x0, x1 = prng.threefry2x32(key, hi, lo)
+    assert np.array_equal(a, x0 ^ x1)
+
+
+# tests/test_stochtrace/test_samplers.py:46-77
+@pytest.mark.parametrize("which", ["signs", "normal"])
+def test_samplers_moments_and_determinism(which):
+    n, num = 5, 100_000
+    make = ref.sampler_signs if which == "signs" else ref.sampler_normal
+    sampler = make(n, num=num)
+    x = sampler(prng.prng_key(1))
+    assert x.shape == (num, n)
+    if which == "signs":
+        assert np.all(np.abs(x) == 1)
+    assert np.allclose(x.mean(axis=0), 0, atol=1e-2)
+    assert np.allclose(x.T @ x / num, np.eye(n), atol=2e-2)
+    assert np.array_equal(x, sampler(prng.prng_key(1)))
+    assert not np.array_equal(x, sampler(prng.prng_key(2)))
+
+
+# ------------------------------------------------------------------ decompositions
+
+
+def _spd(n, dtype=np.float64, seed=1):
+    eig = np.arange(1.0, 1.0 + n).astype(dtype)
+    return ref.hermitian_matrix_from_eigenvalues(eig, prng.prng_key(seed), dtype=dtype)
+
+
+# tests/test_decomp/test_tridiag_sym.py:7-38
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_tridiag_full_rank_reconstructs(reortho):
+    n = 12
+    A = _spd(n)
+    v = prng.normal(prng.prng_key(2), (n,), np.float64)
+    Q, T, res, c = ref.tridiag_sym(n, reortho=reortho)(lambda x: A @ x, v)
+    tol = 1e-5 if reortho == "full" else 1e-1
+    assert np.allclose(Q @ Q.T, np.eye(n), atol=tol)
+    assert np.allclose(Q.T @ Q, np.eye(n), atol=tol)
+    assert np.allclose(Q.T @ T @ Q, A, atol=tol * n)
+    assert np.allclose(c, 1 / np.linalg.norm(v))
+
+
+# tests/test_decomp/test_tridiag_sym.py:43-65
+@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("k", [1, 5, 11])
+def test_tridiag_decomposition_identity(reortho, k):
+    n = 12
+    A = _spd(n)
+    v = prng.normal(prng.prng_key(3), (n,), np.float64)
+    Q, T, q, _ = ref.tridiag_sym(k, reortho=reortho)(lambda x: A @ x, v)
+    e_K = np.eye(k)[-1]
+    ref.assert_allclose(A @ Q.T - Q.T @ T - np.outer(q, e_K), np.zeros((n, k)))
+    ref.assert_allclose(Q @ Q.T, np.eye(k))
+
+
+# tests/test_decomp/test_consistency.py:27-63
+@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("k", [6, 13, 0])
+def test_shapes(reortho, k):
+    n = 13
+    A = _spd(n)
+    v = np.ones(n)
+    Q, T, r, c = ref.tridiag_sym(k, reortho=reortho)(lambda x: A @ x, v)
+    assert Q.shape == (k, n) and T.shape == (k, k) and r.shape == (n,) and np.shape(c) == ()
+
+
+@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("k", [-1, 14])
+def test_num_matvecs_out_of_range(reortho, k):
+    A = _spd(13)
+    with pytest.raises(ValueError, match="exceeds"):
+        ref.tridiag_sym(k, reortho=reortho)(lambda x: A @ x, np.ones(13))
+
+
+def test_unknown_reortho():
+    with pytest.raises(ValueError, match="unsupported"):
+        ref.tridiag_sym(3, reortho="partial")
+
+
+def test_full_offdiag_is_mean_of_norm_and_projection():
+    # offdiag_i = (|v_i| + q_i^T A q_{i+1}) / 2
+    n, k = 20, 6
+    A = _spd(n)
+    v = prng.normal(prng.prng_key(4), (n,), np.float64)
+    Q, (d, e), _, _ = ref.tridiag_sym(k, reortho="full", materialize=False)(lambda x: A @ x, v)
+    assert np.allclose(d, np.einsum("kn,nm,km->k", Q, A, Q))
+    assert np.allclose(e, np.einsum("kn,nm,km->k", Q[:-1], A, Q[1:]), rtol=1e-10)
+
+
+# ------------------------------------------------------------------ funm / SLQ
+
+
+# tests/test_funm/test_monte_carlo_funm_sym_logdet.py:41-67
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_logdet_exact_for_full_depth(reortho):
+    n = 50
+    A = _spd(n)
+    x = prng.normal(prng.prng_key(1), (n,), np.float64) + 10
+    integrand = ref.monte_carlo_funm_sym_logdet(ref.tridiag_sym(n - 1, reortho=reortho))
+    got = integrand(lambda v: A @ v, x)
+    lam, U = np.linalg.eigh(A)
+    want = x @ (U @ np.diag(np.log(lam)) @ U.T) @ x
+    assert np.allclose(got, want)
+
+
+# tests/test_funm/test_monte_carlo_funm_sym_logdet.py:16-38
+def test_logdet_spd_estimate():
+    """The reference's own assertion at the reference's own seeds and dtype (fp32).
+
+    With 10 normal probes the statistical error of this estimate is ~3 %, so the
+    reference's 1 % assertion only holds for its particular realised samples.  It
+    holds for this restatement in JAX's default (partitionable) PRNG mode and
+    fails in legacy mode / other dtypes -- i.e. this test pins the oracle's whole
+    sample stream + Lanczos + quadrature chain against the reference's test.
+    """
+    n, nsig, k = 200, 30, 10
+    key_A, key = prng.split(prng.prng_key(1))
+    d = np.arange(n, dtype=np.float32) / np.float32(n) + np.float32(1.0)
+    d[nsig:] = 0.001
+    A = ref.hermitian_matrix_from_eigenvalues(d, key_A)
+    assert A.dtype == np.float32
+    sampler = ref.sampler_normal(n, num=10, dtype=np.float32)
+    integrand = ref.monte_carlo_funm_sym_logdet(ref.tridiag_sym(k))
+    got = ref.estimator_monte_carlo(integrand, sampler)(lambda v: A @ v, key)
+    want = np.linalg.slogdet(A)[1]
+    assert np.allclose(got, want, atol=1e-2, rtol=1e-2), (got, want)
+
+
+# tests/test_funm/test_funm_lanczos_sym.py:7-37
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_funm_lanczos_sym(reortho):
+    n, k = 11, 6
+    eig = np.arange(1.0, 1.0 + n) / n
+    A = ref.hermitian_matrix_from_eigenvalues(eig, prng.prng_key(1))
+    v = prng.normal(prng.prng_key(2), (n,), np.float64)
+    lam, U = np.linalg.eigh(A)
+    want = U @ (np.sin(lam) * (U.T @ v))
+    fun = ref.funm_lanczos_sym(ref.dense_funm_sym_eigh(np.sin), ref.tridiag_sym(k, reortho=reortho))
+    got = fun(lambda x: A @ x, v)
+    assert np.allclose(got, want, atol=1e-6)
+
+
+# tests/test_stochtrace/test_monte_carlo/test_trace.py:7-37 (real case)
+def test_hutchinson_trace():
+    n = 4
+    J = np.asarray(prng.normal(prng.prng_key(3), (n, n), np.float64))
+    sampler = ref.sampler_normal(n, num=100_000, dtype=np.float64)
+    got = ref.estimator_monte_carlo(ref.monte_carlo_trace(), sampler)(lambda v: J @ v, prng.prng_key(1))
+    assert np.allclose(got, np.trace(J), rtol=1e-2, atol=2e-2)
+
+
+# tests/test_stochtrace/test_monte_carlo/test_estimator_mean_and_std.py:7-93
+def test_mean_and_sem():
+    n, P = 4, 20_000
+    J = np.asarray(prng.normal(prng.prng_key(3), (n, n), np.float64))
+    sampler = ref.sampler_signs(n, num=P, dtype=np.float64)
+    mean, sem = ref.estimator_monte_carlo_mean_and_sem(ref.monte_carlo_trace(), sampler)(
+        lambda v: J @ v, prng.prng_key(1))
+    plain = ref.estimator_monte_carlo(ref.monte_carlo_trace(), sampler)(lambda v: J @ v, prng.prng_key(1))
+    assert np.allclose(mean, plain)
+    # Rademacher: Var[v^T J v] = sum_{i != j} (J_ij^2 + J_ij J_ji)
+    off = J - np.diag(np.diag(J))
+    var = np.sum(off * off) + np.sum(off * off.T)
+    assert np.allclose(sem, np.sqrt(var / P), rtol=5e-2)
+
+
+# ------------------------------------------------------------------ batched == single
+
+
+@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_batched_matches_single(reortho, dtype):
+    n, k, P = 64, 9, 5
+    eig = (1.0 + np.arange(n) / 8.0).astype(dtype)
+    A = ref.hermitian_matrix_from_eigenvalues(eig, prng.prng_key(5), dtype=dtype)
+    V = prng.rademacher(prng.prng_key(1), (P, n), dtype)
+    q, theta = ref.slq_batched(lambda X: X @ A.T, V, k, reortho=reortho)
+    integrand = ref.monte_carlo_funm_sym_logdet(ref.tridiag_sym(k, reortho=reortho))
+    single = np.array([integrand(lambda x: A @ x, v) for v in V])
+    tol = 2e-4 if dtype == np.float32 else 1e-10
+    assert np.allclose(q, single, rtol=tol)
