@@ -1,0 +1,238 @@
+/*
+ * matfree_b200.h -- C ABI of libmatfree_b200.so
+ *
+ * B200 (sm_100a) kernels for matfree's stochastic-Lanczos-quadrature hot path.
+ * The reference (pnkraemer/matfree) is pure Python over JAX and has no FFI of
+ * its own; each entry point below replaces the XLA lowering of the reference
+ * lines cited next to it (paths relative to the reference checkout) and is what
+ * a `jax.ffi.ffi_call` target for that function binds.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name starts with `h_`;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
+ *     void*); nothing here synchronises the device or the stream, allocates or
+ *     frees device memory, or keeps a pointer after returning;
+ *   - scratch memory is caller-provided (`workspace`, sized by the matching
+ *     `*_workspace_bytes` function);
+ *   - return value: 0 on success, a negative MF_ERR_* code otherwise;
+ *     `mf_last_error()` returns a thread-local message for the last failure;
+ *   - `dtype`: MF_F32 or MF_F64 (the arithmetic type of vectors and operator
+ *     values; reductions always accumulate in fp64);
+ *   - block vectors ("blocked layout") are row-major `X[n][ld]`: the `ld`
+ *     probes of a tile are contiguous for each of the n rows.  `ld` must be a
+ *     power of two in [1, 256].  The reference layout is probe-major `(P, n)`
+ *     (matfree/stochtrace.py:961-962).
+ */
+#ifndef MATFREE_B200_H_
+#define MATFREE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_ABI_VERSION 1
+
+/* status codes */
+#define MF_OK 0
+#define MF_ERR_INVALID_ARGUMENT (-1)
+#define MF_ERR_CUDA (-2)
+#define MF_ERR_UNSUPPORTED (-3)
+#define MF_ERR_WORKSPACE (-4)
+
+/* dtypes */
+#define MF_F32 0
+#define MF_F64 1
+
+/* sampler kinds (matfree/stochtrace.py:927-937) */
+#define MF_SAMPLER_SIGNS 0  /* sampler_signs  -> jax.random.rademacher */
+#define MF_SAMPLER_NORMAL 1 /* sampler_normal -> jax.random.normal     */
+
+/* prng flags */
+#define MF_PRNG_X64_BITS 1 /* jax_enable_x64: rademacher consumes a 64-bit draw */
+
+/* probe layouts */
+#define MF_LAYOUT_PROBE_MAJOR 0 /* out[p * ld + r], reference layout (P, n)   */
+#define MF_LAYOUT_BLOCKED 1     /* out[r * ld + b], blocked layout   [n][ld] */
+
+/* operator kinds (new surface; the reference takes any callable,
+ * matfree/stochtrace.py:47-49) */
+#define MF_OP_DENSE 0 /* A[n][n] row-major, symmetric            */
+#define MF_OP_CSR 1   /* indptr[n+1] i32, indices[nnz] i32, data */
+#define MF_OP_GRAM 2  /* A[m][n] row-major; operator is A^T A    */
+
+/* reorthogonalisation (matfree/decomp.py:30-37) */
+#define MF_REORTHO_NONE 0 /* three-term Lanczos, decomp.py:220-292          */
+#define MF_REORTHO_FULL 1 /* Arnoldi + CGS2, T=(H+H^T)/2, decomp.py:125-145 */
+
+/* matrix functions fused into the quadrature (matfree/funm.py:186-202,322-335) */
+#define MF_FN_NONE 0     /* only nodes/weights                  */
+#define MF_FN_LOG 1      /* log(x)        (logdet)              */
+#define MF_FN_EXP 2      /* exp(param*x)                        */
+#define MF_FN_INV 3      /* 1/x                                 */
+#define MF_FN_SQRT 4     /* sqrt(x)                             */
+#define MF_FN_POW 5      /* x^param                             */
+#define MF_FN_IDENTITY 6 /* x                                   */
+#define MF_FN_SIN 7      /* sin(param*x)                        */
+
+/* integrands for mf_estimate_* */
+#define MF_INTEGRAND_SLQ 0   /* funm.monte_carlo_funm_sym[_logdet], funm.py:186-243 */
+#define MF_INTEGRAND_TRACE 1 /* stochtrace.monte_carlo_trace, stochtrace.py:853-865 */
+
+/* An operator; plain pointers and sizes only. */
+typedef struct mf_operator {
+  int32_t kind;           /* MF_OP_*                                     */
+  int32_t dtype;          /* MF_F32 / MF_F64                             */
+  int64_t n;              /* operator is n x n                           */
+  int64_t m;              /* GRAM: rows of A; otherwise ignored          */
+  int64_t nnz;            /* CSR only                                    */
+  const void* values;     /* DENSE A[n][n]; GRAM A[m][n]; CSR data[nnz]  */
+  const int32_t* indptr;  /* CSR only                                    */
+  const int32_t* indices; /* CSR only                                    */
+  int64_t lda;            /* DENSE/GRAM leading dimension (elements)     */
+  void* op_scratch;       /* GRAM: m*ld elements of dtype; else unused   */
+} mf_operator_t;
+
+const char* mf_last_error(void);
+int32_t mf_abi_version(void);
+/* Number of CUDA kernels this library has launched in the calling process. */
+int64_t mf_launch_count(void);
+
+/* Profiling aid (not on the hot path): when enabled, every kernel launch of this
+ * library is bracketed by CUDA events recorded on the launching stream.
+ * mf_timing_collect SYNCHRONISES on those events (the one documented exception to
+ * the no-sync rule; call it only after the stream has been synchronised), adds the
+ * elapsed milliseconds and launch counts per kernel class into the HOST arrays
+ * h_ms[MF_KC_COUNT] / h_launches[MF_KC_COUNT], and resets the recorder. */
+#define MF_KC_PROBE_GEN 0
+#define MF_KC_SPMM_CSR 1
+#define MF_KC_GEMM 2
+#define MF_KC_DOT 3
+#define MF_KC_FINALIZE 4
+#define MF_KC_LANCZOS_UPDATE 5
+#define MF_KC_SCALE 6
+#define MF_KC_REORTH_DOTS 7
+#define MF_KC_REORTH_UPDATE 8
+#define MF_KC_TRIDIAG_QUAD 9
+#define MF_KC_MC_REDUCE 10
+#define MF_KC_OTHER 11
+#define MF_KC_COUNT 12
+int32_t mf_timing_enable(int32_t on);
+int32_t mf_timing_collect(double* h_ms, int64_t* h_launches);
+
+/* K1 -- probe generator.  Replaces jax.random.rademacher / jax.random.normal
+ * as called by matfree/stochtrace.py:957-964 (via matfree/backend/prng.py:14-29):
+ * Threefry-2x32 in JAX's partitionable counter mode, counter = p * n + r for
+ * probe p, component r.  Writes probes p0 .. p0+num_probes-1.  In blocked
+ * layout columns num_probes .. ld-1 are zero-filled.  `sqnorm_out` (optional,
+ * double[ld or num_probes]) receives the squared 2-norm of every probe. */
+int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
+                     int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
+                     int32_t sampler, int32_t prng_flags, double* sqnorm_out,
+                     void* stream);
+
+/* The user matvec (matfree/stochtrace.py:47-49, funm.py:231-235,
+ * decomp.py:163-164) applied to a whole probe block:
+ * W[n][ld] = A @ X[n][ld] (blocked layout). */
+int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* stream);
+int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
+                        void* W, int64_t ld, void* stream);
+int32_t mf_matmat_csr(const int32_t* indptr, const int32_t* indices, const void* data,
+                      int64_t n, int64_t nnz, int32_t dtype, const void* X, void* W,
+                      int64_t ld, void* stream);
+int32_t mf_matmat_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
+                       const void* X, void* Y_scratch, void* W, int64_t ld, void* stream);
+
+/* Layout helpers: probe-major (P, n) <-> blocked [n][ld]. */
+int32_t mf_to_blocked(const void* src_pn, void* dst_blocked, int32_t dtype, int64_t n,
+                      int64_t num_probes, int64_t ld, void* stream);
+int32_t mf_from_blocked(const void* src_blocked, void* dst_pn, int32_t dtype, int64_t n,
+                        int64_t num_probes, int64_t ld, void* stream);
+
+/* decomp.tridiag_sym (matfree/decomp.py:30-122) on a probe block.
+ *   V0        in : start block [n][ld] (blocked), NOT normalised; preserved
+ *   alphas    out: [k][ld]   diagonal of T           (row j = step j)
+ *   betas     out: [k][ld]   row j < k-1: off-diagonal j; row k-1: residual norm
+ *                            (reortho=NONE) / norm of the last residual (FULL)
+ *   init_len  out: [ld]      |V0[:, b]|  (init_length_inv = 1/init_len)
+ *   Q         out: optional [k][n][ld] basis (required for reortho=FULL);
+ *                  Q[j] is the j-th Lanczos vector of every probe
+ *   residual  out: optional [n][ld]; NONE: b_{k-1} * v_k  (decomp.py:167);
+ *                  FULL: last un-normalised vector (decomp.py:141-143)
+ * All scalar outputs are in `dtype`. */
+int64_t mf_lanczos_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k,
+                                   int32_t reortho, int32_t want_Q);
+int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
+                   int32_t reortho, void* alphas, void* betas, void* init_len, void* Q,
+                   void* residual, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K5 -- Gauss quadrature of the tridiagonal matrices of a probe block:
+ * replaces eigh + V f(L) V^T + e1^T(.)e1 of matfree/funm.py:239-241,330-333.
+ * One lane per probe, implicit-QL with the first eigenvector row only.
+ *   alphas [k][ld], betas [k][ld] as produced by mf_lanczos
+ *   quad   out: [ld] (dtype)  init_len^2 * sum_j f(theta_j) w_j  (unless fn==MF_FN_NONE)
+ *   nodes  out: optional double [k][ld] Ritz values, ascending
+ *   weights out: optional double [k][ld] squared first eigenvector components */
+int64_t mf_tridiag_quad_workspace_bytes(int64_t ld, int64_t k);
+int32_t mf_tridiag_quad(const void* alphas, const void* betas, const void* init_len,
+                        int32_t dtype, int64_t ld, int64_t num_probes, int64_t k, int32_t fn,
+                        double fn_param, void* quad, double* nodes, double* weights,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/* K6 -- Monte-Carlo reduction (matfree/stochtrace.py:50,85-86):
+ * stats_out = double[4] {mean, std(ddof=0), sem = std/sqrt(P), P}. */
+int32_t mf_mc_reduce(const void* values, int32_t dtype, int64_t num, double* stats_out,
+                     void* stream);
+
+/* Fused estimator: everything `estimate(matvec, key)` does for one probe range
+ * (matfree/stochtrace.py:47-50 with the SLQ or Hutchinson integrand):
+ * generate probes p0..p0+num_probes-1 of the (P_total, n) sample array of
+ * `key`, run k Lanczos steps per probe (tile by tile, `ld` probes per tile),
+ * quadrature, and write one value per probe to `quad_out[num_probes]` (dtype).
+ * Probes are never materialised in the reference layout.  The caller reduces
+ * `quad_out` with mf_mc_reduce (after gathering the shards of other GPUs).
+ * Optional per-tile outputs (tile t = probes t*ld .. t*ld+ld-1 of the range):
+ * alphas_out / betas_out [tiles][k][ld], lens_out [tiles][ld] (|v0| per probe). */
+int64_t mf_estimate_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k,
+                                    int32_t reortho, int32_t integrand);
+int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
+                    int32_t prng_flags, uint32_t key0, uint32_t key1, int64_t p0,
+                    int64_t num_probes, int64_t ld, int64_t k, int32_t reortho, int32_t fn,
+                    double fn_param, void* quad_out, void* alphas_out, void* betas_out,
+                    void* lens_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Per-kind spellings of the fused estimator (what the per-kind FFI targets bind). */
+int32_t mf_slq_estimate_dense(const void* A, int64_t n, int64_t lda, int32_t dtype,
+                              int32_t sampler, int32_t prng_flags, uint32_t key0,
+                              uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
+                              int64_t k, int32_t reortho, int32_t fn, double fn_param,
+                              void* quad_out, void* workspace, int64_t workspace_bytes,
+                              void* stream);
+int32_t mf_slq_estimate_csr(const int32_t* indptr, const int32_t* indices, const void* data,
+                            int64_t n, int64_t nnz, int32_t dtype, int32_t sampler,
+                            int32_t prng_flags, uint32_t key0, uint32_t key1, int64_t p0,
+                            int64_t num_probes, int64_t ld, int64_t k, int32_t reortho,
+                            int32_t fn, double fn_param, void* quad_out, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+int32_t mf_slq_estimate_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
+                             int32_t sampler, int32_t prng_flags, uint32_t key0,
+                             uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
+                             int64_t k, int32_t reortho, int32_t fn, double fn_param,
+                             void* quad_out, void* workspace, int64_t workspace_bytes,
+                             void* stream);
+
+/* funm.funm_lanczos_sym (matfree/funm.py:114-147) given a stored basis:
+ * out[n][ld] = init_len * sum_j Q[j] * y[j],  y = f(T) e1 per probe
+ * (coeffs [k][ld], dtype).  `mf_tridiag_funm_e1` computes y. */
+int32_t mf_tridiag_funm_e1(const void* alphas, const void* betas, int32_t dtype, int64_t ld,
+                           int64_t num_probes, int64_t k, int32_t fn, double fn_param,
+                           void* coeffs, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+int32_t mf_basis_combine(const void* Q, const void* coeffs, const void* scale, int32_t dtype,
+                         int64_t n, int64_t ld, int64_t k, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATFREE_B200_H_ */

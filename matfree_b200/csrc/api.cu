@@ -1,0 +1,717 @@
+// C-ABI entry points of libmatfree_b200.so and the stream-ordered drivers
+// (Lanczos loops, fused estimator) built from the kernels in this directory.
+// Nothing in this file synchronises, allocates or frees device memory.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "internal.h"
+
+namespace mf {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static std::mutex mu;
+  static int cache[64];
+  static bool have[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 148;
+  }
+  if (dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!have[dev]) {
+    int v = 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      cudaGetLastError();
+      v = 148;
+    }
+    cache[dev] = v;
+    have[dev] = true;
+  }
+  return cache[dev];
+}
+
+// ---------------------------------------------------------------- launch timing
+namespace {
+struct TimingRec {
+  int cls;
+  cudaEvent_t beg, end;
+};
+struct TimingState {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<TimingRec> recs;           // in flight
+  std::vector<cudaEvent_t> free_events;  // recycled
+} g_timing;
+std::atomic<bool> g_timing_on{false};
+
+cudaEvent_t take_event() {
+  if (!g_timing.free_events.empty()) {
+    cudaEvent_t e = g_timing.free_events.back();
+    g_timing.free_events.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+KernelScope::KernelScope(int cls_, cudaStream_t st_) : cls(cls_), st(st_), slot(-1) {
+  if (!g_timing_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  TimingRec r{cls, take_event(), take_event()};
+  cudaEventRecord(r.beg, st);
+  g_timing.recs.push_back(r);
+  slot = (int)g_timing.recs.size() - 1;
+}
+KernelScope::~KernelScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  if (slot < (int)g_timing.recs.size()) cudaEventRecord(g_timing.recs[slot].end, st);
+}
+
+namespace {
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  int64_t size;
+  int64_t used = 0;
+  bool dry;  // sizing pass: never dereferenced
+  Arena(void* b, int64_t s, bool d) : base((char*)b), size(s), dry(d) {}
+  void* take(int64_t bytes) {
+    const int64_t off = used;
+    used = align_up(used + bytes, 256);
+    if (dry) return (void*)(uintptr_t)(off + 256);  // non-null dummy
+    if (used > size) return nullptr;
+    return base + off;
+  }
+};
+
+inline int vec_of(int32_t dtype, int64_t ld) {
+  const int nv = dtype == MF_F64 ? 2 : 4;
+  return ld >= nv ? nv : 1;
+}
+
+int32_t validate_op(const mf_operator_t* op) {
+  if (op == nullptr) {
+    set_error("operator is null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (op->dtype != MF_F32 && op->dtype != MF_F64) {
+    set_error("operator dtype %d unsupported", op->dtype);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (op->n <= 0) {
+    set_error("operator dimension n=%lld must be positive", (long long)op->n);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  switch (op->kind) {
+    case MF_OP_DENSE:
+      if (!op->values || op->lda < op->n) {
+        set_error("dense operator needs values and lda >= n");
+        return MF_ERR_INVALID_ARGUMENT;
+      }
+      return MF_OK;
+    case MF_OP_CSR:
+      if (!op->values || !op->indptr || !op->indices) {
+        set_error("csr operator needs indptr, indices and values");
+        return MF_ERR_INVALID_ARGUMENT;
+      }
+      return MF_OK;
+    case MF_OP_GRAM:
+      if (!op->values || op->m <= 0 || op->lda < op->n) {
+        set_error("gram operator needs values, m > 0 and lda >= n");
+        return MF_ERR_INVALID_ARGUMENT;
+      }
+      return MF_OK;
+    default:
+      set_error("unknown operator kind %d", op->kind);
+      return MF_ERR_INVALID_ARGUMENT;
+  }
+}
+
+// W = s * (A @ X); if alpha_partial != null and the operator can fuse it, also
+// the column sums of (X*s) .* W.  *fused tells the caller whether it happened.
+int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W, int64_t ld,
+                 void* gram_scratch, double* alpha_partial, int* grid_out, bool* fused,
+                 cudaStream_t st) {
+  *fused = false;
+  switch (op->kind) {
+    case MF_OP_CSR:
+      MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X,
+                             s, W, ld, alpha_partial, grid_out, st));
+      *fused = alpha_partial != nullptr;
+      return MF_OK;
+    case MF_OP_DENSE:
+      return launch_gemm_blocked(op->values, op->lda, false, op->n, op->n, X, s, W, ld,
+                                 op->dtype, st);
+    case MF_OP_GRAM: {
+      void* Y = gram_scratch ? gram_scratch : op->op_scratch;
+      if (Y == nullptr) {
+        set_error("gram operator needs a scratch block of m*ld elements");
+        return MF_ERR_INVALID_ARGUMENT;
+      }
+      MF_TRY(launch_gemm_blocked(op->values, op->lda, false, op->m, op->n, X, nullptr, Y, ld,
+                                 op->dtype, st));
+      return launch_gemm_blocked(op->values, op->lda, true, op->n, op->m, Y, s, W, ld,
+                                 op->dtype, st);
+    }
+  }
+  return MF_ERR_INVALID_ARGUMENT;
+}
+
+struct LanczosBufs {
+  void *R0, *R1, *W, *V;       // block vectors
+  void *inv;                   // [k+1][ld] 1/len, 1/beta_j
+  void *h, *h2;                // [k][ld] CGS coefficients
+  double* partial;             // reduction partial rows
+  void* gram;                  // m*ld
+};
+
+int32_t carve_lanczos(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, int32_t reortho,
+                      LanczosBufs* b) {
+  const int64_t es = (int64_t)dtype_size(op->dtype);
+  const int64_t blk = op->n * ld * es;
+  const int grid = reduce_grid(op->n * ld, vec_of(op->dtype, ld));
+  memset(b, 0, sizeof(*b));
+  if (reortho == MF_REORTHO_NONE) {
+    b->R0 = a.take(blk);
+    b->R1 = a.take(blk);
+    b->W = a.take(blk);
+    b->inv = a.take((k + 1) * ld * es);
+    b->partial = (double*)a.take((int64_t)grid * ld * 8);
+  } else {
+    b->V = a.take(blk);
+    b->h = a.take((k + 1) * ld * es);
+    b->h2 = a.take((k + 1) * ld * es);
+    b->partial = (double*)a.take((k + 4) * (int64_t)grid * ld * 8);
+  }
+  if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) b->gram = a.take(op->m * ld * es);
+  if (!a.dry && (b->partial == nullptr || (b->gram == nullptr && op->kind == MF_OP_GRAM &&
+                                            op->op_scratch == nullptr))) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+              (long long)a.size);
+    return MF_ERR_WORKSPACE;
+  }
+  return MF_OK;
+}
+
+inline void* row(void* base, int64_t j, int64_t ld, int32_t dtype) {
+  return (char*)base + j * ld * (int64_t)dtype_size(dtype);
+}
+
+// Three-term Lanczos on a probe block (matfree/decomp.py:220-292), lazily
+// normalised: the un-normalised residual block r_j and 1/beta_{j-1} are kept
+// and v_j = r_j / beta_{j-1} is formed on the fly by the consumers.
+//   v0_owned: V0 may be overwritten (fused estimator) -> one buffer less.
+int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, int64_t ld, int64_t k,
+                     void* alphas, void* betas, void* init_len, void* Q, void* residual,
+                     const LanczosBufs& b, cudaStream_t st) {
+  const int32_t dt = op->dtype;
+  const int64_t n = op->n;
+  const int64_t blk = n * ld * (int64_t)dtype_size(dt);
+  int grid = 0;
+  MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, b.partial, &grid, st));
+  MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, init_len, row(b.inv, 0, ld, dt), nullptr, st));
+  void* Rc = V0;
+  void* Rp = nullptr;
+  for (int64_t j = 0; j < k; ++j) {
+    void* sc = row(b.inv, j, ld, dt);
+    const void* X = Rc;
+    const void* sx = sc;
+    if (Q != nullptr) {  // materialise v_j (decomp.py:279) and read it back un-scaled
+      void* Qj = (char*)Q + j * blk;
+      MF_TRY(launch_scale(Rc, sc, Qj, 0, dt, n, ld, st));
+      X = Qj;
+      sx = nullptr;
+    }
+    bool fused = false;
+    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, b.partial, &grid, &fused, st));
+    if (!fused) MF_TRY(launch_dot(X, sx, b.W, dt, n, ld, b.partial, &grid, st));
+    void* aj = row(alphas, j, ld, dt);
+    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 0, aj, nullptr, nullptr, st));
+    // pick the output buffer: alias Rp when we own it
+    void* out;
+    if (Rp == nullptr) out = b.R0;
+    else if (Rp == V0 && !v0_owned) out = b.R1;
+    else out = Rp;
+    MF_TRY(launch_lanczos_update(b.W, Rc, sc, aj, Rp, j > 0 ? row(b.inv, j - 1, ld, dt) : nullptr,
+                                 j > 0 ? row(betas, j - 1, ld, dt) : nullptr, out, dt, n, ld,
+                                 b.partial, &grid, st));
+    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, row(betas, j, ld, dt),
+                           row(b.inv, j + 1, ld, dt), nullptr, st));
+    Rp = Rc;
+    Rc = out;
+  }
+  if (residual != nullptr) {
+    // b_{k-1} * v_k is the un-normalised r_k itself (decomp.py:167); k == 0: v_0... see below
+    if (k > 0) {
+      if (cudaMemcpyAsync(residual, Rc, blk, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("residual copy failed");
+        return MF_ERR_CUDA;
+      }
+    }
+  }
+  return MF_OK;
+}
+
+// Arnoldi with classical Gram-Schmidt applied twice (matfree/decomp.py:426-477)
+// and T = (H + H^T)/2 (decomp.py:133-135), on a probe block.
+int32_t lanczos_full(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
+                     void* alphas, void* betas, void* init_len, void* Q, void* residual,
+                     const LanczosBufs& b, cudaStream_t st) {
+  const int32_t dt = op->dtype;
+  const int64_t n = op->n;
+  const int64_t es = (int64_t)dtype_size(dt);
+  const int64_t blk = n * ld * es;
+  int grid = 0;
+  MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, b.partial, &grid, st));
+  MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, init_len, nullptr, nullptr, st));
+  const void* length = init_len;
+  for (int64_t i = 0; i < k; ++i) {
+    void* Qi = (char*)Q + i * blk;
+    MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
+    bool fused = false;
+    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, &grid, &fused, st));  // :460
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.h, st));      // :463
+    if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("alpha copy failed");
+      return MF_ERR_CUDA;
+    }
+    if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
+    MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, nullptr, st));  // :464
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.h2, st));          // :468
+    MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, b.partial, &grid, st));
+    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, row(betas, i, ld, dt), nullptr, nullptr,
+                           st));  // :471
+    length = row(betas, i, ld, dt);
+  }
+  if (residual != nullptr) {
+    const void* src = k > 0 ? b.V : V0;
+    if (cudaMemcpyAsync(residual, src, blk, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("residual copy failed");
+      return MF_ERR_CUDA;
+    }
+  }
+  return MF_OK;
+}
+
+}  // namespace
+}  // namespace mf
+
+using namespace mf;
+
+extern "C" {
+
+const char* mf_last_error(void) { return g_err; }
+int32_t mf_abi_version(void) { return MF_ABI_VERSION; }
+int64_t mf_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int32_t mf_timing_enable(int32_t on) {
+  g_timing_on.store(on != 0);
+  return MF_OK;
+}
+
+int32_t mf_timing_collect(double* h_ms, int64_t* h_launches) {
+  std::lock_guard<std::mutex> lk(g_timing.mu);
+  for (auto& r : g_timing.recs) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.end) == cudaSuccess &&
+        cudaEventElapsedTime(&ms, r.beg, r.end) == cudaSuccess) {
+      if (h_ms) h_ms[r.cls] += (double)ms;
+      if (h_launches) h_launches[r.cls] += 1;
+    } else {
+      cudaGetLastError();
+    }
+    g_timing.free_events.push_back(r.beg);
+    g_timing.free_events.push_back(r.end);
+  }
+  g_timing.recs.clear();
+  return MF_OK;
+}
+
+int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
+                     int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
+                     int32_t sampler, int32_t prng_flags, double* sqnorm_out, void* stream) {
+  if (out == nullptr || n < 0 || num_probes < 0 || p0 < 0) {
+    set_error("probe_gen: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (dtype != MF_F32 && dtype != MF_F64) {
+    set_error("probe_gen: dtype %d unsupported", dtype);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (sampler != MF_SAMPLER_SIGNS && sampler != MF_SAMPLER_NORMAL) {
+    set_error("probe_gen: sampler %d unsupported", sampler);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (sqnorm_out != nullptr) {
+    set_error("probe_gen: sqnorm_out requires the fused estimator (use mf_lanczos init_len)");
+    return MF_ERR_UNSUPPORTED;
+  }
+  return launch_probe_gen(out, dtype, layout, n, ld, p0, num_probes, key0, key1, sampler,
+                          prng_flags, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* stream) {
+  MF_TRY(validate_op(op));
+  if (!valid_ld(ld) || X == nullptr || W == nullptr) {
+    set_error("matmat: ld must be a power of two <= 256 and X, W non-null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  bool fused;
+  int grid;
+  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, &grid, &fused, (cudaStream_t)stream);
+}
+
+int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
+                        void* W, int64_t ld, void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_DENSE; op.dtype = dtype; op.n = n; op.values = A; op.lda = lda;
+  return mf_matmat(&op, X, W, ld, stream);
+}
+
+int32_t mf_matmat_csr(const int32_t* indptr, const int32_t* indices, const void* data,
+                      int64_t n, int64_t nnz, int32_t dtype, const void* X, void* W,
+                      int64_t ld, void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_CSR; op.dtype = dtype; op.n = n; op.nnz = nnz; op.values = data;
+  op.indptr = indptr; op.indices = indices;
+  return mf_matmat(&op, X, W, ld, stream);
+}
+
+int32_t mf_matmat_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
+                       const void* X, void* Y_scratch, void* W, int64_t ld, void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_GRAM; op.dtype = dtype; op.n = n; op.m = m; op.values = A; op.lda = lda;
+  op.op_scratch = Y_scratch;
+  return mf_matmat(&op, X, W, ld, stream);
+}
+
+int32_t mf_to_blocked(const void* src_pn, void* dst_blocked, int32_t dtype, int64_t n,
+                      int64_t num_probes, int64_t ld, void* stream) {
+  if (!valid_ld(ld) || num_probes > ld) {
+    set_error("to_blocked: need num_probes <= ld, ld a power of two <= 256");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_transpose(src_pn, dst_blocked, dtype, n, num_probes, ld, true,
+                          (cudaStream_t)stream);
+}
+
+int32_t mf_from_blocked(const void* src_blocked, void* dst_pn, int32_t dtype, int64_t n,
+                        int64_t num_probes, int64_t ld, void* stream) {
+  if (!valid_ld(ld) || num_probes > ld) {
+    set_error("from_blocked: need num_probes <= ld, ld a power of two <= 256");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_transpose(src_blocked, dst_pn, dtype, n, num_probes, ld, false,
+                          (cudaStream_t)stream);
+}
+
+static int32_t check_lanczos_args(const mf_operator_t* op, int64_t ld, int64_t k,
+                                  int32_t reortho) {
+  MF_TRY(validate_op(op));
+  if (!valid_ld(ld)) {
+    set_error("ld=%lld must be a power of two in [1, 256]", (long long)ld);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (k < 0 || k > op->n) {
+    // same wording as matfree/decomp.py:753-756
+    set_error("Parameter 'num_matvecs'=%lld exceeds the acceptable range. "
+              "Expected: 0 <= num_matvecs <= %lld.", (long long)k, (long long)op->n);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (reortho != MF_REORTHO_NONE && reortho != MF_REORTHO_FULL) {
+    set_error("reortho=%d unsupported", reortho);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return MF_OK;
+}
+
+int64_t mf_lanczos_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k,
+                                   int32_t reortho, int32_t want_Q) {
+  (void)want_Q;
+  if (check_lanczos_args(op, ld, k, reortho) != MF_OK) return -1;
+  Arena a(nullptr, 0, true);
+  LanczosBufs b;
+  carve_lanczos(a, op, ld, k, reortho, &b);
+  return a.used + 256;
+}
+
+int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
+                   int32_t reortho, void* alphas, void* betas, void* init_len, void* Q,
+                   void* residual, void* workspace, int64_t workspace_bytes, void* stream) {
+  MF_TRY(check_lanczos_args(op, ld, k, reortho));
+  if (V0 == nullptr || init_len == nullptr || (k > 0 && (alphas == nullptr || betas == nullptr))) {
+    set_error("lanczos: V0, init_len, alphas, betas must be non-null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (reortho == MF_REORTHO_FULL && Q == nullptr && k > 0) {
+    set_error("lanczos: reortho=full needs the basis buffer Q[k][n][ld]");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  Arena a(workspace, workspace_bytes, false);
+  LanczosBufs b;
+  MF_TRY(carve_lanczos(a, op, ld, k, reortho, &b));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (reortho == MF_REORTHO_NONE)
+    return lanczos_none(op, (void*)V0, false, ld, k, alphas, betas, init_len, Q, residual, b, st);
+  return lanczos_full(op, V0, ld, k, alphas, betas, init_len, Q, residual, b, st);
+}
+
+int64_t mf_tridiag_quad_workspace_bytes(int64_t ld, int64_t k) {
+  // d, e, first-row z : 3*k*ld doubles ; full eigenvector variant: (2 + k)*k*ld
+  return (2 + k) * k * ld * 8 + 256;
+}
+
+int32_t mf_tridiag_quad(const void* alphas, const void* betas, const void* init_len,
+                        int32_t dtype, int64_t ld, int64_t num_probes, int64_t k, int32_t fn,
+                        double fn_param, void* quad, double* nodes, double* weights,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  if (k <= 0 || ld <= 0 || num_probes > ld || alphas == nullptr || betas == nullptr) {
+    set_error("tridiag_quad: bad arguments (k=%lld ld=%lld)", (long long)k, (long long)ld);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (workspace == nullptr || workspace_bytes < 3 * k * ld * 8) {
+    set_error("tridiag_quad: workspace too small");
+    return MF_ERR_WORKSPACE;
+  }
+  return launch_tridiag_quad(alphas, betas, init_len, dtype, ld, num_probes, k, fn, fn_param,
+                             quad, nodes, weights, nullptr, (double*)workspace,
+                             (cudaStream_t)stream);
+}
+
+int32_t mf_tridiag_funm_e1(const void* alphas, const void* betas, int32_t dtype, int64_t ld,
+                           int64_t num_probes, int64_t k, int32_t fn, double fn_param,
+                           void* coeffs, void* workspace, int64_t workspace_bytes,
+                           void* stream) {
+  if (k <= 0 || ld <= 0 || num_probes > ld || !alphas || !betas || !coeffs) {
+    set_error("tridiag_funm_e1: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (workspace == nullptr || workspace_bytes < (2 + k) * k * ld * 8) {
+    set_error("tridiag_funm_e1: workspace too small");
+    return MF_ERR_WORKSPACE;
+  }
+  return launch_tridiag_quad(alphas, betas, nullptr, dtype, ld, num_probes, k, fn, fn_param,
+                             nullptr, nullptr, nullptr, coeffs, (double*)workspace,
+                             (cudaStream_t)stream);
+}
+
+int32_t mf_basis_combine(const void* Q, const void* coeffs, const void* scale, int32_t dtype,
+                         int64_t n, int64_t ld, int64_t k, void* out, void* stream) {
+  if (!valid_ld(ld) || !Q || !coeffs || !out) {
+    set_error("basis_combine: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_basis_combine(Q, coeffs, scale, dtype, n, ld, k, out, (cudaStream_t)stream);
+}
+
+int32_t mf_mc_reduce(const void* values, int32_t dtype, int64_t num, double* stats_out,
+                     void* stream) {
+  if (values == nullptr || stats_out == nullptr || num <= 0) {
+    set_error("mc_reduce: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_mc_reduce(values, dtype, num, stats_out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ fused estimator
+
+struct EstimateBufs {
+  void* Z;        // probe block
+  void* Qbasis;   // FULL only: [k][n][ld]
+  void* alphas;   // [k][ld]
+  void* betas;    // [k][ld]
+  void* len;      // [ld]
+  double* qwork;  // 3*k*ld doubles
+  LanczosBufs lb;
+};
+
+static int32_t carve_estimate(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k,
+                              int32_t reortho, int32_t integrand, EstimateBufs* e) {
+  const int64_t es = (int64_t)dtype_size(op->dtype);
+  const int64_t blk = op->n * ld * es;
+  memset(e, 0, sizeof(*e));
+  e->Z = a.take(blk);
+  if (integrand == MF_INTEGRAND_TRACE) {
+    e->lb.W = a.take(blk);
+    const int grid = reduce_grid(op->n * ld, vec_of(op->dtype, ld));
+    e->lb.partial = (double*)a.take((int64_t)grid * ld * 8);
+    if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) e->lb.gram = a.take(op->m * ld * es);
+    if (!a.dry && a.used > a.size) {
+      set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+                (long long)a.size);
+      return MF_ERR_WORKSPACE;
+    }
+    return MF_OK;
+  }
+  if (reortho == MF_REORTHO_FULL) e->Qbasis = a.take(k * blk);
+  e->alphas = a.take((k + 1) * ld * es);
+  e->betas = a.take((k + 1) * ld * es);
+  e->len = a.take(ld * es);
+  e->qwork = (double*)a.take(3 * k * ld * 8);
+  MF_TRY(carve_lanczos(a, op, ld, k, reortho, &e->lb));
+  if (!a.dry && a.used > a.size) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+              (long long)a.size);
+    return MF_ERR_WORKSPACE;
+  }
+  return MF_OK;
+}
+
+int64_t mf_estimate_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k,
+                                    int32_t reortho, int32_t integrand) {
+  if (integrand == MF_INTEGRAND_TRACE) {
+    if (validate_op(op) != MF_OK || !valid_ld(ld)) return -1;
+  } else if (check_lanczos_args(op, ld, k, reortho) != MF_OK) {
+    return -1;
+  }
+  Arena a(nullptr, 0, true);
+  EstimateBufs e;
+  carve_estimate(a, op, ld, k, reortho, integrand, &e);
+  return a.used + 256;
+}
+
+int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
+                    int32_t prng_flags, uint32_t key0, uint32_t key1, int64_t p0,
+                    int64_t num_probes, int64_t ld, int64_t k, int32_t reortho, int32_t fn,
+                    double fn_param, void* quad_out, void* alphas_out, void* betas_out,
+                    void* lens_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (integrand == MF_INTEGRAND_TRACE) {
+    MF_TRY(validate_op(op));
+    if (!valid_ld(ld)) {
+      set_error("ld=%lld must be a power of two in [1, 256]", (long long)ld);
+      return MF_ERR_INVALID_ARGUMENT;
+    }
+  } else if (integrand == MF_INTEGRAND_SLQ) {
+    MF_TRY(check_lanczos_args(op, ld, k, reortho));
+    if (k < 1) {
+      set_error("estimate: the SLQ integrand needs num_matvecs >= 1");
+      return MF_ERR_INVALID_ARGUMENT;
+    }
+  } else {
+    set_error("estimate: unknown integrand %d", integrand);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (quad_out == nullptr || num_probes <= 0 || p0 < 0) {
+    set_error("estimate: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int32_t dt = op->dtype;
+  const int64_t es = (int64_t)dtype_size(dt);
+  Arena a(workspace, workspace_bytes, false);
+  EstimateBufs e;
+  MF_TRY(carve_estimate(a, op, ld, k, reortho, integrand, &e));
+
+  int64_t tile = 0;
+  for (int64_t t0 = 0; t0 < num_probes; t0 += ld, ++tile) {
+    const int64_t np = (num_probes - t0) < ld ? (num_probes - t0) : ld;
+    MF_TRY(launch_probe_gen(e.Z, dt, MF_LAYOUT_BLOCKED, op->n, ld, p0 + t0, np, key0, key1,
+                            sampler, prng_flags, nullptr, nullptr, st));
+    void* q_tile = (char*)quad_out + t0 * es;
+    if (integrand == MF_INTEGRAND_TRACE) {
+      // v^T (A v)  (matfree/stochtrace.py:859-863)
+      bool fused = false;
+      int grid = 0;
+      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, e.lb.partial, &grid, &fused, st));
+      if (!fused) MF_TRY(launch_dot(e.Z, nullptr, e.lb.W, dt, op->n, ld, e.lb.partial, &grid, st));
+      if (np == ld) {
+        MF_TRY(launch_finalize(e.lb.partial, grid, ld, dt, 0, q_tile, nullptr, nullptr, st));
+      } else {
+        // partial tile: finalize into scratch, then copy the live columns
+        MF_TRY(launch_finalize(e.lb.partial, grid, ld, dt, 0, e.lb.W, nullptr, nullptr, st));
+        if (cudaMemcpyAsync(q_tile, e.lb.W, np * es, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+          set_error("estimate: copy failed");
+          return MF_ERR_CUDA;
+        }
+      }
+      continue;
+    }
+    if (reortho == MF_REORTHO_NONE)
+      MF_TRY(lanczos_none(op, e.Z, true, ld, k, e.alphas, e.betas, e.len, nullptr, nullptr, e.lb,
+                          st));
+    else
+      MF_TRY(lanczos_full(op, e.Z, ld, k, e.alphas, e.betas, e.len, e.Qbasis, nullptr, e.lb, st));
+    // quadrature: quad for the np live probes goes straight to the output
+    MF_TRY(launch_tridiag_quad(e.alphas, e.betas, e.len, dt, ld, np, k, fn, fn_param, q_tile,
+                               nullptr, nullptr, nullptr, e.qwork, st));
+    if (alphas_out != nullptr &&
+        cudaMemcpyAsync((char*)alphas_out + tile * k * ld * es, e.alphas, k * ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("estimate: copy failed");
+      return MF_ERR_CUDA;
+    }
+    if (betas_out != nullptr &&
+        cudaMemcpyAsync((char*)betas_out + tile * k * ld * es, e.betas, k * ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("estimate: copy failed");
+      return MF_ERR_CUDA;
+    }
+    if (lens_out != nullptr &&
+        cudaMemcpyAsync((char*)lens_out + tile * ld * es, e.len, ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("estimate: copy failed");
+      return MF_ERR_CUDA;
+    }
+  }
+  return MF_OK;
+}
+
+int32_t mf_slq_estimate_dense(const void* A, int64_t n, int64_t lda, int32_t dtype,
+                              int32_t sampler, int32_t prng_flags, uint32_t key0,
+                              uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
+                              int64_t k, int32_t reortho, int32_t fn, double fn_param,
+                              void* quad_out, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_DENSE; op.dtype = dtype; op.n = n; op.values = A; op.lda = lda;
+  return mf_estimate(&op, MF_INTEGRAND_SLQ, sampler, prng_flags, key0, key1, p0, num_probes, ld,
+                     k, reortho, fn, fn_param, quad_out, nullptr, nullptr, nullptr, workspace,
+                     workspace_bytes, stream);
+}
+
+int32_t mf_slq_estimate_csr(const int32_t* indptr, const int32_t* indices, const void* data,
+                            int64_t n, int64_t nnz, int32_t dtype, int32_t sampler,
+                            int32_t prng_flags, uint32_t key0, uint32_t key1, int64_t p0,
+                            int64_t num_probes, int64_t ld, int64_t k, int32_t reortho,
+                            int32_t fn, double fn_param, void* quad_out, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_CSR; op.dtype = dtype; op.n = n; op.nnz = nnz; op.values = data;
+  op.indptr = indptr; op.indices = indices;
+  return mf_estimate(&op, MF_INTEGRAND_SLQ, sampler, prng_flags, key0, key1, p0, num_probes, ld,
+                     k, reortho, fn, fn_param, quad_out, nullptr, nullptr, nullptr, workspace,
+                     workspace_bytes, stream);
+}
+
+int32_t mf_slq_estimate_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
+                             int32_t sampler, int32_t prng_flags, uint32_t key0,
+                             uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
+                             int64_t k, int32_t reortho, int32_t fn, double fn_param,
+                             void* quad_out, void* workspace, int64_t workspace_bytes,
+                             void* stream) {
+  mf_operator_t op{};
+  op.kind = MF_OP_GRAM; op.dtype = dtype; op.n = n; op.m = m; op.values = A; op.lda = lda;
+  return mf_estimate(&op, MF_INTEGRAND_SLQ, sampler, prng_flags, key0, key1, p0, num_probes, ld,
+                     k, reortho, fn, fn_param, quad_out, nullptr, nullptr, nullptr, workspace,
+                     workspace_bytes, stream);
+}
+
+}  // extern "C"

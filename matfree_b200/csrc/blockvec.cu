@@ -1,0 +1,475 @@
+// K3 / K4 -- HBM-bound block-vector kernels on the blocked layout X[n][ld]:
+//   * column dots, the fused Lanczos three-term update + norm
+//     (matfree/decomp.py:286-292),
+//   * classical Gram-Schmidt passes of the full re-orthogonalisation
+//     (matfree/decomp.py:462-471),
+//   * scaling / layout helpers.
+// Every kernel maps a CTA of 256 threads onto flat 16-byte chunks so that a
+// thread always owns the same probe columns; per-column sums are accumulated in
+// fp64 registers, reduced deterministically inside the CTA and written as one
+// partial row per CTA; `finalize` adds the partial rows in a fixed order.
+#include "internal.h"
+
+namespace mf {
+namespace {
+
+template <typename T, int VEC>
+__device__ __forceinline__ void load_chunk(const T* __restrict__ p, int64_t f, T (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = p[f];
+  } else {
+    vec_load<T>(p + f, v);
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void store_chunk(T* __restrict__ p, int64_t f, const T (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    p[f] = v[0];
+  } else {
+    vec_store<T>(p + f, v);
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void load_cols(const T* __restrict__ s, int ld, T (&v)[VEC], T dflt) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i)
+    v[i] = s ? s[(threadIdx.x * VEC + i) & (ld - 1)] : dflt;
+}
+
+#define MF_FLAT_LOOP(total)                                                                 \
+  for (int64_t f = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC; f < (total);         \
+       f += (int64_t)gridDim.x * kBlock * VEC)
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+dot_kernel(const T* __restrict__ X, const T* __restrict__ sx, const T* __restrict__ Y,
+           int64_t total, int ld, double* __restrict__ partial) {
+  T s[VEC];
+  load_cols<T, VEC>(sx, ld, s, T(1));
+  double acc[1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+  MF_FLAT_LOOP(total) {
+    T x[VEC], y[VEC];
+    load_chunk<T, VEC>(X, f, x);
+    load_chunk<T, VEC>(Y, f, y);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] += (double)(x[i] * s[i]) * (double)y[i];
+  }
+  cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+}
+
+template <typename T>
+__global__ void finalize_kernel(const double* __restrict__ partial, int grid, int ld, int mode,
+                                T* __restrict__ value_out, T* __restrict__ inv_out,
+                                double* __restrict__ dbl_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ld) return;
+  double s = 0.0;
+  for (int b = 0; b < grid; ++b) s += partial[(int64_t)b * ld + c];
+  if (dbl_out) dbl_out[c] = s;
+  if (mode == 0) {
+    if (value_out) value_out[c] = (T)s;
+  } else {
+    const T v = (T)sqrt(s);
+    if (value_out) value_out[c] = v;
+    if (inv_out) inv_out[c] = T(1) / v;
+  }
+}
+
+template <typename T, int VEC, bool HAS_PREV>
+__global__ void __launch_bounds__(kBlock)
+lanczos_update_kernel(const T* __restrict__ W, const T* __restrict__ Rc, const T* __restrict__ sc,
+                      const T* __restrict__ a, const T* Rp, const T* __restrict__ sp,
+                      const T* __restrict__ bprev, T* out, int64_t total, int ld,
+                      double* __restrict__ partial) {
+  T s_c[VEC], al[VEC], s_p[VEC], bp[VEC];
+  load_cols<T, VEC>(sc, ld, s_c, T(1));
+  load_cols<T, VEC>(a, ld, al, T(0));
+  if (HAS_PREV) {
+    load_cols<T, VEC>(sp, ld, s_p, T(1));
+    load_cols<T, VEC>(bprev, ld, bp, T(0));
+  }
+  double acc[1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+  MF_FLAT_LOOP(total) {
+    T w[VEC], rc[VEC], rp[VEC], r[VEC];
+    load_chunk<T, VEC>(W, f, w);
+    load_chunk<T, VEC>(Rc, f, rc);
+    if (HAS_PREV) load_chunk<T, VEC>(Rp, f, rp);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      T t = w[i] - al[i] * (rc[i] * s_c[i]);
+      if (HAS_PREV) t = t - bp[i] * (rp[i] * s_p[i]);
+      r[i] = t;
+      acc[0][i] += (double)t * (double)t;
+    }
+    store_chunk<T, VEC>(out, f, r);
+  }
+  cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+scale_kernel(const T* __restrict__ X, const T* __restrict__ s, T* __restrict__ out, int mode,
+             int64_t total, int ld) {
+  T sv[VEC];
+  load_cols<T, VEC>(s, ld, sv, T(1));
+  MF_FLAT_LOOP(total) {
+    T x[VEC];
+    load_chunk<T, VEC>(X, f, x);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) x[i] = mode == 0 ? x[i] * sv[i] : x[i] / sv[i];
+    store_chunk<T, VEC>(out, f, x);
+  }
+}
+
+// CGS dots for JB basis vectors at a time; V is re-read once per group of JB.
+template <typename T, int VEC, int JB>
+__global__ void __launch_bounds__(kBlock)
+reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
+                   const T* __restrict__ V, int64_t total, int ld, double* __restrict__ partial,
+                   int64_t partial_stride) {
+  double acc[JB][VEC];
+#pragma unroll
+  for (int j = 0; j < JB; ++j)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
+  MF_FLAT_LOOP(total) {
+    T v[VEC];
+    load_chunk<T, VEC>(V, f, v);
+#pragma unroll
+    for (int j = 0; j < JB; ++j) {
+      if (j < nj) {
+        T q[VEC];
+        load_chunk<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, f, q);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[i] * (double)v[i];
+      }
+    }
+  }
+  cta_reduce_columns<VEC, JB>(acc, ld, partial + (int64_t)j0 * partial_stride, partial_stride);
+}
+
+template <typename T>
+__global__ void finalize_multi_kernel(const double* __restrict__ partial, int64_t partial_stride,
+                                      int grid, int ld, int nq, T* __restrict__ h) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nq * ld) return;
+  const int j = idx / ld, c = idx % ld;
+  double s = 0.0;
+  const double* p = partial + (int64_t)j * partial_stride;
+  for (int b = 0; b < grid; ++b) s += p[(int64_t)b * ld + c];
+  h[(int64_t)j * ld + c] = (T)s;
+}
+
+template <typename T, int VEC, bool NORM>
+__global__ void __launch_bounds__(kBlock)
+reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ h,
+                     T* __restrict__ V, int64_t total, int ld, double* __restrict__ partial) {
+  extern __shared__ unsigned char smem_raw[];
+  T* hs = reinterpret_cast<T*>(smem_raw);  // [nq][ld]
+  for (int i = threadIdx.x; i < nq * ld; i += kBlock) hs[i] = h[i];
+  __syncthreads();
+  const int c0 = (threadIdx.x * VEC) & (ld - 1);
+  double acc[1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+  MF_FLAT_LOOP(total) {
+    T v[VEC], s[VEC];
+    load_chunk<T, VEC>(V, f, v);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = T(0);
+    int j = 0;
+    for (; j + 4 <= nq; j += 4) {
+      T q0[VEC], q1[VEC], q2[VEC], q3[VEC];
+      load_chunk<T, VEC>(Q + (int64_t)(j + 0) * q_stride, f, q0);
+      load_chunk<T, VEC>(Q + (int64_t)(j + 1) * q_stride, f, q1);
+      load_chunk<T, VEC>(Q + (int64_t)(j + 2) * q_stride, f, q2);
+      load_chunk<T, VEC>(Q + (int64_t)(j + 3) * q_stride, f, q3);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const int c = (c0 + i) & (ld - 1);
+        s[i] += q0[i] * hs[(j + 0) * ld + c];
+        s[i] += q1[i] * hs[(j + 1) * ld + c];
+        s[i] += q2[i] * hs[(j + 2) * ld + c];
+        s[i] += q3[i] * hs[(j + 3) * ld + c];
+      }
+    }
+    for (; j < nq; ++j) {
+      T q[VEC];
+      load_chunk<T, VEC>(Q + (int64_t)j * q_stride, f, q);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) s[i] += q[i] * hs[j * ld + ((c0 + i) & (ld - 1))];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      v[i] = v[i] - s[i];
+      if (NORM) acc[0][i] += (double)v[i] * (double)v[i];
+    }
+    store_chunk<T, VEC>(V, f, v);
+  }
+  if (NORM) cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+basis_combine_kernel(const T* __restrict__ Q, int64_t q_stride, int k, const T* __restrict__ coef,
+                     const T* __restrict__ scale, T* __restrict__ out, int64_t total, int ld) {
+  T sc[VEC];
+  load_cols<T, VEC>(scale, ld, sc, T(1));
+  const int c0 = (threadIdx.x * VEC) & (ld - 1);
+  MF_FLAT_LOOP(total) {
+    T s[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] = T(0);
+    for (int j = 0; j < k; ++j) {
+      T q[VEC];
+      load_chunk<T, VEC>(Q + (int64_t)j * q_stride, f, q);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) s[i] += q[i] * coef[(int64_t)j * ld + ((c0 + i) & (ld - 1))];
+    }
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) s[i] *= sc[i];
+    store_chunk<T, VEC>(out, f, s);
+  }
+}
+
+// (P, n) <-> [n][ld] through a 32x32 shared-memory tile
+template <typename T, bool TO_BLOCKED>
+__global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t n,
+                                 int64_t num_probes, int64_t ld) {
+  __shared__ T tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int64_t p0 = (int64_t)blockIdx.y * 32;
+  if (TO_BLOCKED) {
+    // read src[p][r] coalesced in r
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int64_t p = p0 + j, r = r0 + threadIdx.x;
+      tile[j][threadIdx.x] = (p < num_probes && r < n) ? src[p * n + r] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int64_t r = r0 + j, p = p0 + threadIdx.x;
+      if (r < n && p < ld) dst[r * ld + p] = tile[threadIdx.x][j];
+    }
+  } else {
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int64_t r = r0 + j, p = p0 + threadIdx.x;
+      tile[j][threadIdx.x] = (r < n && p < ld) ? src[r * ld + p] : T(0);
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int64_t p = p0 + j, r = r0 + threadIdx.x;
+      if (p < num_probes && r < n) dst[p * n + r] = tile[threadIdx.x][j];
+    }
+  }
+}
+
+// offdiag_{i-1} = (|v_{i-1}| + q_{i-1}^T A q_i) / 2   (matfree/decomp.py:133-135)
+template <typename T>
+__global__ void full_offdiag_kernel(T* __restrict__ beta_prev, const T* __restrict__ h_row,
+                                    int ld) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ld) beta_prev[c] = T(0.5) * (h_row[c] + beta_prev[c]);
+}
+
+inline int vec_for(int32_t dtype, int64_t ld) {
+  const int nv = dtype == MF_F64 ? 2 : 4;
+  return ld >= nv ? nv : 1;
+}
+
+}  // namespace
+
+#define MF_DISPATCH_TV(dtype, ld, ...)                     \
+  do {                                                     \
+    if ((dtype) == MF_F32) {                               \
+      using T = float;                                     \
+      if ((ld) >= 4) {                                     \
+        constexpr int VEC = 4;                             \
+        __VA_ARGS__;                                            \
+      } else {                                             \
+        constexpr int VEC = 1;                             \
+        __VA_ARGS__;                                            \
+      }                                                    \
+    } else {                                               \
+      using T = double;                                    \
+      if ((ld) >= 2) {                                     \
+        constexpr int VEC = 2;                             \
+        __VA_ARGS__;                                            \
+      } else {                                             \
+        constexpr int VEC = 1;                             \
+        __VA_ARGS__;                                            \
+      }                                                    \
+    }                                                      \
+  } while (0)
+
+int32_t launch_dot(const void* X, const void* sx, const void* Y, int32_t dtype, int64_t n,
+                   int64_t ld, double* partial, int* grid_out, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_DOT, st);
+  const int64_t total = n * ld;
+  const int grid = reduce_grid(total, vec_for(dtype, ld));
+  MF_DISPATCH_TV(dtype, ld, (dot_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
+                                (const T*)X, (const T*)sx, (const T*)Y, total, (int)ld, partial)));
+  *grid_out = grid;
+  return check_launch("dot");
+}
+
+int32_t launch_finalize(const double* partial, int grid, int64_t ld, int32_t dtype, int mode,
+                        void* value_out, void* inv_out, double* dbl_out, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_FINALIZE, st);
+  const int threads = 128;
+  const int blocks = (int)((ld + threads - 1) / threads);
+  if (dtype == MF_F32)
+    finalize_kernel<float><<<blocks, threads, 0, st>>>(partial, grid, (int)ld, mode,
+                                                       (float*)value_out, (float*)inv_out, dbl_out);
+  else
+    finalize_kernel<double><<<blocks, threads, 0, st>>>(
+        partial, grid, (int)ld, mode, (double*)value_out, (double*)inv_out, dbl_out);
+  return check_launch("finalize");
+}
+
+int32_t launch_lanczos_update(const void* W, const void* Rc, const void* sc, const void* a,
+                              const void* Rp, const void* sp, const void* bprev, void* out,
+                              int32_t dtype, int64_t n, int64_t ld, double* partial,
+                              int* grid_out, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_LANCZOS_UPDATE, st);
+  const int64_t total = n * ld;
+  const int grid = reduce_grid(total, vec_for(dtype, ld));
+  if (Rp != nullptr) {
+    MF_DISPATCH_TV(dtype, ld,
+                   (lanczos_update_kernel<T, VEC, true><<<grid, kBlock, 0, st>>>(
+                       (const T*)W, (const T*)Rc, (const T*)sc, (const T*)a, (const T*)Rp,
+                       (const T*)sp, (const T*)bprev, (T*)out, total, (int)ld, partial)));
+  } else {
+    MF_DISPATCH_TV(dtype, ld,
+                   (lanczos_update_kernel<T, VEC, false><<<grid, kBlock, 0, st>>>(
+                       (const T*)W, (const T*)Rc, (const T*)sc, (const T*)a, nullptr, nullptr,
+                       nullptr, (T*)out, total, (int)ld, partial)));
+  }
+  *grid_out = grid;
+  return check_launch("lanczos_update");
+}
+
+int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t dtype,
+                     int64_t n, int64_t ld, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_SCALE, st);
+  const int64_t total = n * ld;
+  const int vec = vec_for(dtype, ld);
+  int64_t want = (total + (int64_t)kBlock * vec - 1) / ((int64_t)kBlock * vec);
+  int64_t cap = (int64_t)num_sms() * 8;
+  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  MF_DISPATCH_TV(dtype, ld, (scale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
+                                (const T*)X, (const T*)s, (T*)out, mode, total, (int)ld)));
+  return check_launch("scale");
+}
+
+int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
+                           int64_t ld, double* partial, void* h_out, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_REORTH_DOTS, st);
+  const int64_t total = n * ld;
+  const int grid = reduce_grid(total, vec_for(dtype, ld));
+  const int64_t pstride = (int64_t)grid * ld;
+  constexpr int JB = 4;
+  for (int64_t j0 = 0; j0 < nq; j0 += JB) {
+    const int nj = (int)((nq - j0) < JB ? (nq - j0) : JB);
+    MF_DISPATCH_TV(dtype, ld,
+                   (reorth_dots_kernel<T, VEC, JB><<<grid, kBlock, 0, st>>>(
+                       (const T*)Q, total, (int)j0, nj, (const T*)V, total, (int)ld, partial,
+                       pstride)));
+    MF_TRY(check_launch("reorth_dots"));
+  }
+  // the kernel writes JB rows per launch; rows >= nq of the last group hold zeros
+  const int threads = 128;
+  const int blocks = (int)((nq * ld + threads - 1) / threads);
+  if (dtype == MF_F32)
+    finalize_multi_kernel<float><<<blocks, threads, 0, st>>>(partial, pstride, grid, (int)ld,
+                                                             (int)nq, (float*)h_out);
+  else
+    finalize_multi_kernel<double><<<blocks, threads, 0, st>>>(partial, pstride, grid, (int)ld,
+                                                              (int)nq, (double*)h_out);
+  return check_launch("reorth_dots_finalize");
+}
+
+int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
+                             int64_t n, int64_t ld, double* partial, int* grid_out,
+                             cudaStream_t st) {
+  MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
+  const int64_t total = n * ld;
+  const int grid = reduce_grid(total, vec_for(dtype, ld));
+  const size_t smem = (size_t)nq * ld * dtype_size(dtype);
+  if (smem > 200 * 1024) {
+    set_error("reorth_update: %lld basis vectors x %lld probes exceed the shared-memory budget; "
+              "use a narrower tile", (long long)nq, (long long)ld);
+    return MF_ERR_UNSUPPORTED;
+  }
+#define MF_RU(NORM)                                                                           \
+  MF_DISPATCH_TV(dtype, ld, {                                                                 \
+    auto kern = reorth_update_kernel<T, VEC, NORM>;                                           \
+    if (smem > 48 * 1024)                                                                     \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    kern<<<grid, kBlock, smem, st>>>((const T*)Q, total, (int)nq, (const T*)h, (T*)V, total,  \
+                                     (int)ld, partial);                                       \
+  })
+  if (partial != nullptr) {
+    MF_RU(true);
+  } else {
+    MF_RU(false);
+  }
+#undef MF_RU
+  if (grid_out) *grid_out = grid;
+  return check_launch("reorth_update");
+}
+
+int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scale,
+                             int32_t dtype, int64_t n, int64_t ld, int64_t k, void* out,
+                             cudaStream_t st) {
+  MF_KSCOPE(MF_KC_OTHER, st);
+  const int64_t total = n * ld;
+  const int grid = reduce_grid(total, vec_for(dtype, ld));
+  MF_DISPATCH_TV(dtype, ld, (basis_combine_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
+                                (const T*)Q, total, (int)k, (const T*)coeffs, (const T*)scale,
+                                (T*)out, total, (int)ld)));
+  return check_launch("basis_combine");
+}
+
+int32_t launch_transpose(const void* src, void* dst, int32_t dtype, int64_t n,
+                         int64_t num_probes, int64_t ld, bool to_blocked, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_OTHER, st);
+  if (n <= 0) return MF_OK;
+  dim3 block(32, 8);
+  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((ld + 31) / 32));
+  if (dtype == MF_F32) {
+    if (to_blocked)
+      transpose_kernel<float, true><<<grid, block, 0, st>>>((const float*)src, (float*)dst, n,
+                                                            num_probes, ld);
+    else
+      transpose_kernel<float, false><<<grid, block, 0, st>>>((const float*)src, (float*)dst, n,
+                                                             num_probes, ld);
+  } else {
+    if (to_blocked)
+      transpose_kernel<double, true><<<grid, block, 0, st>>>((const double*)src, (double*)dst, n,
+                                                             num_probes, ld);
+    else
+      transpose_kernel<double, false><<<grid, block, 0, st>>>((const double*)src, (double*)dst, n,
+                                                              num_probes, ld);
+  }
+  return check_launch("transpose");
+}
+
+int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dtype, int64_t ld,
+                            cudaStream_t st) {
+  MF_KSCOPE(MF_KC_OTHER, st);
+  const int threads = 128;
+  const int blocks = (int)((ld + threads - 1) / threads);
+  if (dtype == MF_F32)
+    full_offdiag_kernel<float><<<blocks, threads, 0, st>>>((float*)betas_prev_row,
+                                                           (const float*)h_row, (int)ld);
+  else
+    full_offdiag_kernel<double><<<blocks, threads, 0, st>>>((double*)betas_prev_row,
+                                                            (const double*)h_row, (int)ld);
+  return check_launch("full_offdiag");
+}
+
+}  // namespace mf

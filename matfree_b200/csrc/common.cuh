@@ -1,0 +1,137 @@
+// Internal helpers shared by all translation units of libmatfree_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "../../include/matfree_b200.h"
+
+namespace mf {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+inline int32_t check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return MF_ERR_CUDA;
+  }
+  return MF_OK;
+}
+
+// Optional per-launch timing (mf_timing_enable): brackets a launcher's kernels
+// with CUDA events on the launching stream.  Off by default; costs nothing then.
+struct KernelScope {
+  int cls;
+  cudaStream_t st;
+  int slot;
+  KernelScope(int cls_, cudaStream_t st_);
+  ~KernelScope();
+};
+#define MF_KSCOPE(cls, st) ::mf::KernelScope _mf_kscope((cls), (st))
+
+#define MF_TRY(expr)                     \
+  do {                                   \
+    int32_t _mf_rc = (expr);             \
+    if (_mf_rc != MF_OK) return _mf_rc;  \
+  } while (0)
+
+inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+inline bool valid_ld(int64_t ld) { return is_pow2(ld) && ld <= 256; }
+inline size_t dtype_size(int32_t dtype) { return dtype == MF_F64 ? 8 : 4; }
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+int num_sms();
+
+// ---------------------------------------------------------------- device helpers
+constexpr int kBlock = 256;          // threads per CTA of all block-vector kernels
+constexpr int kMaxPartialCtas = 2048;  // upper bound on the grid of reducing kernels
+
+template <typename T>
+struct Vec;  // 16-byte vector of T
+template <>
+struct Vec<float> {
+  using type = float4;
+  static constexpr int N = 4;
+};
+template <>
+struct Vec<double> {
+  using type = double2;
+  static constexpr int N = 2;
+};
+
+template <typename T>
+__device__ __forceinline__ void vec_load(const T* p, T (&v)[Vec<T>::N]) {
+  using V = typename Vec<T>::type;
+  V t = *reinterpret_cast<const V*>(p);
+  const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+  for (int i = 0; i < Vec<T>::N; ++i) v[i] = e[i];
+}
+template <typename T>
+__device__ __forceinline__ void vec_load_nc(const T* p, T (&v)[Vec<T>::N]) {
+  using V = typename Vec<T>::type;
+  V t = __ldg(reinterpret_cast<const V*>(p));
+  const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+  for (int i = 0; i < Vec<T>::N; ++i) v[i] = e[i];
+}
+template <typename T>
+__device__ __forceinline__ void vec_store(T* p, const T (&v)[Vec<T>::N]) {
+  using V = typename Vec<T>::type;
+  V t;
+  T* e = reinterpret_cast<T*>(&t);
+#pragma unroll
+  for (int i = 0; i < Vec<T>::N; ++i) e[i] = v[i];
+  *reinterpret_cast<V*>(p) = t;
+}
+
+// Geometry of the flat mapping of a CTA onto a blocked vector X[n][ld]:
+// with VEC elements per thread, the CTA covers `rows_per_sweep` rows per sweep
+// and a thread always sees the same VEC columns.
+template <int VEC>
+struct Geo {
+  int ld;
+  int col0;            // first column of this thread
+  int row_in_sweep;    // row offset of this thread inside a sweep
+  int rows_per_sweep;  // kBlock * VEC / ld
+  __device__ __forceinline__ explicit Geo(int ld_) : ld(ld_) {
+    int e = threadIdx.x * VEC;
+    col0 = e % ld;
+    row_in_sweep = e / ld;
+    rows_per_sweep = kBlock * VEC / ld;
+  }
+};
+
+// Deterministic CTA-level reduction of per-thread column accumulators.
+// acc[VEC] of thread t belongs to columns col0..col0+VEC-1; threads with equal
+// col0 are summed in increasing thread order.  Result is written to
+// partial[blockIdx.x * ld + col].
+template <int VEC, int NACC = 1>
+__device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int ld,
+                                                   double* __restrict__ partial,
+                                                   int64_t partial_stride) {
+  __shared__ double sh[NACC][kBlock * VEC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sh[a][threadIdx.x * VEC + i] = acc[a][i];
+  __syncthreads();
+  // flat element index e = t*VEC+i maps to column e % ld
+  for (int idx = threadIdx.x; idx < NACC * ld; idx += kBlock) {
+    int a = idx / ld, c = idx % ld;
+    double s = 0.0;
+    for (int e = c; e < kBlock * VEC; e += ld) s += sh[a][e];
+    partial[a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
+  }
+  __syncthreads();
+}
+
+}  // namespace mf

@@ -1,0 +1,247 @@
+"""Matrix functions via Lanczos on the GPU -- mirrors the SLQ part of `matfree/funm.py`.
+
+* `monte_carlo_funm_sym_logdet(tridiag_sym)` / `monte_carlo_funm_sym(dense_funm,
+  tridiag_sym)` (`funm.py:186-243`) -- integrands for
+  `stochtrace.estimator_monte_carlo`; also exported under the names
+  `integrand_funm_sym_logdet` / `integrand_funm_sym`.
+* `dense_funm_sym_eigh(matfun)` (`funm.py:322-335`).
+* `funm_lanczos_sym(dense_funm, tridiag_sym)` (`funm.py:114-147`).
+
+The quadrature ``|v|^2 e1^T f(T) e1`` is computed by `mf_tridiag_quad` (implicit
+QL on the tridiagonal, first eigenvector row only).  Recognised `matfun`s (log,
+exp, sqrt, sin, reciprocal, identity, powers) are fused into that kernel; any
+other elementwise callable is applied on the device to the `(P, k)` array of
+Ritz values the kernel returns (Gauss nodes / weights), which is mathematically
+the same contraction.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from matfree_b200 import _device, _lib, decomp, ops
+
+
+def _known_fn(matfun):
+    """Map a callable / name to (fn_id, param) of the fused kernel, or None."""
+    if isinstance(matfun, str):
+        table = {"log": (_lib.MF_FN_LOG, 0.0), "exp": (_lib.MF_FN_EXP, 1.0),
+                 "sqrt": (_lib.MF_FN_SQRT, 0.0), "inv": (_lib.MF_FN_INV, 0.0),
+                 "identity": (_lib.MF_FN_IDENTITY, 0.0), "sin": (_lib.MF_FN_SIN, 1.0)}
+        if matfun not in table:
+            raise ValueError(f"unknown matrix function {matfun!r}")
+        return table[matfun]
+    if isinstance(matfun, tuple) and len(matfun) == 2 and isinstance(matfun[0], str):
+        name, param = matfun
+        ids = {"exp": _lib.MF_FN_EXP, "pow": _lib.MF_FN_POW, "sin": _lib.MF_FN_SIN}
+        if name not in ids:
+            raise ValueError(f"unknown parametrised matrix function {name!r}")
+        return ids[name], float(param)
+    known = {np.log: (_lib.MF_FN_LOG, 0.0), math.log: (_lib.MF_FN_LOG, 0.0),
+             np.exp: (_lib.MF_FN_EXP, 1.0), math.exp: (_lib.MF_FN_EXP, 1.0),
+             np.sqrt: (_lib.MF_FN_SQRT, 0.0), math.sqrt: (_lib.MF_FN_SQRT, 0.0),
+             np.sin: (_lib.MF_FN_SIN, 1.0), math.sin: (_lib.MF_FN_SIN, 1.0),
+             np.reciprocal: (_lib.MF_FN_INV, 0.0)}
+    try:
+        import torch
+
+        known.update({torch.log: (_lib.MF_FN_LOG, 0.0), torch.exp: (_lib.MF_FN_EXP, 1.0),
+                      torch.sqrt: (_lib.MF_FN_SQRT, 0.0), torch.sin: (_lib.MF_FN_SIN, 1.0),
+                      torch.reciprocal: (_lib.MF_FN_INV, 0.0)})
+    except Exception:  # pragma: no cover
+        pass
+    try:
+        return known.get(matfun)
+    except TypeError:  # unhashable callable
+        return None
+
+
+def dense_funm_sym_eigh(matfun):
+    """Dense matrix function via a symmetric eigendecomposition (`funm.py:322-335`).
+
+    The returned callable works on a dense symmetric device matrix.  It also
+    records `matfun` so the SLQ integrand can fuse it into the quadrature kernel.
+    """
+
+    def fun(dense_matrix):
+        import torch
+
+        M = _device.as_device(dense_matrix)
+        eigvals, eigvecs = torch.linalg.eigh(M)
+        fx = _apply_matfun(matfun, eigvals)
+        return eigvecs @ torch.diag(fx) @ eigvecs.T
+
+    fun._mf_matfun = matfun
+    return fun
+
+
+def _apply_matfun(matfun, x):
+    """Apply an elementwise `matfun` to a device tensor."""
+    import torch
+
+    known = _known_fn(matfun) if not callable(matfun) or _is_hashable(matfun) else None
+    if known is not None:
+        fn, param = known
+        return {
+            _lib.MF_FN_LOG: lambda t: torch.log(t),
+            _lib.MF_FN_EXP: lambda t: torch.exp(param * t),
+            _lib.MF_FN_INV: lambda t: 1.0 / t,
+            _lib.MF_FN_SQRT: lambda t: torch.sqrt(t),
+            _lib.MF_FN_POW: lambda t: t ** param,
+            _lib.MF_FN_IDENTITY: lambda t: t,
+            _lib.MF_FN_SIN: lambda t: torch.sin(param * t),
+        }[fn](x)
+    try:
+        out = matfun(x)
+        if isinstance(out, torch.Tensor):
+            return out
+    except Exception:
+        pass
+    return torch.as_tensor(np.asarray(matfun(x.detach().cpu().numpy())), device=x.device).to(x.dtype)
+
+
+def _is_hashable(obj):
+    try:
+        hash(obj)
+        return True
+    except TypeError:
+        return False
+
+
+def quadrature_blocked(alphas, betas, init_len, num_probes, matfun):
+    """``init_len^2 * e1^T f(T) e1`` for every probe of a tile -> tensor ``[num_probes]``."""
+    import torch
+
+    lib = _lib.load()
+    k, ld = alphas.shape
+    dt = alphas.dtype
+    dev = alphas.device
+    ws = _device.workspace(lib.mf_tridiag_quad_workspace_bytes(ld, k))
+    known = _known_fn(matfun) if (not callable(matfun) or _is_hashable(matfun)) else None
+    quad = torch.empty((ld,), dtype=dt, device=dev)
+    if known is not None:
+        fn, param = known
+        _lib.check(lib.mf_tridiag_quad(alphas.data_ptr(), betas.data_ptr(), init_len.data_ptr(),
+                                       _device.mf_dtype(dt), ld, num_probes, k, fn, param,
+                                       quad.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                       _device.stream()))
+        return quad[:num_probes]
+    nodes = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    weights = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    _lib.check(lib.mf_tridiag_quad(alphas.data_ptr(), betas.data_ptr(), init_len.data_ptr(),
+                                   _device.mf_dtype(dt), ld, num_probes, k, _lib.MF_FN_NONE, 0.0,
+                                   None, nodes.data_ptr(), weights.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _device.stream()))
+    fx = _apply_matfun(matfun, nodes[:, :num_probes].to(dt)).to(torch.float64)
+    q = (fx * weights[:, :num_probes]).sum(dim=0) * init_len[:num_probes].to(torch.float64) ** 2
+    return q.to(dt)
+
+
+def ritz_blocked(alphas, betas, num_probes):
+    """Gauss nodes (Ritz values, ascending) and weights, fp64 ``[k][num_probes]``."""
+    import torch
+
+    lib = _lib.load()
+    k, ld = alphas.shape
+    dev = alphas.device
+    ws = _device.workspace(lib.mf_tridiag_quad_workspace_bytes(ld, k))
+    nodes = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    weights = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    _lib.check(lib.mf_tridiag_quad(alphas.data_ptr(), betas.data_ptr(), None,
+                                   _device.mf_dtype(alphas.dtype), ld, num_probes, k,
+                                   _lib.MF_FN_NONE, 0.0, None, nodes.data_ptr(), weights.data_ptr(),
+                                   ws.data_ptr(), ws.numel(), _device.stream()))
+    return nodes[:, :num_probes], weights[:, :num_probes]
+
+
+def monte_carlo_funm_sym(dense_funm, tridiag_sym, /):
+    """Integrand for matrix-function-trace estimation (`funm.py:205-243`)."""
+    spec = getattr(tridiag_sym, "_mf_spec", None)
+    matfun = getattr(dense_funm, "_mf_matfun", None)
+
+    def quadform(matvec, v0, *parameters):
+        if spec is None or matfun is None:
+            return _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters)
+        if parameters:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        op = ops.require_operator(matvec, "monte_carlo_funm_sym")
+        v = _device.as_device(v0, op.dtype).reshape(-1)
+        k = spec["num_matvecs"]
+        if k < 0 or k > v.shape[0]:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=v.shape[0], minval=0))
+        alphas, betas, init_len, _, _ = decomp.lanczos_blocked(
+            op, v.reshape(-1, 1), k, spec["reortho"], want_Q=False, want_residual=False)
+        return quadrature_blocked(alphas, betas, init_len, 1, matfun)[0]
+
+    quadform._mf_integrand = None if (spec is None or matfun is None) else {
+        "kind": "slq", "num_matvecs": spec["num_matvecs"], "reortho": spec["reortho"],
+        "matfun": matfun}
+    return quadform
+
+
+def _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters):
+    # funm.py:226-241 with user-supplied pieces (device tensors)
+    import torch
+
+    v0 = _device.as_device(v0).reshape(-1)
+    length = torch.linalg.vector_norm(v0)
+    _, dense, *_ = tridiag_sym(matvec, v0 / length, *parameters)
+    fA = dense_funm(dense)
+    return length**2 * fA[0, 0]
+
+
+def monte_carlo_funm_sym_logdet(tridiag_sym, /):
+    """Integrand for the log-determinant (`funm.py:186-202`)."""
+    return monte_carlo_funm_sym(dense_funm_sym_eigh(np.log), tridiag_sym)
+
+
+# BASELINE.json's north_star spells these `integrand_funm_sym[_logdet]`
+integrand_funm_sym = monte_carlo_funm_sym
+integrand_funm_sym_logdet = monte_carlo_funm_sym_logdet
+
+
+def funm_lanczos_sym(dense_funm, tridiag_sym, /):
+    """Matrix-function-vector product ``f(A) v`` via Lanczos (`funm.py:114-147`)."""
+    spec = getattr(tridiag_sym, "_mf_spec", None)
+    matfun = getattr(dense_funm, "_mf_matfun", None)
+
+    def estimate(matvec, vec, *parameters):
+        import torch
+
+        if parameters:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        if spec is None:
+            raise TypeError("funm_lanczos_sym: tridiag_sym must come from matfree_b200.decomp.tridiag_sym")
+        op = ops.require_operator(matvec, "funm_lanczos_sym")
+        lib = _lib.load()
+        v = _device.as_device(vec, op.dtype).reshape(-1)
+        n = v.shape[0]
+        k = spec["num_matvecs"]
+        if k < 0 or k > n:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=n, minval=0))
+        alphas, betas, init_len, Q, _ = decomp.lanczos_blocked(
+            op, v.reshape(n, 1), k, spec["reortho"], want_Q=True, want_residual=False)
+        known = None
+        if matfun is not None and (not callable(matfun) or _is_hashable(matfun)):
+            known = _known_fn(matfun)
+        ld = 1
+        if known is not None:
+            coeffs = torch.empty((k, ld), dtype=op.dtype, device=v.device)
+            ws = _device.workspace(lib.mf_tridiag_quad_workspace_bytes(ld, k))
+            _lib.check(lib.mf_tridiag_funm_e1(alphas.data_ptr(), betas.data_ptr(),
+                                              _device.mf_dtype(op.dtype), ld, 1, k, known[0],
+                                              known[1], coeffs.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _device.stream()))
+        else:
+            T = decomp._todense_tridiag_sym(alphas[:, 0], betas[: k - 1, 0])
+            coeffs = dense_funm(T)[:, 0].reshape(k, 1).contiguous()
+        out = torch.empty((n, ld), dtype=op.dtype, device=v.device)
+        _lib.check(lib.mf_basis_combine(Q.data_ptr(), coeffs.data_ptr(), init_len.data_ptr(),
+                                        _device.mf_dtype(op.dtype), n, ld, k, out.data_ptr(),
+                                        _device.stream()))
+        return out[:, 0]
+
+    return estimate

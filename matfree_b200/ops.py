@@ -1,0 +1,176 @@
+"""Registered matvec operators: dense, CSR, Gram.
+
+The reference takes any JAX-traceable callable ``matvec(v, *params) -> Av``
+(`matfree/stochtrace.py:47-49`, `matfree/funm.py:231-235`,
+`matfree/decomp.py:163-164`).  The operators below keep that callable
+signature -- ``op(v)`` returns ``A @ v`` for a flat device vector -- and
+additionally carry their device buffers, so `decomp`, `funm` and `stochtrace`
+can hand the whole probe block to the fused CUDA kernels
+(`mf_matmat_*`, `mf_lanczos`, `mf_estimate` in `include/matfree_b200.h`).
+A callable that is not one of these raises in the fused entry points: there is
+no CPU (or generic-callable) fallback for the Lanczos kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from matfree_b200 import _device, _lib
+
+
+class Operator:
+    """Base class of the registered operators (callable: ``op(v, *params)``)."""
+
+    kind: int
+    n: int
+    dtype = None  # torch dtype
+
+    def _struct(self, scratch=None) -> _lib.MfOperator:
+        raise NotImplementedError
+
+    @property
+    def shape(self):
+        return (self.n, self.n)
+
+    def _scratch_elems(self, ld: int) -> int:
+        return 0
+
+    # -- the reference's callable signature
+    def __call__(self, v, *params):
+        if params:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        v = _device.as_device(v, self.dtype)
+        if v.ndim != 1 or v.shape[0] != self.n:
+            raise ValueError(f"expected a flat vector of length {self.n}, got shape {tuple(v.shape)}")
+        return self.matmat_blocked(v.reshape(self.n, 1)).reshape(self.n)
+
+    def matmat_blocked(self, X):
+        """``A @ X`` for a blocked device array ``X[n][ld]`` (ld a power of two <= 256)."""
+        import torch
+
+        lib = _lib.load()
+        n, ld = X.shape
+        assert n == self.n and X.is_contiguous() and X.dtype == self.dtype
+        W = torch.empty_like(X)
+        scratch = None
+        if self._scratch_elems(ld):
+            scratch = torch.empty(self._scratch_elems(ld), dtype=self.dtype, device=X.device)
+        st = self._struct(scratch)
+        _lib.check(lib.mf_matmat(ctypes.byref(st), X.data_ptr(), W.data_ptr(), ld, _device.stream()))
+        return W
+
+    def matmat(self, V):
+        """``V @ A^T`` for probe-major ``V (P, n)``; returns ``(P, n)`` (any P)."""
+        import torch
+
+        lib = _lib.load()
+        V = _device.as_device(V, self.dtype)
+        P, n = V.shape
+        out = torch.empty_like(V)
+        ld = _device.ld_for(P)
+        Xb = torch.empty((n, ld), dtype=self.dtype, device=V.device)
+        mfdt = _device.mf_dtype(self.dtype)
+        for p0 in range(0, P, ld):
+            npb = min(ld, P - p0)
+            _lib.check(lib.mf_to_blocked(V[p0:p0 + npb].data_ptr(), Xb.data_ptr(), mfdt, n, npb, ld,
+                                         _device.stream()))
+            Wb = self.matmat_blocked(Xb)
+            _lib.check(lib.mf_from_blocked(Wb.data_ptr(), out[p0:p0 + npb].data_ptr(), mfdt, n, npb,
+                                           ld, _device.stream()))
+        return out
+
+
+class DenseOperator(Operator):
+    kind = _lib.MF_OP_DENSE
+
+    def __init__(self, A):
+        A = _device.as_device(A)
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("ops.dense expects a square matrix")
+        self.dtype = _device.torch_dtype(A.dtype)
+        self.A = A
+        self.n = int(A.shape[0])
+
+    def _struct(self, scratch=None):
+        return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
+                               nnz=0, values=self.A.data_ptr(), indptr=None, indices=None,
+                               lda=self.n, op_scratch=None)
+
+
+class CsrOperator(Operator):
+    kind = _lib.MF_OP_CSR
+
+    def __init__(self, indptr, indices, data, n=None):
+        import torch
+
+        self.data = _device.as_device(data)
+        self.dtype = _device.torch_dtype(self.data.dtype)
+        self.indptr = _device.as_device(indptr, torch.int32)
+        self.indices = _device.as_device(indices, torch.int32)
+        self.n = int(self.indptr.shape[0] - 1) if n is None else int(n)
+        if self.indptr.shape[0] != self.n + 1:
+            raise ValueError("ops.csr: indptr must have n + 1 entries")
+        self.nnz = int(self.data.shape[0])
+        if self.indices.shape[0] != self.nnz:
+            raise ValueError("ops.csr: indices and data must have the same length")
+
+    def _struct(self, scratch=None):
+        return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
+                               nnz=self.nnz, values=self.data.data_ptr(),
+                               indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
+                               lda=0, op_scratch=None)
+
+
+class GramOperator(Operator):
+    """``v -> A^T (A v)`` for a rectangular ``A (m, n)`` (tutorial 1's operator)."""
+
+    kind = _lib.MF_OP_GRAM
+
+    def __init__(self, A):
+        A = _device.as_device(A)
+        if A.ndim != 2:
+            raise ValueError("ops.gram expects a matrix")
+        self.dtype = _device.torch_dtype(A.dtype)
+        self.A = A
+        self.m, self.n = int(A.shape[0]), int(A.shape[1])
+
+    def _scratch_elems(self, ld):
+        return self.m * ld
+
+    def _struct(self, scratch=None):
+        return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.m,
+                               nnz=0, values=self.A.data_ptr(), indptr=None, indices=None,
+                               lda=self.n, op_scratch=None if scratch is None else scratch.data_ptr())
+
+
+def dense(A) -> DenseOperator:
+    """Symmetric dense operator ``v -> A @ v``."""
+    return DenseOperator(A)
+
+
+def csr(indptr, indices, data, n=None) -> CsrOperator:
+    """CSR operator (int32 ``indptr``/``indices``)."""
+    return CsrOperator(indptr, indices, data, n)
+
+
+def csr_from_scipy(mat, dtype=None) -> CsrOperator:
+    mat = mat.tocsr()
+    data = mat.data if dtype is None else mat.data.astype(dtype)
+    return CsrOperator(mat.indptr.astype(np.int32), mat.indices.astype(np.int32), data, mat.shape[0])
+
+
+def gram(A) -> GramOperator:
+    """Gram operator ``v -> A^T (A v)``."""
+    return GramOperator(A)
+
+
+def require_operator(matvec, who: str) -> Operator:
+    if not isinstance(matvec, Operator):
+        raise TypeError(
+            f"{who}: matvec must be a registered operator (matfree_b200.ops.dense / csr / gram); "
+            f"got {type(matvec).__name__}. The Lanczos kernels run on the GPU and have no "
+            "generic-callable or CPU fallback."
+        )
+    return matvec

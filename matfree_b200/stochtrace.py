@@ -1,0 +1,252 @@
+"""Stochastic trace estimation on the GPU -- mirrors the Monte-Carlo part of
+`matfree/stochtrace.py`.
+
+* `sampler_signs(*args_like, num=)`, `sampler_normal(*args_like, num=)`
+  (`stochtrace.py:927-937,957-977`): the returned ``sample(key)`` gives the
+  ``(num, n)`` device array `jax.random.rademacher` / `normal` would produce for
+  that key (bit-exact Rademacher; Threefry-2x32, partitionable counters).
+* `monte_carlo_trace()` (`stochtrace.py:853-865`).
+* `estimator_monte_carlo(integrand, sampler)` and `_mean_and_sem`
+  (`stochtrace.py:7-52,55-89`).
+
+When the integrand is one of this package's (SLQ or Hutchinson trace), the
+sampler is one of this package's and the matvec is a registered operator,
+``estimate(matvec, key)`` runs the fused `mf_estimate` kernel chain: probes are
+generated tile by tile directly in the blocked layout and never materialised as
+a ``(num, n)`` array -- which is what makes 8192 probes of a 16.7M-row operator
+possible at all (the reference would need 550 GB for the samples alone).
+
+Multi-GPU: inside `probe_sharding(group)` every rank evaluates its contiguous
+slice of the probe range (the counter-based PRNG makes the slices of the
+single-device sample array bit-identical), the per-probe values are
+all-gathered over NCCL and every rank performs the same reduction.
+"""
+
+from __future__ import annotations
+
+import contextlib
+import ctypes
+
+import numpy as np
+
+from matfree_b200 import _device, _lib, _sharding, funm as _funm, ops
+
+_PROBE_GROUP = {"group": None, "enabled": False}
+
+
+@contextlib.contextmanager
+def probe_sharding(group=None):
+    """Shard the probes of every fused `estimate` call across `group` (default: WORLD)."""
+    old = dict(_PROBE_GROUP)
+    _PROBE_GROUP.update(group=group, enabled=True)
+    try:
+        yield
+    finally:
+        _PROBE_GROUP.update(old)
+
+
+def _flat_like(*args_like):
+    """Length and dtype of the flattened `args_like` (a flat array, or a simple pytree)."""
+    leaves = []
+
+    def visit(x):
+        if isinstance(x, dict):
+            for key in sorted(x):
+                visit(x[key])
+        elif isinstance(x, (list, tuple)):
+            for y in x:
+                visit(y)
+        else:
+            leaves.append(x)
+
+    visit(args_like[0] if len(args_like) == 1 else list(args_like))
+    n = 0
+    is64 = False
+    for leaf in leaves:
+        shape = tuple(getattr(leaf, "shape", np.shape(leaf)))
+        n += int(np.prod(shape)) if shape else 1
+        dt = str(getattr(leaf, "dtype", np.asarray(leaf).dtype))
+        is64 = is64 or dt.endswith("float64")
+    import torch
+
+    return n, (torch.float64 if is64 else torch.float32)
+
+
+def _make_sampler(kind: int, args_like, num: int):
+    n, dtype = _flat_like(*args_like)
+    num = int(num)
+
+    def sample(key):
+        import torch
+
+        lib = _lib.load()
+        out = torch.empty((num, n), dtype=dtype, device=_device.device())
+        _lib.check(lib.mf_probe_gen(out.data_ptr(), _device.mf_dtype(dtype),
+                                    _lib.MF_LAYOUT_PROBE_MAJOR, n, n, 0, num, int(key[0]),
+                                    int(key[1]), kind, 0, None, _device.stream()))
+        return out
+
+    sample._mf_sampler = {"kind": kind, "n": n, "num": num, "dtype": dtype}
+    return sample
+
+
+def sampler_normal(*args_like, num):
+    """Sample from a standard-normal distribution (`stochtrace.py:927-929`)."""
+    return _make_sampler(_lib.MF_SAMPLER_NORMAL, args_like, num)
+
+
+def sampler_signs(*args_like, num):
+    """Sample signs uniformly / Rademacher (`stochtrace.py:932-937`; real dtypes only)."""
+    return _make_sampler(_lib.MF_SAMPLER_SIGNS, args_like, num)
+
+
+def monte_carlo_trace():
+    """Integrand ``v^T (A v)`` (`stochtrace.py:853-865`)."""
+
+    def integrand(matvec, v, *parameters):
+        import torch
+
+        v = _device.as_device(v).reshape(-1)
+        Qv = matvec(v, *parameters)
+        return torch.dot(v, _device.as_device(Qv, v.dtype).reshape(-1))
+
+    integrand._mf_integrand = {"kind": "trace"}
+    return integrand
+
+
+# ----------------------------------------------------------------------------
+
+
+def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, return_coeffs=False):
+    """Per-probe integrand values through `mf_estimate`; None if not fusable."""
+    ispec = getattr(integrand, "_mf_integrand", None)
+    sspec = getattr(sampler, "_mf_sampler", None)
+    if ispec is None or sspec is None or not isinstance(matvec, ops.Operator) or parameters:
+        return None
+    import torch
+
+    lib = _lib.load()
+    op = matvec
+    if sspec["n"] != op.n:
+        raise ValueError(f"sampler draws vectors of length {sspec['n']}, operator dimension is {op.n}")
+    if sspec["dtype"] != op.dtype:
+        raise TypeError(f"sampler dtype {sspec['dtype']} does not match operator dtype {op.dtype}")
+    P = sspec["num"]
+    dt = op.dtype
+    dev = _device.device()
+
+    # probe range of this rank
+    p0, p1 = 0, P
+    group = None
+    world = 1
+    if _PROBE_GROUP["enabled"]:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            group = _PROBE_GROUP["group"]
+            world = dist.get_world_size(group)
+            p0, p1 = _sharding.shard_range(P, world, dist.get_rank(group))
+    nloc = p1 - p0
+
+    if ispec["kind"] == "trace":
+        integ, k, rflag, fn, param = _lib.MF_INTEGRAND_TRACE, 0, _lib.MF_REORTHO_NONE, 0, 0.0
+        host_fn = None
+    else:
+        integ = _lib.MF_INTEGRAND_SLQ
+        k = ispec["num_matvecs"]
+        rflag = _lib.MF_REORTHO_FULL if ispec["reortho"] == "full" else _lib.MF_REORTHO_NONE
+        matfun = ispec["matfun"]
+        known = _funm._known_fn(matfun) if (not callable(matfun) or _funm._is_hashable(matfun)) else None
+        host_fn = None if known is not None else matfun
+        fn, param = known if known is not None else (_lib.MF_FN_LOG, 0.0)
+        if k < 0 or k > op.n:
+            from matfree_b200 import decomp
+
+            raise ValueError(decomp._error_num_matvecs(k, maxval=op.n, minval=0))
+
+    ld = int(tile) if tile else _device.ld_for(max(nloc, 1))
+    ntiles = max(1, -(-nloc // ld))
+    st = op._struct()
+    ws_bytes = lib.mf_estimate_workspace_bytes(ctypes.byref(st), ld, k, rflag, integ)
+    if ws_bytes < 0:
+        _lib.check(-1)
+    ws = _device.workspace(ws_bytes)
+    quad = torch.empty((max(nloc, 1),), dtype=dt, device=dev)
+    need_coeffs = return_coeffs or host_fn is not None
+    alphas = betas = lens = None
+    if need_coeffs and integ == _lib.MF_INTEGRAND_SLQ:
+        alphas = torch.empty((ntiles, k, ld), dtype=dt, device=dev)
+        betas = torch.empty((ntiles, k, ld), dtype=dt, device=dev)
+        lens = torch.empty((ntiles, ld), dtype=dt, device=dev)
+    if nloc > 0:
+        _lib.check(lib.mf_estimate(ctypes.byref(st), integ, sspec["kind"], 0, int(key[0]),
+                                   int(key[1]), p0, nloc, ld, k, rflag,
+                                   _lib.MF_FN_NONE if host_fn is not None else fn, param,
+                                   quad.data_ptr(),
+                                   None if alphas is None else alphas.data_ptr(),
+                                   None if betas is None else betas.data_ptr(),
+                                   None if lens is None else lens.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _device.stream()))
+    quad = quad[:nloc]
+    if host_fn is not None and nloc > 0:
+        # arbitrary matfun: Gauss nodes/weights from the kernel, f applied on the device
+        parts = []
+        for t in range(ntiles):
+            npb = min(ld, nloc - t * ld)
+            parts.append(_funm.quadrature_blocked(alphas[t], betas[t], lens[t], npb, host_fn))
+        quad = torch.cat(parts)
+    if world > 1:
+        quad = _sharding.gather_shards(quad, P, group)
+    if return_coeffs:
+        return quad, alphas, betas, lens
+    return quad
+
+
+def _reduce(values):
+    """mean, std(ddof=0)/sqrt(P) through `mf_mc_reduce` (deterministic, fp64 accumulation)."""
+    import torch
+
+    lib = _lib.load()
+    values = values.contiguous()
+    stats = torch.empty((4,), dtype=torch.float64, device=values.device)
+    _lib.check(lib.mf_mc_reduce(values.data_ptr(), _device.mf_dtype(values.dtype), values.numel(),
+                                stats.data_ptr(), _device.stream()))
+    return stats[0].to(values.dtype), stats[2].to(values.dtype)
+
+
+def _generic_values(integrand, sampler, matvecs, key, parameters):
+    import torch
+
+    samples = sampler(key)
+    vals = [integrand(matvecs, s, *parameters) for s in samples]
+    return torch.stack([_device.as_device(v) for v in vals])
+
+
+def estimator_monte_carlo(integrand, /, sampler):
+    """Construct a stochastic trace-/diagonal-estimator (`stochtrace.py:7-52`)."""
+
+    def estimate(matvecs, key, *parameters):
+        vals = _fused_values(integrand, sampler, matvecs, key, parameters)
+        if vals is not None:
+            return _reduce(vals)[0]
+        Qs = _generic_values(integrand, sampler, matvecs, key, parameters)
+        return Qs.mean(dim=0)
+
+    estimate.per_probe = lambda matvecs, key, *parameters, **kw: _fused_values(
+        integrand, sampler, matvecs, key, parameters, **kw)
+    return estimate
+
+
+def estimator_monte_carlo_mean_and_sem(integrand, /, sampler):
+    """Estimator returning ``(mean, sem)`` with ``sem = std/sqrt(num)`` (`stochtrace.py:55-89`)."""
+
+    def estimate(matvecs, key, *parameters):
+        import torch
+
+        vals = _fused_values(integrand, sampler, matvecs, key, parameters)
+        if vals is not None:
+            return _reduce(vals)
+        Qs = _generic_values(integrand, sampler, matvecs, key, parameters)
+        return Qs.mean(dim=0), Qs.std(dim=0, unbiased=False) / np.sqrt(Qs.shape[0])
+
+    return estimate

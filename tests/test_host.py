@@ -1,0 +1,142 @@
+"""CPU tests: the C-ABI library loads and exports every declared symbol; host logic."""
+
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import prng as oprng
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from matfree_b200 import _lib
+
+    lib = _lib.load()  # raises if missing or a symbol is absent
+    header = open(os.path.join(ROOT, "include", "matfree_b200.h")).read()
+    declared = set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", header))
+    declared -= {"mf_operator"}
+    assert declared, "no declarations found"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert lib.mf_abi_version() == 1
+    assert lib.mf_launch_count() == 0
+
+
+def test_argument_validation_without_gpu():
+    """Invalid arguments are rejected before any CUDA call (no GPU needed)."""
+    import ctypes
+
+    from matfree_b200 import _lib
+
+    lib = _lib.load()
+    op = _lib.MfOperator(kind=_lib.MF_OP_CSR, dtype=0, n=13, m=13, nnz=1, values=8, indptr=8, indices=8,
+                         lda=0, op_scratch=None)
+    assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 16, 14, 0, 0) == -1
+    assert b"exceeds the acceptable range" in lib.mf_last_error()
+    assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 16, -1, 0, 0) == -1
+    assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 24, 3, 0, 0) == -1  # ld not a power of two
+    assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 16, 3, 0, 0) > 0
+    assert lib.mf_estimate_workspace_bytes(ctypes.byref(op), 16, 3, 1, 0) > 0
+    with pytest.raises(ValueError, match="exceeds"):
+        _lib.check(lib.mf_lanczos(ctypes.byref(op), 8, 16, 14, 0, 8, 8, 8, None, None, 8, 1 << 20, None))
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    from matfree_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.LibraryMissingError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import matfree_b200 as m
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.ops.dense(np.eye(3, dtype=np.float32))
+
+
+def test_product_does_not_import_oracle():
+    out = subprocess.run(
+        [sys.executable, "-c",
+         "import sys, matfree_b200, matfree_b200.workloads; "
+         "print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"],
+        cwd=ROOT, capture_output=True, text=True, check=True)
+    assert out.stdout.strip() == "False"
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "matfree_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_prng_key_and_split_match_oracle():
+    from matfree_b200.backend import prng
+
+    for seed in (0, 1, 42, 2**40 + 7):
+        assert np.array_equal(prng.prng_key(seed), oprng.prng_key(seed))
+        assert np.array_equal(prng.split(prng.prng_key(seed), 5), oprng.split(oprng.prng_key(seed), 5))
+
+
+def test_factories_validate_like_the_reference():
+    import matfree_b200 as m
+
+    with pytest.raises(ValueError, match="unsupported"):
+        m.decomp.tridiag_sym(3, reortho="partial")
+    tri = m.decomp.tridiag_sym(4, reortho="none", materialize=False)
+    assert tri._mf_spec == {"kind": "tridiag_sym", "num_matvecs": 4, "reortho": "none", "materialize": False}
+    integ = m.funm.integrand_funm_sym_logdet(tri)
+    assert integ._mf_integrand["kind"] == "slq" and integ._mf_integrand["matfun"] is np.log
+    assert m.stochtrace.monte_carlo_trace()._mf_integrand == {"kind": "trace"}
+
+
+def test_shard_range_partitions_probes():
+    from matfree_b200._sharding import shard_range
+
+    for P in (1, 7, 8, 1000, 8192):
+        for world in (1, 2, 3, 4, 8):
+            got = [shard_range(P, world, r) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == P
+            for (a0, a1), (b0, b1) in zip(got[:-1], got[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert sum(b - a for a, b in got) == P
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MF_ROOT"])
+from matfree_b200._sharding import shard_range, gather_shards
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P = int(os.environ["MF_P"])
+full = torch.arange(P, dtype=torch.float32) * 0.5 + 1.0
+p0, p1 = shard_range(P, world, rank)
+got = gather_shards(full[p0:p1].clone(), P)
+assert torch.equal(got, full), (rank, got, full)
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+@pytest.mark.parametrize("P", [8, 13])
+def test_gather_shards_world_size_2_gloo(tmp_path, P):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MF_ROOT=ROOT, MF_P=str(P), MASTER_ADDR="127.0.0.1")
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", str(29531 + P), str(script)],
+        env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
