@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- SLQ log-determinant throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], "C2"): SLQ log-determinant of the 2-D 5-point
+Laplacian on a 4096 x 4096 grid (n = 16 777 216 rows, CSR, int32 indices, fp32 values)
+plus 1.0 * I, Lanczos depth 30 without re-orthogonalisation, Rademacher probes of
+`jax.random` key 1, 1024 probes per GPU (8192 on 8 GPUs; weak scaling), probe tile 256.
+
+One "step" = one complete `estimate(matvec, key)` call of the public API
+(`stochtrace.estimator_monte_carlo_mean_and_sem`) over this rank's probes: probe
+generation, 30 Lanczos steps per probe, tridiagonal quadrature, Monte-Carlo reduction
+(and, for N > 1, the all-gather of the per-probe values).
+
+Metric: probe.Lanczos-steps / second = (probes of all ranks * depth) / step time.
+  value  -- operator already resident in HBM; CUDA events, max over ranks.
+  e2e    -- the same call starting from HOST (pinned) CSR arrays: the host->device copy
+            of the operator and the device->host read of (mean, sem) are inside the
+            timed region.
+  roofline -- dominant kernel class: algorithmic bytes per launch / mean launch time,
+            the launch times measured live with CUDA events on the launching stream
+            (`mf_timing_enable`), against MEASURED_PEAKS.json.
+  cpu_baseline -- the oracle's multi-threaded C port (oracle/slq_port.c) on the host
+            cores, on a bounded probe sample of the same operator (N = 1, rank 0 only).
+
+`--impl reference` times that CPU port instead (the reference itself needs JAX, which
+is not installable here -- see DESIGN.md); each step is a bounded probe sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "slq_logdet_probe_lanczos_steps_per_sec"
+UNIT = "probe*steps/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=4096, help="grid side m (n = m*m rows)")
+    ap.add_argument("--depth", type=int, default=30)
+    ap.add_argument("--probes-per-gpu", type=int, default=1024)
+    ap.add_argument("--tile", type=int, default=256)
+    ap.add_argument("--cpu-probes", type=int, default=16, help="probe sample of the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="profiling run: honour --warmup below 3")
+    return ap.parse_args()
+
+
+def workload_name(a, world):
+    return (f"C2: SLQ logdet, 2-D 5-pt Laplacian {a.grid}^2 (n={a.grid * a.grid}) CSR + 1.0*I, fp32, "
+            f"depth {a.depth}, reortho=none, {a.probes_per_gpu} Rademacher probes per GPU "
+            f"({a.probes_per_gpu * world} total), key PRNGKey(1)")
+
+
+# --------------------------------------------------------------------------- clocks
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU every 200 ms in a thread (NVML)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+
+    def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        names = {
+            0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+            0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting",
+            0x100: "display_clock_setting", 0x10: "sync_boost",
+        }
+        while not self._stop.is_set():
+            if self._nvml is not None:
+                try:
+                    p = self._nvml
+                    self.samples.append(int(p.nvmlDeviceGetClockInfo(self._h, p.NVML_CLOCK_SM)))
+                    try:
+                        r = int(p.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                    except Exception:
+                        r = int(p.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+            else:
+                self._smi()
+            self._stop.wait(0.2)
+
+    def _smi(self):
+        try:
+            out = subprocess.run(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits"],
+                capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            self.samples.append(int(float(out[0])))
+            self.max_mhz = int(float(out[1]))
+            for nm, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], out[2:]):
+                if "Active" in v and "Not" not in v:
+                    self.reasons.add(nm)
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+
+
+def cpu_csr_arrays(grid):
+    from matfree_b200 import workloads
+
+    ip, ix, d = workloads.laplacian_csr((grid, grid), shift=1.0)
+    return ip.numpy(), ix.numpy(), d.numpy()
+
+
+def cpu_sample(csr, probes, depth):
+    """One bounded sample on the host cores through the oracle's C port; returns seconds."""
+    from oracle import port
+
+    ip, ix, d = csr
+    t0 = time.perf_counter()
+    port.csr_logdet_quadforms(ip, ix, d, (0, 1), 0, probes, depth)
+    return time.perf_counter() - t0
+
+
+def run_reference(a, rank, world):
+    """`--impl reference`: the CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import port
+
+    port.build()
+    csr = cpu_csr_arrays(a.grid)
+    probes = min(a.cpu_probes, 8)
+    for _ in range(a.warmup):
+        cpu_sample(csr, probes, a.depth)
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        cpu_sample(csr, probes, a.depth)
+    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    value = probes * a.depth / dt
+    sample = f"{probes} probes x depth {a.depth} on the full {a.grid}^2 operator per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.num_threads(), "kind": "port",
+                         "sample": sample,
+                         "note": "oracle/slq_port.c (OpenMP C restatement); the JAX reference is not installable here"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- GPU arm
+
+
+def algorithmic_bytes(cls, n, ld, nnz, s=4):
+    """Algorithmic HBM bytes of ONE launch of a kernel class on a tile of `ld` probes
+    (DESIGN.md 'Kernels'): block vectors are n*ld*s bytes each."""
+    blk = n * ld * s
+    matrix = nnz * (s + 4) + 4 * (n + 1)
+    return {
+        "spmm_csr": 2 * blk + matrix,      # read v_j, write w (alpha fused), stream the matrix once
+        "lanczos_update": 4 * blk,         # read w, r_j, r_{j-1}; write r_{j+1} (beta fused)
+        "probe_gen": blk,                  # write the probe block
+        "dot": 2 * blk,
+        "scale": 2 * blk,
+    }.get(cls)
+
+
+def run_ours(a, rank, local_rank, world):
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import matfree_b200 as m
+    from matfree_b200 import _lib, workloads
+
+    lib = _lib.load()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = a.grid * a.grid
+    P_local, P_total, k = a.probes_per_gpu, a.probes_per_gpu * world, a.depth
+    ip, ix, d = workloads.laplacian_csr((a.grid, a.grid), shift=1.0, device=dev)
+    nnz = int(d.numel())
+    op = m.ops.csr(ip, ix, d)
+    torch.cuda.empty_cache()
+    key = m.prng.prng_key(1)
+    sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1.0), (n,)), num=P_total)
+    integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+    estimate = m.stochtrace.estimator_monte_carlo_mean_and_sem(integrand, sampler)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with m.stochtrace.probe_sharding():
+            return estimate(op, key)
+
+    # host-resident operator for the end-to-end leg
+    h_ip, h_ix, h_d = (t.cpu().pin_memory() for t in (ip, ix, d))
+    h2d = h_ip.numel() * 4 + h_ix.numel() * 4 + h_d.numel() * 4
+
+    def step_e2e():
+        op_h = m.ops.csr(h_ip.to(dev, non_blocking=True), h_ix.to(dev, non_blocking=True),
+                         h_d.to(dev, non_blocking=True))
+        with m.stochtrace.probe_sharding():
+            mean, sem = estimate(op_h, key)
+        return float(mean), float(sem)  # device -> host read of the result
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / max(steps, 1), out
+
+    # ---- warm-up (also creates the timing events once)
+    _lib.timing_enable(True)
+    warmup = a.warmup if a.profile else max(a.warmup, 3)
+    for _ in range(warmup):
+        out = step_resident()
+    torch.cuda.synchronize()
+    _lib.timing_collect()
+
+    # ---- timed region: K steps, clocks sampled during it, per-launch events live
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = lib.mf_launch_count()
+    ms_step, out = timed(step_resident, a.steps)
+    launches = lib.mf_launch_count() - launches0
+    clk = clocks.stop()
+    per_class = _lib.timing_collect()
+    _lib.timing_enable(False)
+    mean, sem = float(out[0]), float(out[1])
+    value = P_total * k / (ms_step * 1e-3)
+
+    # ---- end-to-end leg (host buffers)
+    e2e = None
+    if not a.no_e2e:
+        step_e2e()
+        ms_e2e, _ = timed(step_e2e, a.steps)
+        e2e = {"value": P_total * k / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": 2 * 4, "ms_per_step": ms_e2e,
+               "what": "ops.csr(host pinned CSR arrays) -> estimate(op, key) -> float(mean), float(sem)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    total_ms = sum(v[0] for v in per_class.values()) or 1.0
+    kernels = {}
+    for cls, (ms, cnt) in sorted(per_class.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_launch": ms / cnt, "launches": int(cnt), "share": ms / total_ms}
+        ab = algorithmic_bytes(cls, n, min(a.tile, P_local), nnz)
+        if ab:
+            ent["achieved_gbs"] = ab / (ms / cnt * 1e-3) / 1e9
+            ent["frac_of_peak"] = ent["achieved_gbs"] / peak
+        kernels[cls] = ent
+    top = next(iter(kernels))
+    roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top].get("achieved_gbs"),
+                "peak": peak, "unit": "GB/s", "frac": kernels[top].get("frac_of_peak"),
+                "traffic": None, "peak_source": peak_kind, "share_of_step": kernels[top]["share"],
+                "algorithmic_bytes_per_launch": algorithmic_bytes(top, n, min(a.tile, P_local), nnz)}
+    # whole-step roofline: SURVEY section 8(d): 6*n*s + matrix/B_tile per probe*step
+    step_bytes = 6 * n * 4 + (nnz * 8 + 4 * (n + 1)) / min(a.tile, P_local)
+    whole = {"algorithmic_bytes_per_probe_step": step_bytes,
+             "achieved_gbs": value / world * step_bytes / 1e9,
+             "frac_of_peak": value / world * step_bytes / 1e9 / peak}
+
+    truth = workloads.laplacian_logdet((a.grid, a.grid), 1.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "tile": min(a.tile, P_local),
+                   "l2": "working set per tile (4 block vectors x 17 GB) >> 126 MB L2; no flush needed",
+                   "parallelism": f"probe-sharded x{world}"},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": roofline, "kernels": kernels, "step_roofline": whole,
+        "result": {"logdet_estimate": mean, "sem": sem, "closed_form_logdet": truth,
+                   "rel_err": abs(mean - truth) / abs(truth)},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only), bounded sample
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            from oracle import port
+
+            port.build()
+            del op, ip, ix, d
+            torch.cuda.empty_cache()
+            csr = (h_ip.numpy(), h_ix.numpy(), h_d.numpy())
+            dt = cpu_sample(csr, a.cpu_probes, k)
+            line["cpu_baseline"] = {
+                "value": a.cpu_probes * k / dt, "unit": UNIT, "cores": port.num_threads(), "kind": "port",
+                "sample": f"{a.cpu_probes} probes x depth {k} on the full operator, {dt:.1f} s",
+                "host_cpus": os.cpu_count(),
+                "note": "oracle/slq_port.c, OpenMP; the JAX reference cannot be installed here"}
+        except Exception as exc:  # the baseline must never lose the GPU line
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
+    if world != a.gpus and world == 1 and a.gpus > 1:
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(a, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()
