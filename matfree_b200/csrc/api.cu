@@ -101,7 +101,7 @@ struct Arena {
   }
 };
 
-inline int vec_of(int32_t dtype, int64_t ld) {
+[[maybe_unused]] inline int vec_of(int32_t dtype, int64_t ld) {
   const int nv = dtype == MF_F64 ? 2 : 4;
   return ld >= nv ? nv : 1;
 }
@@ -144,17 +144,16 @@ int32_t validate_op(const mf_operator_t* op) {
   }
 }
 
-// W = s * (A @ X); if alpha_partial != null and the operator can fuse it, also
-// the column sums of (X*s) .* W.  *fused tells the caller whether it happened.
+// W = s * (A @ X); if red != null and the operator can fuse it, also the column
+// sums of (X*s) .* W -> red->fin.  *fused tells the caller whether it happened.
 int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W, int64_t ld,
-                 void* gram_scratch, double* alpha_partial, int* grid_out, bool* fused,
-                 cudaStream_t st) {
+                 void* gram_scratch, const Reduce* red, bool* fused, cudaStream_t st) {
   *fused = false;
   switch (op->kind) {
     case MF_OP_CSR:
       MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X,
-                             s, W, ld, alpha_partial, grid_out, st));
-      *fused = alpha_partial != nullptr;
+                             s, W, ld, red, st));
+      *fused = red != nullptr;
       return MF_OK;
     case MF_OP_DENSE:
       return launch_gemm_blocked(op->values, op->lda, false, op->n, op->n, X, s, W, ld,
@@ -178,7 +177,8 @@ struct LanczosBufs {
   void *R0, *R1, *W, *V;       // block vectors
   void *inv;                   // [k+1][ld] 1/len, 1/beta_j
   void *h, *h2;                // [k][ld] CGS coefficients
-  double* partial;             // reduction partial rows
+  double* partial;             // per-CTA partial rows of the reductions
+  unsigned int* counter;       // ticket counter of the fused finalize (zeroed per call)
   void* gram;                  // m*ld
 };
 
@@ -186,26 +186,33 @@ int32_t carve_lanczos(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, 
                       LanczosBufs* b) {
   const int64_t es = (int64_t)dtype_size(op->dtype);
   const int64_t blk = op->n * ld * es;
-  const int grid = reduce_grid(op->n * ld, vec_of(op->dtype, ld));
   memset(b, 0, sizeof(*b));
+  b->counter = (unsigned int*)a.take(256);
   if (reortho == MF_REORTHO_NONE) {
     b->R0 = a.take(blk);
     b->R1 = a.take(blk);
     b->W = a.take(blk);
     b->inv = a.take((k + 1) * ld * es);
-    b->partial = (double*)a.take((int64_t)grid * ld * 8);
+    b->partial = (double*)a.take(partial_bytes(ld, 1));
   } else {
     b->V = a.take(blk);
     b->h = a.take((k + 1) * ld * es);
     b->h2 = a.take((k + 1) * ld * es);
-    b->partial = (double*)a.take((k + 4) * (int64_t)grid * ld * 8);
+    b->partial = (double*)a.take(partial_bytes(ld, 4));
   }
   if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) b->gram = a.take(op->m * ld * es);
-  if (!a.dry && (b->partial == nullptr || (b->gram == nullptr && op->kind == MF_OP_GRAM &&
-                                            op->op_scratch == nullptr))) {
+  if (!a.dry && a.used > a.size) {
     set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
               (long long)a.size);
     return MF_ERR_WORKSPACE;
+  }
+  return MF_OK;
+}
+
+int32_t zero_counter(const LanczosBufs& b, cudaStream_t st) {
+  if (cudaMemsetAsync(b.counter, 0, 256, st) != cudaSuccess) {
+    set_error("counter memset failed");
+    return MF_ERR_CUDA;
   }
   return MF_OK;
 }
@@ -218,15 +225,17 @@ inline void* row(void* base, int64_t j, int64_t ld, int32_t dtype) {
 // normalised: the un-normalised residual block r_j and 1/beta_{j-1} are kept
 // and v_j = r_j / beta_{j-1} is formed on the fly by the consumers.
 //   v0_owned: V0 may be overwritten (fused estimator) -> one buffer less.
-int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, int64_t ld, int64_t k,
-                     void* alphas, void* betas, void* init_len, void* Q, void* residual,
-                     const LanczosBufs& b, cudaStream_t st) {
+//   have_len: init_len and inv[0] were already written (by the probe generator).
+int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have_len, int64_t ld,
+                     int64_t k, void* alphas, void* betas, void* init_len, void* Q,
+                     void* residual, const LanczosBufs& b, cudaStream_t st) {
   const int32_t dt = op->dtype;
   const int64_t n = op->n;
   const int64_t blk = n * ld * (int64_t)dtype_size(dt);
-  int grid = 0;
-  MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, b.partial, &grid, st));
-  MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, init_len, row(b.inv, 0, ld, dt), nullptr, st));
+  if (!have_len) {
+    const Reduce red{b.partial, Finalize{b.counter, 1, init_len, row(b.inv, 0, ld, dt), nullptr}};
+    MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, red, st));
+  }
   void* Rc = V0;
   void* Rp = nullptr;
   for (int64_t j = 0; j < k; ++j) {
@@ -239,26 +248,26 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, int64_t l
       X = Qj;
       sx = nullptr;
     }
-    bool fused = false;
-    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, b.partial, &grid, &fused, st));
-    if (!fused) MF_TRY(launch_dot(X, sx, b.W, dt, n, ld, b.partial, &grid, st));
     void* aj = row(alphas, j, ld, dt);
-    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 0, aj, nullptr, nullptr, st));
+    const Reduce red_a{b.partial, Finalize{b.counter, 0, aj, nullptr, nullptr}};
+    bool fused = false;
+    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, &red_a, &fused, st));
+    if (!fused) MF_TRY(launch_dot(X, sx, b.W, dt, n, ld, red_a, st));
     // pick the output buffer: alias Rp when we own it
     void* out;
     if (Rp == nullptr) out = b.R0;
     else if (Rp == V0 && !v0_owned) out = b.R1;
     else out = Rp;
+    const Reduce red_b{b.partial, Finalize{b.counter, 1, row(betas, j, ld, dt),
+                                           row(b.inv, j + 1, ld, dt), nullptr}};
     MF_TRY(launch_lanczos_update(b.W, Rc, sc, aj, Rp, j > 0 ? row(b.inv, j - 1, ld, dt) : nullptr,
                                  j > 0 ? row(betas, j - 1, ld, dt) : nullptr, out, dt, n, ld,
-                                 b.partial, &grid, st));
-    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, row(betas, j, ld, dt),
-                           row(b.inv, j + 1, ld, dt), nullptr, st));
+                                 red_b, st));
     Rp = Rc;
     Rc = out;
   }
   if (residual != nullptr) {
-    // b_{k-1} * v_k is the un-normalised r_k itself (decomp.py:167); k == 0: v_0... see below
+    // b_{k-1} * v_k is the un-normalised r_k itself (decomp.py:167)
     if (k > 0) {
       if (cudaMemcpyAsync(residual, Rc, blk, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
         set_error("residual copy failed");
@@ -271,34 +280,34 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, int64_t l
 
 // Arnoldi with classical Gram-Schmidt applied twice (matfree/decomp.py:426-477)
 // and T = (H + H^T)/2 (decomp.py:133-135), on a probe block.
-int32_t lanczos_full(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
-                     void* alphas, void* betas, void* init_len, void* Q, void* residual,
-                     const LanczosBufs& b, cudaStream_t st) {
+int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int64_t ld,
+                     int64_t k, void* alphas, void* betas, void* init_len, void* Q,
+                     void* residual, const LanczosBufs& b, cudaStream_t st) {
   const int32_t dt = op->dtype;
   const int64_t n = op->n;
   const int64_t es = (int64_t)dtype_size(dt);
   const int64_t blk = n * ld * es;
-  int grid = 0;
-  MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, b.partial, &grid, st));
-  MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, init_len, nullptr, nullptr, st));
+  if (!have_len) {
+    const Reduce red{b.partial, Finalize{b.counter, 1, init_len, nullptr, nullptr}};
+    MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, red, st));
+  }
   const void* length = init_len;
   for (int64_t i = 0; i < k; ++i) {
     void* Qi = (char*)Q + i * blk;
     MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
     bool fused = false;
-    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, &grid, &fused, st));  // :460
-    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.h, st));      // :463
+    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, &fused, st));  // :460
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st));  // :463
     if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
       set_error("alpha copy failed");
       return MF_ERR_CUDA;
     }
     if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
-    MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, nullptr, st));  // :464
-    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.h2, st));          // :468
-    MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, b.partial, &grid, st));
-    MF_TRY(launch_finalize(b.partial, grid, ld, dt, 1, row(betas, i, ld, dt), nullptr, nullptr,
-                           st));  // :471
+    MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, st));  // :464
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st));  // :468
+    const Reduce red_n{b.partial, Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr}};
+    MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, &red_n, st));  // :468,471
     length = row(betas, i, ld, dt);
   }
   if (residual != nullptr) {
@@ -365,7 +374,7 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
     return MF_ERR_UNSUPPORTED;
   }
   return launch_probe_gen(out, dtype, layout, n, ld, p0, num_probes, key0, key1, sampler,
-                          prng_flags, nullptr, nullptr, (cudaStream_t)stream);
+                          prng_flags, nullptr, (cudaStream_t)stream);
 }
 
 int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* stream) {
@@ -375,8 +384,7 @@ int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, v
     return MF_ERR_INVALID_ARGUMENT;
   }
   bool fused;
-  int grid;
-  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, &grid, &fused, (cudaStream_t)stream);
+  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, &fused, (cudaStream_t)stream);
 }
 
 int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
@@ -469,9 +477,11 @@ int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t 
   LanczosBufs b;
   MF_TRY(carve_lanczos(a, op, ld, k, reortho, &b));
   cudaStream_t st = (cudaStream_t)stream;
+  MF_TRY(zero_counter(b, st));
   if (reortho == MF_REORTHO_NONE)
-    return lanczos_none(op, (void*)V0, false, ld, k, alphas, betas, init_len, Q, residual, b, st);
-  return lanczos_full(op, V0, ld, k, alphas, betas, init_len, Q, residual, b, st);
+    return lanczos_none(op, (void*)V0, false, false, ld, k, alphas, betas, init_len, Q, residual,
+                        b, st);
+  return lanczos_full(op, V0, false, ld, k, alphas, betas, init_len, Q, residual, b, st);
 }
 
 int64_t mf_tridiag_quad_workspace_bytes(int64_t ld, int64_t k) {
@@ -550,9 +560,10 @@ static int32_t carve_estimate(Arena& a, const mf_operator_t* op, int64_t ld, int
   memset(e, 0, sizeof(*e));
   e->Z = a.take(blk);
   if (integrand == MF_INTEGRAND_TRACE) {
+    e->lb.counter = (unsigned int*)a.take(256);
     e->lb.W = a.take(blk);
-    const int grid = reduce_grid(op->n * ld, vec_of(op->dtype, ld));
-    e->lb.partial = (double*)a.take((int64_t)grid * ld * 8);
+    e->lb.partial = (double*)a.take(partial_bytes(ld, 1));
+    e->len = a.take(ld * es);
     if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) e->lb.gram = a.take(op->m * ld * es);
     if (!a.dry && a.used > a.size) {
       set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
@@ -620,35 +631,41 @@ int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
   EstimateBufs e;
   MF_TRY(carve_estimate(a, op, ld, k, reortho, integrand, &e));
 
+  MF_TRY(zero_counter(e.lb, st));
   int64_t tile = 0;
   for (int64_t t0 = 0; t0 < num_probes; t0 += ld, ++tile) {
     const int64_t np = (num_probes - t0) < ld ? (num_probes - t0) : ld;
-    MF_TRY(launch_probe_gen(e.Z, dt, MF_LAYOUT_BLOCKED, op->n, ld, p0 + t0, np, key0, key1,
-                            sampler, prng_flags, nullptr, nullptr, st));
     void* q_tile = (char*)quad_out + t0 * es;
     if (integrand == MF_INTEGRAND_TRACE) {
       // v^T (A v)  (matfree/stochtrace.py:859-863)
+      MF_TRY(launch_probe_gen(e.Z, dt, MF_LAYOUT_BLOCKED, op->n, ld, p0 + t0, np, key0, key1,
+                              sampler, prng_flags, nullptr, st));
+      // full tile: the last CTA writes straight to the output; partial tile: via scratch
+      void* dst = np == ld ? q_tile : e.len;
+      const Reduce red{e.lb.partial, Finalize{e.lb.counter, 0, dst, nullptr, nullptr}};
       bool fused = false;
-      int grid = 0;
-      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, e.lb.partial, &grid, &fused, st));
-      if (!fused) MF_TRY(launch_dot(e.Z, nullptr, e.lb.W, dt, op->n, ld, e.lb.partial, &grid, st));
-      if (np == ld) {
-        MF_TRY(launch_finalize(e.lb.partial, grid, ld, dt, 0, q_tile, nullptr, nullptr, st));
-      } else {
-        // partial tile: finalize into scratch, then copy the live columns
-        MF_TRY(launch_finalize(e.lb.partial, grid, ld, dt, 0, e.lb.W, nullptr, nullptr, st));
-        if (cudaMemcpyAsync(q_tile, e.lb.W, np * es, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-          set_error("estimate: copy failed");
-          return MF_ERR_CUDA;
-        }
+      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, &red, &fused, st));
+      if (!fused) MF_TRY(launch_dot(e.Z, nullptr, e.lb.W, dt, op->n, ld, red, st));
+      if (np != ld &&
+          cudaMemcpyAsync(q_tile, e.len, np * es, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("estimate: copy failed");
+        return MF_ERR_CUDA;
       }
       continue;
     }
+    // probes + |v0| and 1/|v0| in one kernel (funm.py:228-229, decomp.py:227 / :435)
+    {
+      void* inv0 = reortho == MF_REORTHO_NONE ? e.lb.inv : nullptr;
+      const Reduce red{e.lb.partial, Finalize{e.lb.counter, 1, e.len, inv0, nullptr}};
+      MF_TRY(launch_probe_gen(e.Z, dt, MF_LAYOUT_BLOCKED, op->n, ld, p0 + t0, np, key0, key1,
+                              sampler, prng_flags, &red, st));
+    }
     if (reortho == MF_REORTHO_NONE)
-      MF_TRY(lanczos_none(op, e.Z, true, ld, k, e.alphas, e.betas, e.len, nullptr, nullptr, e.lb,
-                          st));
+      MF_TRY(lanczos_none(op, e.Z, true, true, ld, k, e.alphas, e.betas, e.len, nullptr, nullptr,
+                          e.lb, st));
     else
-      MF_TRY(lanczos_full(op, e.Z, ld, k, e.alphas, e.betas, e.len, e.Qbasis, nullptr, e.lb, st));
+      MF_TRY(lanczos_full(op, e.Z, true, ld, k, e.alphas, e.betas, e.len, e.Qbasis, nullptr, e.lb,
+                          st));
     // quadrature: quad for the np live probes goes straight to the output
     MF_TRY(launch_tridiag_quad(e.alphas, e.betas, e.len, dt, ld, np, k, fn, fn_param, q_tile,
                                nullptr, nullptr, nullptr, e.qwork, st));

@@ -43,7 +43,7 @@ __device__ __forceinline__ void load_cols(const T* __restrict__ s, int ld, T (&v
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
 dot_kernel(const T* __restrict__ X, const T* __restrict__ sx, const T* __restrict__ Y,
-           int64_t total, int ld, double* __restrict__ partial) {
+           int64_t total, int ld, double* __restrict__ partial, Finalize fin) {
   T s[VEC];
   load_cols<T, VEC>(sx, ld, s, T(1));
   double acc[1][VEC];
@@ -56,25 +56,7 @@ dot_kernel(const T* __restrict__ X, const T* __restrict__ sx, const T* __restric
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[0][i] += (double)(x[i] * s[i]) * (double)y[i];
   }
-  cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
-}
-
-template <typename T>
-__global__ void finalize_kernel(const double* __restrict__ partial, int grid, int ld, int mode,
-                                T* __restrict__ value_out, T* __restrict__ inv_out,
-                                double* __restrict__ dbl_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ld) return;
-  double s = 0.0;
-  for (int b = 0; b < grid; ++b) s += partial[(int64_t)b * ld + c];
-  if (dbl_out) dbl_out[c] = s;
-  if (mode == 0) {
-    if (value_out) value_out[c] = (T)s;
-  } else {
-    const T v = (T)sqrt(s);
-    if (value_out) value_out[c] = v;
-    if (inv_out) inv_out[c] = T(1) / v;
-  }
+  cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
 }
 
 template <typename T, int VEC, bool HAS_PREV>
@@ -82,7 +64,7 @@ __global__ void __launch_bounds__(kBlock)
 lanczos_update_kernel(const T* __restrict__ W, const T* __restrict__ Rc, const T* __restrict__ sc,
                       const T* __restrict__ a, const T* Rp, const T* __restrict__ sp,
                       const T* __restrict__ bprev, T* out, int64_t total, int ld,
-                      double* __restrict__ partial) {
+                      double* __restrict__ partial, Finalize fin) {
   T s_c[VEC], al[VEC], s_p[VEC], bp[VEC];
   load_cols<T, VEC>(sc, ld, s_c, T(1));
   load_cols<T, VEC>(a, ld, al, T(0));
@@ -107,7 +89,7 @@ lanczos_update_kernel(const T* __restrict__ W, const T* __restrict__ Rc, const T
     }
     store_chunk<T, VEC>(out, f, r);
   }
-  cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+  cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
 }
 
 template <typename T, int VEC>
@@ -130,7 +112,7 @@ template <typename T, int VEC, int JB>
 __global__ void __launch_bounds__(kBlock)
 reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
                    const T* __restrict__ V, int64_t total, int ld, double* __restrict__ partial,
-                   int64_t partial_stride) {
+                   int64_t partial_stride, Finalize fin) {
   double acc[JB][VEC];
 #pragma unroll
   for (int j = 0; j < JB; ++j)
@@ -149,25 +131,14 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
       }
     }
   }
-  cta_reduce_columns<VEC, JB>(acc, ld, partial + (int64_t)j0 * partial_stride, partial_stride);
-}
-
-template <typename T>
-__global__ void finalize_multi_kernel(const double* __restrict__ partial, int64_t partial_stride,
-                                      int grid, int ld, int nq, T* __restrict__ h) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nq * ld) return;
-  const int j = idx / ld, c = idx % ld;
-  double s = 0.0;
-  const double* p = partial + (int64_t)j * partial_stride;
-  for (int b = 0; b < grid; ++b) s += p[(int64_t)b * ld + c];
-  h[(int64_t)j * ld + c] = (T)s;
+  cta_reduce_finalize<T, VEC, JB>(acc, ld, partial, partial_stride, nj, fin);
 }
 
 template <typename T, int VEC, bool NORM>
 __global__ void __launch_bounds__(kBlock)
 reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ h,
-                     T* __restrict__ V, int64_t total, int ld, double* __restrict__ partial) {
+                     T* __restrict__ V, int64_t total, int ld, double* __restrict__ partial,
+                     Finalize fin) {
   extern __shared__ unsigned char smem_raw[];
   T* hs = reinterpret_cast<T*>(smem_raw);  // [nq][ld]
   for (int i = threadIdx.x; i < nq * ld; i += kBlock) hs[i] = h[i];
@@ -210,7 +181,7 @@ reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T*
     }
     store_chunk<T, VEC>(V, f, v);
   }
-  if (NORM) cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+  if (NORM) cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
 }
 
 template <typename T, int VEC>
@@ -305,50 +276,46 @@ inline int vec_for(int32_t dtype, int64_t ld) {
     }                                                      \
   } while (0)
 
+// one wave of CTAs, each looping over flat 16-byte chunks
+#define MF_STREAM_GRID(kern, total, vec) \
+  resident_grid((const void*)(kern), kBlock, 0, ((total) + (int64_t)kBlock * (vec)-1) / ((int64_t)kBlock * (vec)))
+
 int32_t launch_dot(const void* X, const void* sx, const void* Y, int32_t dtype, int64_t n,
-                   int64_t ld, double* partial, int* grid_out, cudaStream_t st) {
+                   int64_t ld, const Reduce& red, cudaStream_t st) {
   MF_KSCOPE(MF_KC_DOT, st);
   const int64_t total = n * ld;
-  const int grid = reduce_grid(total, vec_for(dtype, ld));
-  MF_DISPATCH_TV(dtype, ld, (dot_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
-                                (const T*)X, (const T*)sx, (const T*)Y, total, (int)ld, partial)));
-  *grid_out = grid;
+  MF_DISPATCH_TV(dtype, ld, {
+    auto kern = dot_kernel<T, VEC>;
+    const int grid = MF_STREAM_GRID(kern, total, VEC);
+    kern<<<grid, kBlock, 0, st>>>((const T*)X, (const T*)sx, (const T*)Y, total, (int)ld,
+                                  red.partial, red.fin);
+  });
   return check_launch("dot");
-}
-
-int32_t launch_finalize(const double* partial, int grid, int64_t ld, int32_t dtype, int mode,
-                        void* value_out, void* inv_out, double* dbl_out, cudaStream_t st) {
-  MF_KSCOPE(MF_KC_FINALIZE, st);
-  const int threads = 128;
-  const int blocks = (int)((ld + threads - 1) / threads);
-  if (dtype == MF_F32)
-    finalize_kernel<float><<<blocks, threads, 0, st>>>(partial, grid, (int)ld, mode,
-                                                       (float*)value_out, (float*)inv_out, dbl_out);
-  else
-    finalize_kernel<double><<<blocks, threads, 0, st>>>(
-        partial, grid, (int)ld, mode, (double*)value_out, (double*)inv_out, dbl_out);
-  return check_launch("finalize");
 }
 
 int32_t launch_lanczos_update(const void* W, const void* Rc, const void* sc, const void* a,
                               const void* Rp, const void* sp, const void* bprev, void* out,
-                              int32_t dtype, int64_t n, int64_t ld, double* partial,
-                              int* grid_out, cudaStream_t st) {
+                              int32_t dtype, int64_t n, int64_t ld, const Reduce& red,
+                              cudaStream_t st) {
   MF_KSCOPE(MF_KC_LANCZOS_UPDATE, st);
   const int64_t total = n * ld;
-  const int grid = reduce_grid(total, vec_for(dtype, ld));
   if (Rp != nullptr) {
-    MF_DISPATCH_TV(dtype, ld,
-                   (lanczos_update_kernel<T, VEC, true><<<grid, kBlock, 0, st>>>(
-                       (const T*)W, (const T*)Rc, (const T*)sc, (const T*)a, (const T*)Rp,
-                       (const T*)sp, (const T*)bprev, (T*)out, total, (int)ld, partial)));
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = lanczos_update_kernel<T, VEC, true>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)W, (const T*)Rc, (const T*)sc, (const T*)a,
+                                    (const T*)Rp, (const T*)sp, (const T*)bprev, (T*)out, total,
+                                    (int)ld, red.partial, red.fin);
+    });
   } else {
-    MF_DISPATCH_TV(dtype, ld,
-                   (lanczos_update_kernel<T, VEC, false><<<grid, kBlock, 0, st>>>(
-                       (const T*)W, (const T*)Rc, (const T*)sc, (const T*)a, nullptr, nullptr,
-                       nullptr, (T*)out, total, (int)ld, partial)));
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = lanczos_update_kernel<T, VEC, false>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)W, (const T*)Rc, (const T*)sc, (const T*)a, nullptr,
+                                    nullptr, nullptr, (T*)out, total, (int)ld, red.partial,
+                                    red.fin);
+    });
   }
-  *grid_out = grid;
   return check_launch("lanczos_update");
 }
 
@@ -356,69 +323,67 @@ int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t 
                      int64_t n, int64_t ld, cudaStream_t st) {
   MF_KSCOPE(MF_KC_SCALE, st);
   const int64_t total = n * ld;
-  const int vec = vec_for(dtype, ld);
-  int64_t want = (total + (int64_t)kBlock * vec - 1) / ((int64_t)kBlock * vec);
-  int64_t cap = (int64_t)num_sms() * 8;
-  const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-  MF_DISPATCH_TV(dtype, ld, (scale_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
-                                (const T*)X, (const T*)s, (T*)out, mode, total, (int)ld)));
+  MF_DISPATCH_TV(dtype, ld, {
+    auto kern = scale_kernel<T, VEC>;
+    const int grid = MF_STREAM_GRID(kern, total, VEC);
+    kern<<<grid, kBlock, 0, st>>>((const T*)X, (const T*)s, (T*)out, mode, total, (int)ld);
+  });
   return check_launch("scale");
 }
 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
-                           int64_t ld, double* partial, void* h_out, cudaStream_t st) {
+                           int64_t ld, double* partial, unsigned int* counter, void* h_out,
+                           cudaStream_t st) {
   MF_KSCOPE(MF_KC_REORTH_DOTS, st);
   const int64_t total = n * ld;
-  const int grid = reduce_grid(total, vec_for(dtype, ld));
-  const int64_t pstride = (int64_t)grid * ld;
+  const int64_t pstride = (int64_t)kMaxPartialCtas * ld;
   constexpr int JB = 4;
   for (int64_t j0 = 0; j0 < nq; j0 += JB) {
     const int nj = (int)((nq - j0) < JB ? (nq - j0) : JB);
-    MF_DISPATCH_TV(dtype, ld,
-                   (reorth_dots_kernel<T, VEC, JB><<<grid, kBlock, 0, st>>>(
-                       (const T*)Q, total, (int)j0, nj, (const T*)V, total, (int)ld, partial,
-                       pstride)));
+    Finalize fin{counter, 0, (char*)h_out + j0 * ld * (int64_t)dtype_size(dtype), nullptr, nullptr};
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = reorth_dots_kernel<T, VEC, JB>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)Q, total, (int)j0, nj, (const T*)V, total, (int)ld,
+                                    partial, pstride, fin);
+    });
     MF_TRY(check_launch("reorth_dots"));
   }
-  // the kernel writes JB rows per launch; rows >= nq of the last group hold zeros
-  const int threads = 128;
-  const int blocks = (int)((nq * ld + threads - 1) / threads);
-  if (dtype == MF_F32)
-    finalize_multi_kernel<float><<<blocks, threads, 0, st>>>(partial, pstride, grid, (int)ld,
-                                                             (int)nq, (float*)h_out);
-  else
-    finalize_multi_kernel<double><<<blocks, threads, 0, st>>>(partial, pstride, grid, (int)ld,
-                                                              (int)nq, (double*)h_out);
-  return check_launch("reorth_dots_finalize");
+  return MF_OK;
 }
 
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
-                             int64_t n, int64_t ld, double* partial, int* grid_out,
-                             cudaStream_t st) {
+                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st) {
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
-  const int grid = reduce_grid(total, vec_for(dtype, ld));
   const size_t smem = (size_t)nq * ld * dtype_size(dtype);
-  if (smem > 200 * 1024) {
+  if (smem > 160 * 1024) {
     set_error("reorth_update: %lld basis vectors x %lld probes exceed the shared-memory budget; "
               "use a narrower tile", (long long)nq, (long long)ld);
     return MF_ERR_UNSUPPORTED;
   }
+  Finalize fin{};
+  double* partial = nullptr;
+  if (red) {
+    fin = red->fin;
+    partial = red->partial;
+  }
 #define MF_RU(NORM)                                                                           \
   MF_DISPATCH_TV(dtype, ld, {                                                                 \
     auto kern = reorth_update_kernel<T, VEC, NORM>;                                           \
-    if (smem > 48 * 1024)                                                                     \
+    if (smem > 40 * 1024)                                                                     \
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    const int grid = resident_grid((const void*)kern, kBlock, smem,                       \
+                                   (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC)); \
     kern<<<grid, kBlock, smem, st>>>((const T*)Q, total, (int)nq, (const T*)h, (T*)V, total,  \
-                                     (int)ld, partial);                                       \
+                                     (int)ld, partial, fin);                                  \
   })
-  if (partial != nullptr) {
+  if (red != nullptr) {
     MF_RU(true);
   } else {
     MF_RU(false);
   }
 #undef MF_RU
-  if (grid_out) *grid_out = grid;
   return check_launch("reorth_update");
 }
 
@@ -427,10 +392,12 @@ int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scal
                              cudaStream_t st) {
   MF_KSCOPE(MF_KC_OTHER, st);
   const int64_t total = n * ld;
-  const int grid = reduce_grid(total, vec_for(dtype, ld));
-  MF_DISPATCH_TV(dtype, ld, (basis_combine_kernel<T, VEC><<<grid, kBlock, 0, st>>>(
-                                (const T*)Q, total, (int)k, (const T*)coeffs, (const T*)scale,
-                                (T*)out, total, (int)ld)));
+  MF_DISPATCH_TV(dtype, ld, {
+    auto kern = basis_combine_kernel<T, VEC>;
+    const int grid = MF_STREAM_GRID(kern, total, VEC);
+    kern<<<grid, kBlock, 0, st>>>((const T*)Q, total, (int)k, (const T*)coeffs, (const T*)scale,
+                                  (T*)out, total, (int)ld);
+  });
   return check_launch("basis_combine");
 }
 

@@ -52,7 +52,7 @@ int num_sms();
 
 // ---------------------------------------------------------------- device helpers
 constexpr int kBlock = 256;          // threads per CTA of all block-vector kernels
-constexpr int kMaxPartialCtas = 2048;  // upper bound on the grid of reducing kernels
+constexpr int kMaxPartialCtas = 1280;  // upper bound on the grid of reducing kernels
 
 template <typename T>
 struct Vec;  // 16-byte vector of T
@@ -132,6 +132,55 @@ __device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int
     partial[a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
   }
   __syncthreads();
+}
+
+// What the LAST CTA of a reducing kernel does with the column sums ("fused
+// finalize"): every CTA writes its partial row, takes a ticket on `counter`, and
+// the CTA that draws the last ticket adds the partial rows in the fixed order
+// b = 0 .. gridDim.x-1 (so the result does not depend on which CTA finishes
+// last) and writes the scalars the next kernel needs.  The counter is reset by
+// that CTA, so one zero-initialised counter serves a whole stream of launches.
+struct Finalize {
+  unsigned int* counter;  // device; 0 before the launch
+  int mode;               // 0: value = sum ; 1: value = sqrt(sum), inv = 1 / value
+  void* value;            // T[nacc][ld] (row a at value + a*ld), may be null
+  void* inv;              // T[ld], mode 1 only, may be null
+  double* dbl;            // optional double[nacc][ld]: the fp64 sums
+};
+
+template <typename T, int VEC, int NACC = 1>
+__device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], int ld,
+                                                    double* __restrict__ partial,
+                                                    int64_t partial_stride, int nacc_live,
+                                                    const Finalize& fin) {
+  cta_reduce_columns<VEC, NACC>(acc, ld, partial, partial_stride);
+  if (fin.counter == nullptr) return;
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(fin.counter, 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int grid = gridDim.x;
+  for (int idx = threadIdx.x; idx < nacc_live * ld; idx += kBlock) {
+    const int a = idx / ld, c = idx % ld;
+    const double* p = partial + a * partial_stride + c;
+    double s = 0.0;
+    for (int b = 0; b < grid; ++b) s += __ldcg(p + (int64_t)b * ld);
+    if (fin.dbl) fin.dbl[(int64_t)a * ld + c] = s;
+    if (fin.mode == 0) {
+      if (fin.value) reinterpret_cast<T*>(fin.value)[(int64_t)a * ld + c] = (T)s;
+    } else {
+      const T v = (T)sqrt(s);
+      if (fin.value) reinterpret_cast<T*>(fin.value)[(int64_t)a * ld + c] = v;
+      if (fin.inv) reinterpret_cast<T*>(fin.inv)[(int64_t)a * ld + c] = T(1) / v;
+    }
+  }
+  if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
 }  // namespace mf

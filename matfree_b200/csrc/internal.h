@@ -5,45 +5,52 @@
 
 namespace mf {
 
-// grid used by all reducing block-vector kernels for a problem of `total`
-// elements processed `per_cta_sweep` elements per CTA sweep.
-int reduce_grid(int64_t total_elems, int vec);
+// Number of CTAs of `kernel` (block size `block`, `smem` dynamic bytes) that are
+// co-resident on the device, capped at `want` and at kMaxPartialCtas.  Reducing
+// and streaming kernels are launched with exactly this many CTAs (one wave) and
+// loop over their work, so work assignment is sequential in memory.
+int resident_grid(const void* kernel, int block, size_t smem, int64_t want);
+
+// A reduction request handed to the reducing launchers: the per-CTA partial rows
+// plus what the last CTA writes (common.cuh, `Finalize`).
+struct Reduce {
+  double* partial;  // double[nacc][kMaxPartialCtas * ld]
+  Finalize fin;
+};
+inline int64_t partial_bytes(int64_t ld, int nacc = 1) {
+  return (int64_t)nacc * kMaxPartialCtas * ld * 8;
+}
 
 // ---- probe_gen.cu
+// red (optional): column sums of squares -> red->fin (mode 1: |probe|, 1/|probe|)
 int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
                          int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
-                         int32_t sampler, int32_t prng_flags, double* partial,
-                         double* sqnorm_out, cudaStream_t st);
+                         int32_t sampler, int32_t prng_flags, const Reduce* red,
+                         cudaStream_t st);
 
 // ---- blockvec.cu : all operate on blocked vectors X[n][ld]
-// partial buffers are double[kMaxPartialCtas * ld] (times nacc where noted)
-
-// out[c] = sum_r (X[r][c] * sx[c]) * Y[r][c]         (sx may be null)
+// sum_r (X[r][c] * sx[c]) * Y[r][c] -> red.fin         (sx may be null)
 int32_t launch_dot(const void* X, const void* sx, const void* Y, int32_t dtype, int64_t n,
-                   int64_t ld, double* partial, int* grid_out, cudaStream_t st);
-// reduce partial[grid][ld] -> value (dtype) ; mode 0: value = sum ; mode 1: value = sqrt(sum),
-// inv = 1/value.  dbl_out (optional) gets the fp64 sum.
-int32_t launch_finalize(const double* partial, int grid, int64_t ld, int32_t dtype, int mode,
-                        void* value_out, void* inv_out, double* dbl_out, cudaStream_t st);
+                   int64_t ld, const Reduce& red, cudaStream_t st);
 // Lanczos three-term update (matfree/decomp.py:286-292, lazily normalised):
-//   out = (W - a * (Rc * sc)) - bprev * (Rp * sp);  partial <- column sums of out^2
+//   out = (W - a * (Rc * sc)) - bprev * (Rp * sp);  column sums of out^2 -> red.fin
 // Rp/bprev/sp may be null (first step).  out may alias Rp.
 int32_t launch_lanczos_update(const void* W, const void* Rc, const void* sc, const void* a,
                               const void* Rp, const void* sp, const void* bprev, void* out,
-                              int32_t dtype, int64_t n, int64_t ld, double* partial,
-                              int* grid_out, cudaStream_t st);
+                              int32_t dtype, int64_t n, int64_t ld, const Reduce& red,
+                              cudaStream_t st);
 // out = X * s (mode 0) or X / s (mode 1), per column; s may be null (copy)
 int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t dtype,
                      int64_t n, int64_t ld, cudaStream_t st);
 // CGS pass, dots: h[j][c] = sum_r Q[j][r][c] * V[r][c], j = 0..nq-1
-// (matfree/decomp.py:463,468).  partial: double[nq][kMaxPartialCtas*ld]
+// (matfree/decomp.py:463,468).  partial: double[4][kMaxPartialCtas*ld]
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
-                           int64_t ld, double* partial, void* h_out, cudaStream_t st);
+                           int64_t ld, double* partial, unsigned int* counter, void* h_out,
+                           cudaStream_t st);
 // CGS pass, update: V <- V - sum_j Q[j] * h[j]  (decomp.py:464,468); optional
-// column sums of the new V^2 into partial (norm fused).
+// column sums of the new V^2 -> red->fin (norm fused).
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
-                             int64_t n, int64_t ld, double* partial, int* grid_out,
-                             cudaStream_t st);
+                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st);
 // out[r][c] = scale[c] * sum_j Q[j][r][c] * coeff[j][c]
 int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scale,
                              int32_t dtype, int64_t n, int64_t ld, int64_t k, void* out,
@@ -55,11 +62,11 @@ int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dty
                             cudaStream_t st);
 
 // ---- spmm_csr.cu
-// W = s * (A @ X) per column (s may be null); if partial != null also
-// partial <- column sums of (X*s) * W   (the Lanczos alpha, decomp.py:288)
+// W = s * (A @ X) per column (s may be null); if red != null also the column sums
+// of (X*s) * W -> red->fin   (the Lanczos alpha, decomp.py:288)
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
-                        void* W, int64_t ld, double* partial, int* grid_out, cudaStream_t st);
+                        void* W, int64_t ld, const Reduce* red, cudaStream_t st);
 
 // ---- gemm.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)

@@ -89,7 +89,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
 probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int ld, int64_t p0, int num_probes,
                          uint32_t k0, uint32_t k1, int sampler, int flags,
-                         double* __restrict__ partial) {
+                         double* __restrict__ partial, Finalize fin) {
   const int64_t total = n * (int64_t)ld;
   const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
   double acc[1][VEC];
@@ -120,7 +120,7 @@ probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int ld, int64_t p0, int
       out[f] = v[0];
     }
   }
-  if (partial != nullptr) cta_reduce_columns<VEC, 1>(acc, ld, partial, 0);
+  if (partial != nullptr) cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
 }
 
 // Reference layout (P, n): out[p * ld + r]
@@ -139,20 +139,10 @@ probe_gen_pn_kernel(T* __restrict__ out, int64_t n, int64_t ld, int64_t p0, int6
 
 }  // namespace
 
-int reduce_grid(int64_t total_elems, int vec) {
-  const int64_t per_cta = (int64_t)kBlock * vec;
-  int64_t want = (total_elems + per_cta - 1) / per_cta;
-  int64_t cap = (int64_t)num_sms() * 8;
-  if (cap > kMaxPartialCtas) cap = kMaxPartialCtas;
-  if (want > cap) want = cap;
-  if (want < 1) want = 1;
-  return (int)want;
-}
-
 int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
                          int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
-                         int32_t sampler, int32_t prng_flags, double* partial,
-                         double* sqnorm_out, cudaStream_t st) {
+                         int32_t sampler, int32_t prng_flags, const Reduce* red,
+                         cudaStream_t st) {
   MF_KSCOPE(MF_KC_PROBE_GEN, st);
   if (n <= 0 || num_probes <= 0) return MF_OK;
   if (layout == MF_LAYOUT_BLOCKED) {
@@ -161,32 +151,24 @@ int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, in
       return MF_ERR_INVALID_ARGUMENT;
     }
     const int64_t total = n * ld;
-    int grid;
+    double* partial = red ? red->partial : nullptr;
+    Finalize fin{};
+    if (red) fin = red->fin;
+#define MF_PG(T, VEC)                                                                          \
+  do {                                                                                         \
+    auto kern = probe_gen_blocked_kernel<T, VEC>;                                              \
+    const int grid = resident_grid((const void*)kern, kBlock, 0,                               \
+                                   (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC)); \
+    kern<<<grid, kBlock, 0, st>>>((T*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, \
+                                  prng_flags, partial, fin);                                   \
+  } while (0)
     if (dtype == MF_F32) {
-      if (ld >= 4) {
-        grid = reduce_grid(total, 4);
-        probe_gen_blocked_kernel<float, 4><<<grid, kBlock, 0, st>>>(
-            (float*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, prng_flags, partial);
-      } else {
-        grid = reduce_grid(total, 1);
-        probe_gen_blocked_kernel<float, 1><<<grid, kBlock, 0, st>>>(
-            (float*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, prng_flags, partial);
-      }
+      if (ld >= 4) MF_PG(float, 4); else MF_PG(float, 1);
     } else {
-      if (ld >= 2) {
-        grid = reduce_grid(total, 2);
-        probe_gen_blocked_kernel<double, 2><<<grid, kBlock, 0, st>>>(
-            (double*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, prng_flags, partial);
-      } else {
-        grid = reduce_grid(total, 1);
-        probe_gen_blocked_kernel<double, 1><<<grid, kBlock, 0, st>>>(
-            (double*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, prng_flags, partial);
-      }
+      if (ld >= 2) MF_PG(double, 2); else MF_PG(double, 1);
     }
-    MF_TRY(check_launch("probe_gen_blocked"));
-    if (partial != nullptr && sqnorm_out != nullptr)
-      MF_TRY(launch_finalize(partial, grid, ld, MF_F64, 0, sqnorm_out, nullptr, nullptr, st));
-    return MF_OK;
+#undef MF_PG
+    return check_launch("probe_gen_blocked");
   }
   if (layout == MF_LAYOUT_PROBE_MAJOR) {
     if (ld < n) {
