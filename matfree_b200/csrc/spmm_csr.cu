@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(kBlock)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, int ld, int ld_shift,
-                int rows_per_chunk, double* __restrict__ partial, Finalize fin) {
+                int rows_per_chunk, int prefetch, double* __restrict__ partial, Finalize fin) {
   __shared__ int32_t s_ptr[kMaxRows + 1];
   __shared__ int32_t s_col[kCap];
   __shared__ T s_val[kCap];
@@ -81,6 +81,19 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     const int64_t r0 = ch * rows_per_chunk;
     const int nr = (int)((n - r0) < rows_per_chunk ? (n - r0) : rows_per_chunk);
     __syncthreads();  // the previous chunk's readers are done with the staging buffers
+    if (prefetch) {
+      // Pull the rows of X this CTA will own in its NEXT chunk into L2 now: one window of
+      // gridDim.x chunks ahead of the demand gathers, with no registers tied up, so the
+      // gathers below (own rows and stencil neighbours alike) find their lines in L2.
+      const int64_t pr0 = r0 + (int64_t)gridDim.x * rows_per_chunk;
+      if (pr0 < n) {
+        const int64_t pnr = (n - pr0) < rows_per_chunk ? (n - pr0) : rows_per_chunk;
+        const char* pbase = reinterpret_cast<const char*>(X + (pr0 << ld_shift));
+        const int64_t pbytes = (pnr << ld_shift) * (int64_t)sizeof(T);
+        for (int64_t o = (int64_t)threadIdx.x * 128; o < pbytes; o += (int64_t)kBlock * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase + o));
+      }
+    }
     for (int i = threadIdx.x; i <= nr; i += kBlock) s_ptr[i] = __ldg(indptr + r0 + i);
     __syncthreads();
     const int32_t base = s_ptr[0];
@@ -195,6 +208,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   // staging buffer on average, at most kMaxRows.
   static const int env_rows = env_int("MF_SPMM_ROWS", 0);
   static const int env_group = env_int("MF_SPMM_GROUP", 0);
+  static const int env_prefetch = env_int("MF_SPMM_PREFETCH", 1);
   const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   int64_t R = env_rows > 0 ? env_rows : 64;
   const int64_t fit = (int64_t)(kCap / (avg > 1.0 ? avg : 1.0));
@@ -217,14 +231,14 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
       auto kern = spmm_csr_kernel<T, VEC, G, true>;                                            \
       const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                   \
       kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,           \
-                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R, partial,    \
-                                    fin);                                                      \
+                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R,             \
+                                    env_prefetch, partial, fin);                                                    \
     } else {                                                                                   \
       auto kern = spmm_csr_kernel<T, VEC, G, false>;                                           \
       const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                   \
       kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,           \
-                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R, nullptr,    \
-                                    fin);                                                      \
+                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R,             \
+                                    env_prefetch, nullptr, fin);                                                    \
     }                                                                                          \
   } while (0)
 #define MF_SPMM(T, VEC)                                 \
