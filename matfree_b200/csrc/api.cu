@@ -147,12 +147,13 @@ int32_t validate_op(const mf_operator_t* op) {
 // W = s * (A @ X); if red != null and the operator can fuse it, also the column
 // sums of (X*s) .* W -> red->fin.  *fused tells the caller whether it happened.
 int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W, int64_t ld,
-                 void* gram_scratch, const Reduce* red, bool* fused, cudaStream_t st) {
+                 void* gram_scratch, const Reduce* red, unsigned int* tickets, bool* fused,
+                 cudaStream_t st) {
   *fused = false;
   switch (op->kind) {
     case MF_OP_CSR:
       MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X,
-                             s, W, ld, red, st));
+                             s, W, ld, red, tickets, st));
       *fused = red != nullptr;
       return MF_OK;
     case MF_OP_DENSE:
@@ -251,7 +252,7 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have
     void* aj = row(alphas, j, ld, dt);
     const Reduce red_a{b.partial, Finalize{b.counter, 0, aj, nullptr, nullptr}};
     bool fused = false;
-    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, &red_a, &fused, st));
+    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, &red_a, b.counter + 8, &fused, st));
     if (!fused) MF_TRY(launch_dot(X, sx, b.W, dt, n, ld, red_a, st));
     // pick the output buffer: alias Rp when we own it
     void* out;
@@ -296,7 +297,7 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     void* Qi = (char*)Q + i * blk;
     MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
     bool fused = false;
-    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, &fused, st));  // :460
+    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, b.counter + 8, &fused, st));  // :460
     MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st));  // :463
     if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
@@ -384,7 +385,7 @@ int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, v
     return MF_ERR_INVALID_ARGUMENT;
   }
   bool fused;
-  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, &fused, (cudaStream_t)stream);
+  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, nullptr, &fused, (cudaStream_t)stream);
 }
 
 int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
@@ -644,7 +645,7 @@ int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
       void* dst = np == ld ? q_tile : e.len;
       const Reduce red{e.lb.partial, Finalize{e.lb.counter, 0, dst, nullptr, nullptr}};
       bool fused = false;
-      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, &red, &fused, st));
+      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, &red, e.lb.counter + 8, &fused, st));
       if (!fused) MF_TRY(launch_dot(e.Z, nullptr, e.lb.W, dt, op->n, ld, red, st));
       if (np != ld &&
           cudaMemcpyAsync(q_tile, e.len, np * es, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {

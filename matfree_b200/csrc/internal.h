@@ -63,10 +63,13 @@ int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dty
 
 // ---- spmm_csr.cu
 // W = s * (A @ X) per column (s may be null); if red != null also the column sums
-// of (X*s) * W -> red->fin   (the Lanczos alpha, decomp.py:288)
+// of (X*s) * W -> red->fin   (the Lanczos alpha, decomp.py:288).
+// tickets (optional): two zeroed unsigned ints; chunks of rows are then handed out in
+// global row order (re-armed by the kernel itself).
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
-                        void* W, int64_t ld, const Reduce* red, cudaStream_t st);
+                        void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
+                        cudaStream_t st);
 
 // ---- gemm.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)

@@ -5,21 +5,30 @@
 // The user matvec of the reference (matfree/stochtrace.py:47-49) has no sparse
 // implementation; under vmap XLA would gather per probe.  Here all probes of a
 // tile advance together: a group of ld/VEC threads owns one row, every
-// non-zero costs one 16-byte load per thread of the contiguous segment
+// non-zero costs one 16-byte copy per thread of the contiguous segment
 // X[col][c0..c0+VEC), i.e. ld*sizeof(T) contiguous bytes per non-zero per row
 // (1 KB at ld = 256).
 //
-// Structure (one wave of persistent CTAs, sequential chunks of rows):
-//   * a CTA takes chunks of R consecutive rows; the CSR metadata of a chunk
-//     (R+1 row pointers, then the contiguous slice of column indices / values)
-//     is staged in shared memory with coalesced loads, so the only global loads
-//     on the per-row critical path are the gathers of X themselves;
-//   * per row the gathers are issued in predicated groups of G non-zeros, so a
-//     stencil row (5 or 7 non-zeros) has all its gathers in flight at once;
-//   * chunk c goes to CTA c % grid: at any time the CTAs work on one contiguous
-//     window of rows, which keeps the re-used rows of X (the +-1 and +-stride
-//     neighbours of a stencil) in L1/L2 and makes DRAM traffic ~ read X once,
-//     write W once, stream the matrix once.
+// Structure (measured on B200, profiles/: after the fixes below the kernel is bound by the
+// latency of the gathers -- not by issue, L2 or DRAM bandwidth):
+//   * one wave of persistent CTAs; a CTA takes chunks of R consecutive rows.
+//     Chunk c goes to CTA c % grid (static => the per-CTA reduction order is
+//     fixed => bit-reproducible results); a completed-chunk counter keeps every
+//     CTA within one window of the slowest, so the rows in flight are always one
+//     contiguous window and the stencil neighbours of a row stay in L2 between
+//     their uses (measured: DRAM reads drop from 1.6x to 1.0x of the algorithmic
+//     bytes; without it the CTAs drift apart by more than the L2 can hold);
+//   * the CSR metadata of the NEXT chunks (row pointers two chunks ahead, column
+//     indices / values one chunk ahead) streams into multi-buffered shared
+//     memory with cp.async while the current chunk is processed, so the only
+//     global loads on the per-row critical path are the gathers of X themselves;
+//   * per row all gathers (a whole 5- or 7-point stencil row) are issued
+//     back to back into registers before the first FMA, one IMAD.WIDE + one
+//     LDG.128 per non-zero (tile width is a template constant).
+// Variants that were measured and rejected (tools/gpu_run*.sh, profiles/README.md):
+// dynamic chunk tickets (same speed, not reproducible), a cp.async ring in shared
+// memory as the landing zone (2x the instructions, fewer warps: slower), register
+// software pipelining across rows (spills), L1/L2 software prefetch (no gain).
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -29,9 +38,26 @@
 namespace mf {
 namespace {
 
-constexpr int kCap = 2048;      // non-zeros of a chunk staged in shared memory
-constexpr int kMaxRows = 256;   // rows per chunk, upper bound
+constexpr int kCap = 1024;     // non-zeros of a chunk staged in shared memory
+constexpr int kMaxRows = 256;  // rows per chunk, upper bound
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t saddr, const void* g) {
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+  } else if constexpr (BYTES == 8) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 template <typename T, int VEC>
 __device__ __forceinline__ void ldx(const T* __restrict__ X, int64_t off, T (&v)[VEC]) {
   if constexpr (VEC == 1) {
@@ -55,20 +81,71 @@ __device__ __forceinline__ void stw(T* __restrict__ W, int64_t off, const T (&v)
   }
 }
 
-template <typename T, int VEC, int G, bool FUSE_DOT>
-__global__ void __launch_bounds__(kBlock)
+struct SpmmParams {
+  int ld;              // tile width (power of two)
+  int rows_per_chunk;  // R, a multiple of the CTA sweep
+  int prefetch;        // L2 prefetch of the rows one window ahead
+  int l1pf;            // L1 prefetch of the gathers of the row `l1pf` sweeps ahead (0 = off)
+  int window;          // throttle: a chunk may start when done + window > chunk
+};
+
+// The gathers of one row held in registers: up to SEGL non-zeros (a whole stencil row);
+// longer rows finish in a serial tail.
+template <typename T, int VEC, int SEGL>
+struct RowRegs {
+  T x[SEGL][VEC];
+  int jb, len;
+};
+
+template <typename T, int VEC, int SEGL>
+__device__ __forceinline__ void issue_row(const int32_t* __restrict__ ptrb, int32_t base,
+                                          const int32_t* __restrict__ colb,
+                                          const T* __restrict__ Xc, int ld, int lr,
+                                          RowRegs<T, VEC, SEGL>& r) {
+  r.jb = ptrb[lr] - base;
+  r.len = ptrb[lr + 1] - base - r.jb;
+  int32_t c[SEGL];
+#pragma unroll
+  for (int u = 0; u < SEGL; ++u) c[u] = u < r.len ? colb[r.jb + u] : 0;
+#pragma unroll
+  for (int u = 0; u < SEGL; ++u)
+    if (u < r.len) ldx<T, VEC>(Xc, (int64_t)c[u] * ld, r.x[u]);
+}
+
+template <typename T, int VEC, int SEGL>
+__device__ __forceinline__ void prefetch_row_l1(const int32_t* __restrict__ ptrb, int32_t base,
+                                                const int32_t* __restrict__ colb,
+                                                const T* __restrict__ Xc, int ld, int lr) {
+  const int jb = ptrb[lr] - base;
+  const int len = ptrb[lr + 1] - base - jb;
+#pragma unroll
+  for (int u = 0; u < SEGL; ++u)
+    if (u < len)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(Xc + (int64_t)colb[jb + u] * ld));
+}
+
+// LD > 0: the tile width is a compile-time constant (address arithmetic folds into one
+// IMAD.WIDE per gather); LD == 0: any power of two, read from p.ld.
+// PIPE: the gathers of the next row are issued before the current row is multiplied.
+template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT>
+__global__ void __launch_bounds__(kBlock, PIPE ? 3 : 4)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
-                const T* __restrict__ s, T* __restrict__ W, int ld, int ld_shift,
-                int rows_per_chunk, int prefetch, double* __restrict__ partial, Finalize fin) {
-  __shared__ int32_t s_ptr[kMaxRows + 1];
-  __shared__ int32_t s_col[kCap];
-  __shared__ T s_val[kCap];
+                const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
+                unsigned int* __restrict__ progress, double* __restrict__ partial,
+                Finalize fin) {
+  __shared__ int32_t s_ptr[3][kMaxRows + 1];
+  __shared__ int32_t s_col[2][kCap];
+  __shared__ T s_val[2][kCap];
 
-  const int tpr = ld / VEC;   // threads per row
+  const int ld = LD > 0 ? LD : p.ld;
+  const int tpr = ld / VEC;      // threads per row
   const int rps = kBlock / tpr;  // rows per sweep of the CTA
   const int my_row = threadIdx.x / tpr;
   const int c0 = (threadIdx.x % tpr) * VEC;
+  const T* __restrict__ Xc = X + c0;
+  T* __restrict__ Wc = W + c0;
+  const int R = p.rows_per_chunk;
   T sv[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) sv[i] = s ? s[c0 + i] : T(1);
@@ -76,84 +153,172 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
 
-  const int64_t nchunks = (n + rows_per_chunk - 1) / rows_per_chunk;
-  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-    const int64_t r0 = ch * rows_per_chunk;
-    const int nr = (int)((n - r0) < rows_per_chunk ? (n - r0) : rows_per_chunk);
-    __syncthreads();  // the previous chunk's readers are done with the staging buffers
-    if (prefetch) {
-      // Pull the rows of X this CTA will own in its NEXT chunk into L2 now: one window of
-      // gridDim.x chunks ahead of the demand gathers, with no registers tied up, so the
-      // gathers below (own rows and stencil neighbours alike) find their lines in L2.
-      const int64_t pr0 = r0 + (int64_t)gridDim.x * rows_per_chunk;
+  const int64_t nchunks = (n + R - 1) / R;
+  const int64_t G = gridDim.x;
+
+  // ---- metadata pipeline (all threads): cp.async into multi-buffered shared memory --------
+  auto issue_ptr = [&](int64_t c, int buf) {  // row pointers of chunk c -> s_ptr[buf]
+    if (c < nchunks) {
+      const int64_t r0 = c * R;
+      const int nr = (int)((n - r0) < R ? (n - r0) : R);
+      for (int i = threadIdx.x; i <= nr; i += kBlock)
+        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf][i]), indptr + r0 + i);
+    }
+  };
+  auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
+    if (c < nchunks) {
+      const int64_t r0 = c * R;
+      const int nr = (int)((n - r0) < R ? (n - r0) : R);
+      const int32_t base = s_ptr[pbuf][0];
+      const int total = s_ptr[pbuf][nr] - base;
+      if (total <= kCap) {  // larger chunks read their entries straight from global memory
+        for (int i = threadIdx.x; i < total; i += kBlock) {
+          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_col[ebuf][i]), indices + base + i);
+          cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&s_val[ebuf][i]),
+                                   data + base + i);
+        }
+      }
+    }
+  };
+
+  // finish one row: scale, store, fused dot
+  auto finish_row = [&](T (&sum)[VEC], int64_t off) {
+    T w[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) w[i] = sum[i] * sv[i];
+    stw<T, VEC>(Wc, off, w);
+    if (FUSE_DOT) {
+      T xo[VEC];
+      ldx<T, VEC>(Xc, off, xo);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[0][i] += (double)(xo[i] * sv[i]) * (double)w[i];
+    }
+  };
+
+  int64_t ch = blockIdx.x;
+  issue_ptr(ch, 0);
+  issue_ptr(ch + G, 1);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  issue_ent(ch, 0, 0);
+  cp_async_commit();
+  cp_async_wait<0>();
+
+  unsigned int seen_done = 0;  // thread 0: last value read from progress[0]
+  for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
+    const int pb = (int)(t % 3), eb = (int)(t & 1);
+    // Throttle: do not run more than `window` chunks ahead of the completed count.
+    if (progress != nullptr && threadIdx.x == 0) {
+      while ((int64_t)seen_done + p.window <= ch) {
+        seen_done = *reinterpret_cast<volatile unsigned int*>(progress);
+        if ((int64_t)seen_done + p.window <= ch) __nanosleep(200);
+      }
+    }
+    __syncthreads();  // metadata of chunk t visible; everyone is done with chunk t-1
+    if (progress != nullptr && threadIdx.x == 0 && t > 0) atomicAdd(progress, 1u);
+    // stream in the metadata of the next chunks while this one is processed
+    issue_ent(ch + G, (int)((t + 1) % 3), (int)((t + 1) & 1));
+    issue_ptr(ch + 2 * G, (int)((t + 2) % 3));
+    cp_async_commit();
+
+    const int64_t r0 = ch * R;
+    const int nr = (int)((n - r0) < R ? (n - r0) : R);
+    if (p.prefetch) {
+      const int64_t pr0 = r0 + G * R;
       if (pr0 < n) {
-        const int64_t pnr = (n - pr0) < rows_per_chunk ? (n - pr0) : rows_per_chunk;
-        const char* pbase = reinterpret_cast<const char*>(X + (pr0 << ld_shift));
-        const int64_t pbytes = (pnr << ld_shift) * (int64_t)sizeof(T);
+        const int64_t pnr = (n - pr0) < R ? (n - pr0) : R;
+        const char* pbase = reinterpret_cast<const char*>(X + pr0 * ld);
+        const int64_t pbytes = pnr * ld * (int64_t)sizeof(T);
         for (int64_t o = (int64_t)threadIdx.x * 128; o < pbytes; o += (int64_t)kBlock * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase + o));
       }
     }
-    for (int i = threadIdx.x; i <= nr; i += kBlock) s_ptr[i] = __ldg(indptr + r0 + i);
-    __syncthreads();
-    const int32_t base = s_ptr[0];
-    const int total = s_ptr[nr] - base;
-    const int cnt = total < kCap ? total : kCap;
-    for (int i = threadIdx.x; i < cnt; i += kBlock) {
-      s_col[i] = __ldg(indices + base + i);
-      s_val[i] = __ldg(data + base + i);
-    }
-    __syncthreads();
+    const int32_t* __restrict__ ptrb = s_ptr[pb];
+    const int32_t base = ptrb[0];
+    const int total = ptrb[nr] - base;
+    const int32_t* __restrict__ colb = s_col[eb];
+    const T* __restrict__ valb = s_val[eb];
+    const int64_t coff = r0 * ld;
 
-    for (int lr = my_row; lr < nr; lr += rps) {
-      const int jb = s_ptr[lr] - base, je = s_ptr[lr + 1] - base;
-      const int js = je < kCap ? je : kCap;  // end of the staged part of this row
-      T sum[VEC];
+    if (total > kCap) {
+      // oversized chunk (very long rows): plain serial loop over global metadata
+      for (int lr = my_row; lr < nr; lr += rps) {
+        T sum[VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) sum[i] = T(0);
-      for (int j = jb; j < js; j += G) {
-        int32_t c[G];
-        T a[G];
+        for (int i = 0; i < VEC; ++i) sum[i] = T(0);
+        for (int j = ptrb[lr]; j < ptrb[lr + 1]; ++j) {
+          const int32_t c = __ldg(indices + j);
+          const T a = __ldg(data + j);
+          T x[VEC];
+          ldx<T, VEC>(Xc, (int64_t)c * ld, x);
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-          const bool ok = j + u < js;
-          c[u] = ok ? s_col[j + u] : -1;
-          a[u] = ok ? s_val[j + u] : T(0);
+          for (int i = 0; i < VEC; ++i) sum[i] += a * x[i];
         }
-        T x[G][VEC];
+        finish_row(sum, coff + (int64_t)lr * ld);
+      }
+    } else {
+      // multiply the gathers held in r (and the serial tail of a long row)
+      auto consume = [&](RowRegs<T, VEC, SEGL>& r, int lr) {
+        T sum[VEC];
 #pragma unroll
-        for (int u = 0; u < G; ++u) {
-          if (c[u] >= 0) {
-            ldx<T, VEC>(X, ((int64_t)c[u] << ld_shift) + c0, x[u]);
-          } else {
+        for (int i = 0; i < VEC; ++i) sum[i] = T(0);
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) x[u][i] = T(0);
+        for (int u = 0; u < SEGL; ++u) {
+          if (u < r.len) {
+            const T a = valb[r.jb + u];
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) sum[i] += a * r.x[u][i];
           }
         }
+        for (int u = SEGL; u < r.len; ++u) {
+          const T a = valb[r.jb + u];
+          T x[VEC];
+          ldx<T, VEC>(Xc, (int64_t)colb[r.jb + u] * ld, x);
 #pragma unroll
-        for (int u = 0; u < G; ++u)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) sum[i] += a[u] * x[u][i];
+          for (int i = 0; i < VEC; ++i) sum[i] += a * x[i];
+        }
+        finish_row(sum, coff + (int64_t)lr * ld);
+      };
+      if (PIPE) {
+        RowRegs<T, VEC, SEGL> ra, rb;
+        int lr = my_row;
+        if (lr < nr) issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra);
+        while (lr < nr) {
+          const int lr1 = lr + rps;
+          if (lr1 < nr) issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr1, rb);
+          consume(ra, lr);
+          if (lr1 >= nr) break;
+          const int lr2 = lr1 + rps;
+          if (lr2 < nr) issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr2, ra);
+          consume(rb, lr1);
+          lr = lr2;
+        }
+      } else {
+        for (int lr = my_row; lr < nr; lr += rps) {
+          RowRegs<T, VEC, SEGL> ra;
+          issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra);
+          if (p.l1pf) {
+            const int lp = lr + p.l1pf * rps;
+            if (lp < nr) prefetch_row_l1<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lp);
+          }
+          consume(ra, lr);
+        }
       }
-      // rows longer than the staging buffer: the rest straight from global memory
-      for (int j = (jb > kCap ? jb : kCap); j < je; ++j) {
-        const int32_t c = __ldg(indices + base + j);
-        const T a = __ldg(data + base + j);
-        T x[VEC];
-        ldx<T, VEC>(X, ((int64_t)c << ld_shift) + c0, x);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) sum[i] += a * x[i];
-      }
-      T w[VEC];
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) w[i] = sum[i] * sv[i];
-      const int64_t off = ((r0 + lr) << ld_shift) + c0;
-      stw<T, VEC>(W, off, w);
-      if (FUSE_DOT) {
-        T xo[VEC];
-        ldx<T, VEC>(X, off, xo);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[0][i] += (double)(xo[i] * sv[i]) * (double)w[i];
+    }
+    cp_async_wait<0>();  // next chunk's metadata landed
+  }
+  cp_async_wait<0>();
+  if (progress != nullptr) {
+    // count my last chunk; the last CTA to leave re-arms the counters for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (blockIdx.x < nchunks) atomicAdd(progress, 1u);
+      __threadfence();
+      const unsigned int left = atomicAdd(progress + 1, 1u);
+      if (left == gridDim.x - 1) {
+        progress[0] = 0u;
+        progress[1] = 0u;
       }
     }
   }
@@ -171,7 +336,7 @@ int resident_grid(const void* kernel, int block, size_t smem, int64_t want) {
   static std::mutex mu;
   static std::unordered_map<const void*, int> cache;
   int per_sm = 0;
-  {
+  if (smem == 0) {
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(kernel);
     if (it != cache.end()) per_sm = it->second;
@@ -196,63 +361,76 @@ int resident_grid(const void* kernel, int block, size_t smem, int64_t want) {
 
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
-                        void* W, int64_t ld, const Reduce* red, cudaStream_t st) {
+                        void* W, int64_t ld, const Reduce* red, unsigned int* progress,
+                        cudaStream_t st) {
   MF_KSCOPE(MF_KC_SPMM_CSR, st);
   if (n <= 0) return MF_OK;
   const int nv = dtype == MF_F64 ? 2 : 4;
   const int vec = ld >= nv ? nv : 1;
   const int rps = kBlock / (int)(ld / vec);
-  int ld_shift = 0;
-  while ((1ll << ld_shift) < ld) ++ld_shift;
+  static const int env_rows = env_int("MF_SPMM_ROWS", 0);
+  static const int env_prefetch = env_int("MF_SPMM_PREFETCH", 0);
+  static const int env_l1pf = env_int("MF_SPMM_L1PF", 0);
+  static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
+  static const int env_pipe = env_int("MF_SPMM_PIPE", 0);
+  static const int env_slack = env_int("MF_SPMM_SLACK", 0);
+  if (!env_throttle) progress = nullptr;
+  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   // rows per chunk: a multiple of the CTA sweep, sized so the chunk's non-zeros fit the
   // staging buffer on average, at most kMaxRows.
-  static const int env_rows = env_int("MF_SPMM_ROWS", 0);
-  static const int env_group = env_int("MF_SPMM_GROUP", 0);
-  static const int env_prefetch = env_int("MF_SPMM_PREFETCH", 1);
-  const double avg = n > 0 ? (double)nnz / (double)n : 1.0;
   int64_t R = env_rows > 0 ? env_rows : 64;
   const int64_t fit = (int64_t)(kCap / (avg > 1.0 ? avg : 1.0));
   if (R > fit) R = fit;
+  if (R > kMaxRows) R = kMaxRows;
   R = R / rps * rps;
-  if (R < rps) R = rps;
-  if (R > kMaxRows) R = kMaxRows / rps * rps;
-  if (R < 1 || R > kMaxRows) R = rps <= kMaxRows ? rps : kMaxRows;  // rps == 256 at ld == 1
+  if (R < rps) R = rps;  // rps <= 256 == kMaxRows
   const int64_t nchunks = (n + R - 1) / R;
-  const int group = env_group > 0 ? env_group : (avg > 4.5 ? 8 : 4);
   Finalize fin{};
   double* partial = nullptr;
   if (red) {
     fin = red->fin;
     partial = red->partial;
   }
-#define MF_SPMM_G(T, VEC, G)                                                                   \
+  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0};
+#define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
   do {                                                                                         \
-    if (red) {                                                                                 \
-      auto kern = spmm_csr_kernel<T, VEC, G, true>;                                            \
-      const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                   \
-      kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,           \
-                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R,             \
-                                    env_prefetch, partial, fin);                                                    \
-    } else {                                                                                   \
-      auto kern = spmm_csr_kernel<T, VEC, G, false>;                                           \
-      const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                   \
-      kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,           \
-                                    (const T*)s, (T*)W, (int)ld, ld_shift, (int)R,             \
-                                    env_prefetch, nullptr, fin);                                                    \
-    }                                                                                          \
+    auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT>;                                  \
+    const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                     \
+    prm.window = grid + (env_slack > 0 ? env_slack : (grid / 4 > 8 ? grid / 4 : 8));           \
+    kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,             \
+                                  (const T*)s, (T*)W, prm, progress, partial, fin);            \
   } while (0)
-#define MF_SPMM(T, VEC)                                 \
-  do {                                                  \
-    if (group >= 8) MF_SPMM_G(T, VEC, 8);               \
-    else MF_SPMM_G(T, VEC, 4);                          \
+#define MF_SPMM_D(T, VEC, LD, SEGL, PIPE)                     \
+  do {                                                        \
+    if (red) MF_SPMM_L(T, VEC, LD, SEGL, PIPE, true);         \
+    else MF_SPMM_L(T, VEC, LD, SEGL, PIPE, false);            \
+  } while (0)
+  // segment length: a whole row of a 5-point (2-D) or 7-point (3-D) stencil, else 8
+  const int segl = avg <= 5.0 ? 5 : (avg <= 7.0 ? 7 : 8);
+#define MF_SPMM_S(T, VEC, LD)                                           \
+  do {                                                                  \
+    if (segl == 5) {                                                    \
+      if (env_pipe) MF_SPMM_D(T, VEC, LD, 5, true);                     \
+      else MF_SPMM_D(T, VEC, LD, 5, false);                             \
+    } else if (segl == 7) {                                             \
+      MF_SPMM_D(T, VEC, LD, 7, false);                                  \
+    } else {                                                            \
+      MF_SPMM_D(T, VEC, LD, 8, false);                                  \
+    }                                                                   \
   } while (0)
   if (dtype == MF_F32) {
-    if (vec == 4) MF_SPMM(float, 4); else MF_SPMM(float, 1);
+    if (ld == 256) MF_SPMM_S(float, 4, 256);
+    else if (ld == 128) MF_SPMM_S(float, 4, 128);
+    else if (vec == 4) MF_SPMM_S(float, 4, 0);
+    else MF_SPMM_S(float, 1, 0);
   } else {
-    if (vec == 2) MF_SPMM(double, 2); else MF_SPMM(double, 1);
+    if (ld == 256) MF_SPMM_S(double, 2, 256);
+    else if (vec == 2) MF_SPMM_S(double, 2, 0);
+    else MF_SPMM_S(double, 1, 0);
   }
-#undef MF_SPMM
-#undef MF_SPMM_G
+#undef MF_SPMM_S
+#undef MF_SPMM_D
+#undef MF_SPMM_L
   return check_launch("spmm_csr");
 }
 
