@@ -1,0 +1,67 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): probe sharding over NCCL gives the
+same per-probe values and estimate as one GPU."""
+
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MF_ROOT"])
+import matfree_b200 as m
+from matfree_b200 import workloads
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+shape, P, k = (96, 96), 300, 12
+n = shape[0] * shape[1]
+ip, ix, d = workloads.laplacian_csr(shape, shift=1.0, device=f"cuda:{local}")
+op = m.ops.csr(ip, ix, d)
+key = m.prng.prng_key(7)
+sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1), (n,)), num=P)
+integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+est = m.stochtrace.estimator_monte_carlo_mean_and_sem(integrand, sampler)
+plain = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+single = plain.per_probe(op, key, tile=64)          # all probes on this GPU
+mean1, sem1 = est(op, key)
+with m.stochtrace.probe_sharding():
+    sharded = plain.per_probe(op, key, tile=64)     # my shard, all-gathered
+    mean2, sem2 = est(op, key)
+assert sharded.shape == single.shape == (P,)
+assert torch.equal(sharded, single), (sharded - single).abs().max()
+assert float(mean1) == float(mean2) and float(sem1) == float(sem2)
+# Hutchinson trace, sharded
+tr = m.stochtrace.estimator_monte_carlo(m.stochtrace.monte_carlo_trace(), sampler)
+t1 = float(tr(op, key))
+with m.stochtrace.probe_sharding():
+    t2 = float(tr(op, key))
+assert t1 == t2
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_probe_sharding_nccl_matches_single_gpu(tmp_path):
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MF_ROOT=ROOT)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == world
