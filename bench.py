@@ -227,6 +227,9 @@ def run_ours(a, rank, local_rank, world):
     lib = _lib.load()
     dist = None
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at level VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist  # noqa: F811
 
         dist.init_process_group("nccl", device_id=dev)
