@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 1
+#define MF_ABI_VERSION 2
 
 /* status codes */
 #define MF_OK 0
@@ -91,7 +91,10 @@ typedef struct mf_operator {
   const int32_t* indptr;  /* CSR only                                    */
   const int32_t* indices; /* CSR only                                    */
   int64_t lda;            /* DENSE/GRAM leading dimension (elements)     */
-  void* op_scratch;       /* GRAM: m*ld elements of dtype; else unused   */
+  const void* split_planes; /* DENSE/GRAM fp32, optional: TF32 planes [2][rows][lda]
+                             * of `values` made by mf_operator_split.  With them the
+                             * operator runs on the tcgen05 tensor cores (3xTF32);
+                             * without them on the CUDA-core kernel.                */
 } mf_operator_t;
 
 const char* mf_last_error(void);
@@ -132,17 +135,37 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
                      int32_t sampler, int32_t prng_flags, double* sqnorm_out,
                      void* stream);
 
+/* One-time preprocessing of an fp32 dense / Gram operator for the tensor-core
+ * path: the two TF32 planes of its matrix, hi = rna_tf32(A), lo = rna_tf32(A - hi),
+ * written to planes[2][rows][lda] (rows = n, or m for GRAM).  The fp32 product is
+ * then formed as A_hi X_hi + A_hi X_lo + A_lo X_hi with fp32 accumulation in TMEM
+ * ("3xTF32"), which is what replaces XLA's fp32 `dot_general` of the user matvec
+ * (matfree/stochtrace.py:47-49; tutorials/1_log_determinants.py:19-21).
+ * mf_operator_split_bytes returns 0 for operators that have no planes (CSR, fp64). */
+int64_t mf_operator_split_bytes(const mf_operator_t* op);
+/* Tuning / cross-check knob of the dense path (process-wide).  variant 0: 128-row
+ * tiles, 128-byte swizzle; variant 1: 256-row tiles (two TMEM accumulators), 64-byte
+ * swizzle.  use_tensor_cores = 0 routes dense / Gram operators to the CUDA-core
+ * kernel even when TF32 planes are present (used by the tests to cross-check). */
+int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores);
+int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
+
 /* The user matvec (matfree/stochtrace.py:47-49, funm.py:231-235,
  * decomp.py:163-164) applied to a whole probe block:
- * W[n][ld] = A @ X[n][ld] (blocked layout). */
-int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* stream);
-int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
-                        void* W, int64_t ld, void* stream);
+ * W[n][ld] = A @ X[n][ld] (blocked layout).  Dense and Gram operators need
+ * scratch (TF32 planes of X, the intermediate A X): mf_matmat_workspace_bytes. */
+int64_t mf_matmat_workspace_bytes(const mf_operator_t* op, int64_t ld);
+int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+int32_t mf_matmat_dense(const void* A, const void* A_planes, int64_t n, int64_t lda,
+                        int32_t dtype, const void* X, void* W, int64_t ld, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 int32_t mf_matmat_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                       int64_t n, int64_t nnz, int32_t dtype, const void* X, void* W,
                       int64_t ld, void* stream);
-int32_t mf_matmat_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
-                       const void* X, void* Y_scratch, void* W, int64_t ld, void* stream);
+int32_t mf_matmat_gram(const void* A, const void* A_planes, int64_t m, int64_t n, int64_t lda,
+                       int32_t dtype, const void* X, void* W, int64_t ld, void* workspace,
+                       int64_t workspace_bytes, void* stream);
 
 /* Layout helpers: probe-major (P, n) <-> blocked [n][ld]. */
 int32_t mf_to_blocked(const void* src_pn, void* dst_blocked, int32_t dtype, int64_t n,
@@ -203,8 +226,8 @@ int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
                     void* lens_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* Per-kind spellings of the fused estimator (what the per-kind FFI targets bind). */
-int32_t mf_slq_estimate_dense(const void* A, int64_t n, int64_t lda, int32_t dtype,
-                              int32_t sampler, int32_t prng_flags, uint32_t key0,
+int32_t mf_slq_estimate_dense(const void* A, const void* A_planes, int64_t n, int64_t lda,
+                              int32_t dtype, int32_t sampler, int32_t prng_flags, uint32_t key0,
                               uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
                               int64_t k, int32_t reortho, int32_t fn, double fn_param,
                               void* quad_out, void* workspace, int64_t workspace_bytes,
@@ -215,8 +238,8 @@ int32_t mf_slq_estimate_csr(const int32_t* indptr, const int32_t* indices, const
                             int64_t num_probes, int64_t ld, int64_t k, int32_t reortho,
                             int32_t fn, double fn_param, void* quad_out, void* workspace,
                             int64_t workspace_bytes, void* stream);
-int32_t mf_slq_estimate_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
-                             int32_t sampler, int32_t prng_flags, uint32_t key0,
+int32_t mf_slq_estimate_gram(const void* A, const void* A_planes, int64_t m, int64_t n,
+                             int64_t lda, int32_t dtype, int32_t sampler, int32_t prng_flags, uint32_t key0,
                              uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
                              int64_t k, int32_t reortho, int32_t fn, double fn_param,
                              void* quad_out, void* workspace, int64_t workspace_bytes,

@@ -32,7 +32,7 @@ class MfOperator(Structure):
         ("indptr", c_void_p),
         ("indices", c_void_p),
         ("lda", c_int64),
-        ("op_scratch", c_void_p),
+        ("split_planes", c_void_p),
     ]
 
 
@@ -46,13 +46,17 @@ SIGNATURES = {
     "mf_timing_collect": (c_int32, [c_void_p, c_void_p]),
     "mf_probe_gen": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64,
                                c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p]),
-    "mf_matmat": (c_int32, [_OP, c_void_p, c_void_p, c_int64, c_void_p]),
-    "mf_matmat_dense": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
-                                  c_int64, c_void_p]),
+    "mf_gemm_config": (c_int32, [c_int32, c_int32]),
+    "mf_operator_split_bytes": (c_int64, [_OP]),
+    "mf_operator_split": (c_int32, [_OP, c_void_p, c_void_p]),
+    "mf_matmat_workspace_bytes": (c_int64, [_OP, c_int64]),
+    "mf_matmat": (c_int32, [_OP, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mf_matmat_dense": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p,
+                                  c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "mf_matmat_csr": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int32,
                                 c_void_p, c_void_p, c_int64, c_void_p]),
-    "mf_matmat_gram": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_void_p,
-                                 c_void_p, c_void_p, c_int64, c_void_p]),
+    "mf_matmat_gram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "mf_to_blocked": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p]),
     "mf_from_blocked": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p]),
     "mf_lanczos_workspace_bytes": (c_int64, [_OP, c_int64, c_int64, c_int32, c_int32]),
@@ -67,7 +71,7 @@ SIGNATURES = {
     "mf_estimate": (c_int32, [_OP, c_int32, c_int32, c_int32, c_uint32, c_uint32, c_int64, c_int64,
                               c_int64, c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
-    "mf_slq_estimate_dense": (c_int32, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
+    "mf_slq_estimate_dense": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32,
                                         c_uint32, c_uint32, c_int64, c_int64, c_int64, c_int64,
                                         c_int32, c_int32, c_double, c_void_p, c_void_p, c_int64,
                                         c_void_p]),
@@ -75,7 +79,7 @@ SIGNATURES = {
                                       c_int32, c_int32, c_uint32, c_uint32, c_int64, c_int64,
                                       c_int64, c_int64, c_int32, c_int32, c_double, c_void_p,
                                       c_void_p, c_int64, c_void_p]),
-    "mf_slq_estimate_gram": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
+    "mf_slq_estimate_gram": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
                                        c_int32, c_uint32, c_uint32, c_int64, c_int64, c_int64,
                                        c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p,
                                        c_int64, c_void_p]),

@@ -2,6 +2,7 @@
 // (Lanczos loops, fused estimator) built from the kernels in this directory.
 // Nothing in this file synchronises, allocates or frees device memory.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -144,32 +145,83 @@ int32_t validate_op(const mf_operator_t* op) {
   }
 }
 
+// Scratch an operator application needs (carved from the caller's workspace).
+struct OpScratch {
+  void* gram;    // SIMT Gram path: Y = A X, m*ld elements
+  void* xsplit;  // tcgen05 path: TF32 planes of X, 2*n*ld floats
+  void* tsplit;  // tcgen05 Gram path: TF32 planes of A X, 2*m*ld floats
+};
+
+// Tuning knobs of the dense path (mf_gemm_config; environment MF_GEMM_VARIANT /
+// MF_GEMM_FORCE_SIMT give the initial values).
+std::atomic<int> g_gemm_variant{[] {
+  const char* e = getenv("MF_GEMM_VARIANT");
+  return e ? atoi(e) : 0;
+}()};
+std::atomic<int> g_gemm_tc{getenv("MF_GEMM_FORCE_SIMT") == nullptr ? 1 : 0};
+int gemm_variant() { return g_gemm_variant.load(std::memory_order_relaxed); }
+
+// The fp32 dense / Gram operators run on the tcgen05 tensor cores (3xTF32) when the
+// operator carries its TF32 planes (mf_operator_split) and the shape qualifies;
+// otherwise (fp64, tiny ld, unaligned lda) on the CUDA-core kernel.
+bool use_tc(const mf_operator_t* op, int64_t ld) {
+  if (op->kind != MF_OP_DENSE && op->kind != MF_OP_GRAM) return false;
+  if (op->split_planes == nullptr) return false;
+  if (g_gemm_tc.load(std::memory_order_relaxed) == 0) return false;
+  const int64_t rows = op->kind == MF_OP_GRAM ? op->m : op->n;
+  return tc_gemm_supported(op->lda, rows, op->n, ld, op->dtype);
+}
+
+void carve_op_scratch(Arena& a, const mf_operator_t* op, int64_t ld, OpScratch* s) {
+  memset(s, 0, sizeof(*s));
+  const int64_t es = (int64_t)dtype_size(op->dtype);
+  if (use_tc(op, ld)) {
+    s->xsplit = a.take(2 * op->n * ld * 4);
+    if (op->kind == MF_OP_GRAM) s->tsplit = a.take(2 * op->m * ld * 4);
+  } else if (op->kind == MF_OP_GRAM) {
+    s->gram = a.take(op->m * ld * es);
+  }
+}
+
 // W = s * (A @ X); if red != null and the operator can fuse it, also the column
 // sums of (X*s) .* W -> red->fin.  *fused tells the caller whether it happened.
 int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W, int64_t ld,
-                 void* gram_scratch, const Reduce* red, unsigned int* tickets, bool* fused,
+                 const OpScratch& scr, const Reduce* red, unsigned int* tickets, bool* fused,
                  cudaStream_t st) {
   *fused = false;
-  switch (op->kind) {
-    case MF_OP_CSR:
-      MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X,
-                             s, W, ld, red, tickets, st));
-      *fused = red != nullptr;
-      return MF_OK;
-    case MF_OP_DENSE:
-      return launch_gemm_blocked(op->values, op->lda, false, op->n, op->n, X, s, W, ld,
-                                 op->dtype, st);
-    case MF_OP_GRAM: {
-      void* Y = gram_scratch ? gram_scratch : op->op_scratch;
-      if (Y == nullptr) {
-        set_error("gram operator needs a scratch block of m*ld elements");
-        return MF_ERR_INVALID_ARGUMENT;
-      }
-      MF_TRY(launch_gemm_blocked(op->values, op->lda, false, op->m, op->n, X, nullptr, Y, ld,
-                                 op->dtype, st));
-      return launch_gemm_blocked(op->values, op->lda, true, op->n, op->m, Y, s, W, ld,
-                                 op->dtype, st);
+  if (op->kind == MF_OP_CSR) {
+    MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X, s, W,
+                           ld, red, tickets, st));
+    *fused = red != nullptr;
+    return MF_OK;
+  }
+  if (use_tc(op, ld)) {
+    if (scr.xsplit == nullptr || (op->kind == MF_OP_GRAM && scr.tsplit == nullptr)) {
+      set_error("dense/gram operator: workspace for the TF32 planes is missing");
+      return MF_ERR_WORKSPACE;
     }
+    const int variant = gemm_variant();
+    MF_TRY(launch_split_tf32(X, scr.xsplit, op->n * ld, st));
+    if (op->kind == MF_OP_DENSE)
+      return launch_gemm_tcgen05(op->split_planes, op->lda, false, op->n, op->n, scr.xsplit, 1, s,
+                                 W, nullptr, ld, variant, st);
+    // Gram: T = A X lands directly as TF32 planes (epilogue split), then W = A^T T
+    MF_TRY(launch_gemm_tcgen05(op->split_planes, op->lda, false, op->m, op->n, scr.xsplit, 1,
+                               nullptr, nullptr, scr.tsplit, ld, variant, st));
+    return launch_gemm_tcgen05(op->split_planes, op->lda, true, op->n, op->m, scr.tsplit, 1, s, W,
+                               nullptr, ld, variant, st);
+  }
+  if (op->kind == MF_OP_DENSE)
+    return launch_gemm_simt(op->values, op->lda, false, op->n, op->n, X, s, W, ld, op->dtype, st);
+  if (op->kind == MF_OP_GRAM) {
+    if (scr.gram == nullptr) {
+      set_error("gram operator needs a scratch block of m*ld elements");
+      return MF_ERR_WORKSPACE;
+    }
+    MF_TRY(launch_gemm_simt(op->values, op->lda, false, op->m, op->n, X, nullptr, scr.gram, ld,
+                            op->dtype, st));
+    return launch_gemm_simt(op->values, op->lda, true, op->n, op->m, scr.gram, s, W, ld, op->dtype,
+                            st);
   }
   return MF_ERR_INVALID_ARGUMENT;
 }
@@ -180,7 +232,7 @@ struct LanczosBufs {
   void *h, *h2;                // [k][ld] CGS coefficients
   double* partial;             // per-CTA partial rows of the reductions
   unsigned int* counter;       // ticket counter of the fused finalize (zeroed per call)
-  void* gram;                  // m*ld
+  OpScratch scr;               // operator scratch
 };
 
 int32_t carve_lanczos(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, int32_t reortho,
@@ -201,7 +253,7 @@ int32_t carve_lanczos(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, 
     b->h2 = a.take((k + 1) * ld * es);
     b->partial = (double*)a.take(partial_bytes(ld, 4));
   }
-  if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) b->gram = a.take(op->m * ld * es);
+  carve_op_scratch(a, op, ld, &b->scr);
   if (!a.dry && a.used > a.size) {
     set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
               (long long)a.size);
@@ -252,7 +304,7 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have
     void* aj = row(alphas, j, ld, dt);
     const Reduce red_a{b.partial, Finalize{b.counter, 0, aj, nullptr, nullptr}};
     bool fused = false;
-    MF_TRY(apply_op(op, X, sx, b.W, ld, b.gram, &red_a, b.counter + 8, &fused, st));
+    MF_TRY(apply_op(op, X, sx, b.W, ld, b.scr, &red_a, b.counter + 8, &fused, st));
     if (!fused) MF_TRY(launch_dot(X, sx, b.W, dt, n, ld, red_a, st));
     // pick the output buffer: alias Rp when we own it
     void* out;
@@ -297,7 +349,7 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     void* Qi = (char*)Q + i * blk;
     MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
     bool fused = false;
-    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.gram, nullptr, b.counter + 8, &fused, st));  // :460
+    MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.scr, nullptr, b.counter + 8, &fused, st));  // :460
     MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st));  // :463
     if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
@@ -378,21 +430,71 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
                           prng_flags, nullptr, (cudaStream_t)stream);
 }
 
-int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* stream) {
+int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores) {
+  if (variant < 0 || variant > 1) {
+    set_error("gemm_config: variant must be 0 or 1");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  g_gemm_variant.store(variant);
+  g_gemm_tc.store(use_tensor_cores != 0);
+  return MF_OK;
+}
+
+int64_t mf_operator_split_bytes(const mf_operator_t* op) {
+  if (validate_op(op) != MF_OK) return -1;
+  if (op->dtype != MF_F32 || (op->kind != MF_OP_DENSE && op->kind != MF_OP_GRAM)) return 0;
+  const int64_t rows = op->kind == MF_OP_GRAM ? op->m : op->n;
+  return 2 * rows * op->lda * 4;
+}
+
+int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream) {
+  MF_TRY(validate_op(op));
+  if (op->dtype != MF_F32 || (op->kind != MF_OP_DENSE && op->kind != MF_OP_GRAM)) {
+    set_error("operator_split: only fp32 dense / gram operators have TF32 planes");
+    return MF_ERR_UNSUPPORTED;
+  }
+  if (planes == nullptr) {
+    set_error("operator_split: planes is null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t rows = op->kind == MF_OP_GRAM ? op->m : op->n;
+  return launch_split_tf32(op->values, planes, rows * op->lda, (cudaStream_t)stream);
+}
+
+int64_t mf_matmat_workspace_bytes(const mf_operator_t* op, int64_t ld) {
+  if (validate_op(op) != MF_OK || !valid_ld(ld)) return -1;
+  Arena a(nullptr, 0, true);
+  OpScratch scr;
+  carve_op_scratch(a, op, ld, &scr);
+  return a.used + 256;
+}
+
+int32_t mf_matmat(const mf_operator_t* op, const void* X, void* W, int64_t ld, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
   MF_TRY(validate_op(op));
   if (!valid_ld(ld) || X == nullptr || W == nullptr) {
     set_error("matmat: ld must be a power of two <= 256 and X, W non-null");
     return MF_ERR_INVALID_ARGUMENT;
   }
+  Arena a(workspace, workspace_bytes, false);
+  OpScratch scr;
+  carve_op_scratch(a, op, ld, &scr);
+  if (a.used > a.size) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+              (long long)a.size);
+    return MF_ERR_WORKSPACE;
+  }
   bool fused;
-  return apply_op(op, X, nullptr, W, ld, nullptr, nullptr, nullptr, &fused, (cudaStream_t)stream);
+  return apply_op(op, X, nullptr, W, ld, scr, nullptr, nullptr, &fused, (cudaStream_t)stream);
 }
 
-int32_t mf_matmat_dense(const void* A, int64_t n, int64_t lda, int32_t dtype, const void* X,
-                        void* W, int64_t ld, void* stream) {
+int32_t mf_matmat_dense(const void* A, const void* A_planes, int64_t n, int64_t lda,
+                        int32_t dtype, const void* X, void* W, int64_t ld, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
   mf_operator_t op{};
   op.kind = MF_OP_DENSE; op.dtype = dtype; op.n = n; op.values = A; op.lda = lda;
-  return mf_matmat(&op, X, W, ld, stream);
+  op.split_planes = A_planes;
+  return mf_matmat(&op, X, W, ld, workspace, workspace_bytes, stream);
 }
 
 int32_t mf_matmat_csr(const int32_t* indptr, const int32_t* indices, const void* data,
@@ -401,15 +503,16 @@ int32_t mf_matmat_csr(const int32_t* indptr, const int32_t* indices, const void*
   mf_operator_t op{};
   op.kind = MF_OP_CSR; op.dtype = dtype; op.n = n; op.nnz = nnz; op.values = data;
   op.indptr = indptr; op.indices = indices;
-  return mf_matmat(&op, X, W, ld, stream);
+  return mf_matmat(&op, X, W, ld, nullptr, 0, stream);
 }
 
-int32_t mf_matmat_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
-                       const void* X, void* Y_scratch, void* W, int64_t ld, void* stream) {
+int32_t mf_matmat_gram(const void* A, const void* A_planes, int64_t m, int64_t n, int64_t lda,
+                       int32_t dtype, const void* X, void* W, int64_t ld, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
   mf_operator_t op{};
   op.kind = MF_OP_GRAM; op.dtype = dtype; op.n = n; op.m = m; op.values = A; op.lda = lda;
-  op.op_scratch = Y_scratch;
-  return mf_matmat(&op, X, W, ld, stream);
+  op.split_planes = A_planes;
+  return mf_matmat(&op, X, W, ld, workspace, workspace_bytes, stream);
 }
 
 int32_t mf_to_blocked(const void* src_pn, void* dst_blocked, int32_t dtype, int64_t n,
@@ -565,7 +668,7 @@ static int32_t carve_estimate(Arena& a, const mf_operator_t* op, int64_t ld, int
     e->lb.W = a.take(blk);
     e->lb.partial = (double*)a.take(partial_bytes(ld, 1));
     e->len = a.take(ld * es);
-    if (op->kind == MF_OP_GRAM && op->op_scratch == nullptr) e->lb.gram = a.take(op->m * ld * es);
+    carve_op_scratch(a, op, ld, &e->lb.scr);
     if (!a.dry && a.used > a.size) {
       set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
                 (long long)a.size);
@@ -645,7 +748,7 @@ int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
       void* dst = np == ld ? q_tile : e.len;
       const Reduce red{e.lb.partial, Finalize{e.lb.counter, 0, dst, nullptr, nullptr}};
       bool fused = false;
-      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.gram, &red, e.lb.counter + 8, &fused, st));
+      MF_TRY(apply_op(op, e.Z, nullptr, e.lb.W, ld, e.lb.scr, &red, e.lb.counter + 8, &fused, st));
       if (!fused) MF_TRY(launch_dot(e.Z, nullptr, e.lb.W, dt, op->n, ld, red, st));
       if (np != ld &&
           cudaMemcpyAsync(q_tile, e.len, np * es, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
@@ -692,7 +795,8 @@ int32_t mf_estimate(const mf_operator_t* op, int32_t integrand, int32_t sampler,
   return MF_OK;
 }
 
-int32_t mf_slq_estimate_dense(const void* A, int64_t n, int64_t lda, int32_t dtype,
+int32_t mf_slq_estimate_dense(const void* A, const void* A_planes, int64_t n, int64_t lda,
+                              int32_t dtype,
                               int32_t sampler, int32_t prng_flags, uint32_t key0,
                               uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
                               int64_t k, int32_t reortho, int32_t fn, double fn_param,
@@ -700,6 +804,7 @@ int32_t mf_slq_estimate_dense(const void* A, int64_t n, int64_t lda, int32_t dty
                               void* stream) {
   mf_operator_t op{};
   op.kind = MF_OP_DENSE; op.dtype = dtype; op.n = n; op.values = A; op.lda = lda;
+  op.split_planes = A_planes;
   return mf_estimate(&op, MF_INTEGRAND_SLQ, sampler, prng_flags, key0, key1, p0, num_probes, ld,
                      k, reortho, fn, fn_param, quad_out, nullptr, nullptr, nullptr, workspace,
                      workspace_bytes, stream);
@@ -719,7 +824,8 @@ int32_t mf_slq_estimate_csr(const int32_t* indptr, const int32_t* indices, const
                      workspace_bytes, stream);
 }
 
-int32_t mf_slq_estimate_gram(const void* A, int64_t m, int64_t n, int64_t lda, int32_t dtype,
+int32_t mf_slq_estimate_gram(const void* A, const void* A_planes, int64_t m, int64_t n,
+                             int64_t lda, int32_t dtype,
                              int32_t sampler, int32_t prng_flags, uint32_t key0,
                              uint32_t key1, int64_t p0, int64_t num_probes, int64_t ld,
                              int64_t k, int32_t reortho, int32_t fn, double fn_param,
@@ -727,6 +833,7 @@ int32_t mf_slq_estimate_gram(const void* A, int64_t m, int64_t n, int64_t lda, i
                              void* stream) {
   mf_operator_t op{};
   op.kind = MF_OP_GRAM; op.dtype = dtype; op.n = n; op.m = m; op.values = A; op.lda = lda;
+  op.split_planes = A_planes;
   return mf_estimate(&op, MF_INTEGRAND_SLQ, sampler, prng_flags, key0, key1, p0, num_probes, ld,
                      k, reortho, fn, fn_param, quad_out, nullptr, nullptr, nullptr, workspace,
                      workspace_bytes, stream);

@@ -81,6 +81,18 @@ int32_t launch_gemm_simt(const void* A, int64_t lda, bool trans, int64_t M, int6
                          const void* B, const void* colscale, void* C, int64_t ld,
                          int32_t dtype, cudaStream_t st);
 
+// ---- gemm_tcgen05.cu : fp32 via 3xTF32 on the tcgen05 tensor cores
+// Can the tensor-core kernel take this problem?  (fp32, ld in {32,64,128,256},
+// lda a multiple of 4 elements so TMA strides are multiples of 16 bytes)
+bool tc_gemm_supported(int64_t lda, int64_t M, int64_t K, int64_t ld, int32_t dtype);
+// planes[0][i] = rna_tf32(src[i]); planes[1][i] = rna_tf32(src[i] - planes[0][i])
+int32_t launch_split_tf32(const void* src, void* planes, int64_t count, cudaStream_t st);
+// C[batch][M][ld] = colscale .* (op(A) @ B) from TF32 planes Aplanes [2][rows][lda] and
+// Bplanes [batch][2][K][ld]; writes C and/or the planes of the result, Csplit [batch][2][M][ld]
+int32_t launch_gemm_tcgen05(const void* Aplanes, int64_t lda, bool trans, int64_t M, int64_t K,
+                            const void* Bplanes, int64_t nbatch, const void* colscale, void* C,
+                            void* Csplit, int64_t ld, int variant, cudaStream_t st);
+
 // ---- tridiag_quad.cu
 int32_t launch_tridiag_quad(const void* alphas, const void* betas, const void* init_len,
                             int32_t dtype, int64_t ld, int64_t num_probes, int64_t k,

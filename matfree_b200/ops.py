@@ -27,15 +27,25 @@ class Operator:
     n: int
     dtype = None  # torch dtype
 
-    def _struct(self, scratch=None) -> _lib.MfOperator:
+    def _struct(self) -> _lib.MfOperator:
         raise NotImplementedError
 
     @property
     def shape(self):
         return (self.n, self.n)
 
-    def _scratch_elems(self, ld: int) -> int:
-        return 0
+    def _make_planes(self):
+        """TF32 hi/lo planes of an fp32 dense / Gram matrix (`mf_operator_split`): with
+        them the operator runs on the tcgen05 tensor cores (3xTF32)."""
+        lib = _lib.load()
+        self._planes = None
+        st = self._struct()
+        nbytes = lib.mf_operator_split_bytes(ctypes.byref(st))
+        if nbytes <= 0:
+            return
+        planes = _device.workspace(nbytes)
+        _lib.check(lib.mf_operator_split(ctypes.byref(st), planes.data_ptr(), _device.stream()))
+        self._planes = planes
 
     # -- the reference's callable signature
     def __call__(self, v, *params):
@@ -54,11 +64,13 @@ class Operator:
         n, ld = X.shape
         assert n == self.n and X.is_contiguous() and X.dtype == self.dtype
         W = torch.empty_like(X)
-        scratch = None
-        if self._scratch_elems(ld):
-            scratch = torch.empty(self._scratch_elems(ld), dtype=self.dtype, device=X.device)
-        st = self._struct(scratch)
-        _lib.check(lib.mf_matmat(ctypes.byref(st), X.data_ptr(), W.data_ptr(), ld, _device.stream()))
+        st = self._struct()
+        nbytes = lib.mf_matmat_workspace_bytes(ctypes.byref(st), ld)
+        if nbytes < 0:
+            _lib.check(-1)
+        ws = _device.workspace(nbytes)
+        _lib.check(lib.mf_matmat(ctypes.byref(st), X.data_ptr(), W.data_ptr(), ld, ws.data_ptr(),
+                                 ws.numel(), _device.stream()))
         return W
 
     def matmat(self, V):
@@ -92,11 +104,14 @@ class DenseOperator(Operator):
         self.dtype = _device.torch_dtype(A.dtype)
         self.A = A
         self.n = int(A.shape[0])
+        self._planes = None
+        self._make_planes()
 
-    def _struct(self, scratch=None):
+    def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=0, values=self.A.data_ptr(), indptr=None, indices=None,
-                               lda=self.n, op_scratch=None)
+                               lda=self.n,
+                               split_planes=None if self._planes is None else self._planes.data_ptr())
 
 
 class CsrOperator(Operator):
@@ -116,11 +131,11 @@ class CsrOperator(Operator):
         if self.indices.shape[0] != self.nnz:
             raise ValueError("ops.csr: indices and data must have the same length")
 
-    def _struct(self, scratch=None):
+    def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
-                               lda=0, op_scratch=None)
+                               lda=0, split_planes=None)
 
 
 class GramOperator(Operator):
@@ -135,14 +150,14 @@ class GramOperator(Operator):
         self.dtype = _device.torch_dtype(A.dtype)
         self.A = A
         self.m, self.n = int(A.shape[0]), int(A.shape[1])
+        self._planes = None
+        self._make_planes()
 
-    def _scratch_elems(self, ld):
-        return self.m * ld
-
-    def _struct(self, scratch=None):
+    def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.m,
                                nnz=0, values=self.A.data_ptr(), indptr=None, indices=None,
-                               lda=self.n, op_scratch=None if scratch is None else scratch.data_ptr())
+                               lda=self.n,
+                               split_planes=None if self._planes is None else self._planes.data_ptr())
 
 
 def dense(A) -> DenseOperator:

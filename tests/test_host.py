@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.mf_abi_version() == 1
+    assert lib.mf_abi_version() == 2
     assert lib.mf_launch_count() == 0
 
 
@@ -36,7 +36,7 @@ def test_argument_validation_without_gpu():
 
     lib = _lib.load()
     op = _lib.MfOperator(kind=_lib.MF_OP_CSR, dtype=0, n=13, m=13, nnz=1, values=8, indptr=8, indices=8,
-                         lda=0, op_scratch=None)
+                         lda=0, split_planes=None)
     assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 16, 14, 0, 0) == -1
     assert b"exceeds the acceptable range" in lib.mf_last_error()
     assert lib.mf_lanczos_workspace_bytes(ctypes.byref(op), 16, -1, 0, 0) == -1
