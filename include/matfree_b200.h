@@ -143,9 +143,10 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
  * (matfree/stochtrace.py:47-49; tutorials/1_log_determinants.py:19-21).
  * mf_operator_split_bytes returns 0 for operators that have no planes (CSR, fp64). */
 int64_t mf_operator_split_bytes(const mf_operator_t* op);
-/* Tuning / cross-check knob of the dense path (process-wide).  variant 0: 128-row
- * tiles, 128-byte swizzle; variant 1: 256-row tiles (two TMEM accumulators), 64-byte
- * swizzle.  use_tensor_cores = 0 routes dense / Gram operators to the CUDA-core
+/* Tuning / cross-check knob of the dense path (process-wide).  variant = how many
+ * 32-k stages the tensor core sums in TMEM before the partial sum moves to the fp32
+ * register accumulators (0: two stages, the default; 1: one; 2: four -- fewer TMEM
+ * drains, more truncation drift).  use_tensor_cores = 0 routes dense / Gram operators to the CUDA-core
  * kernel even when TF32 planes are present (used by the tests to cross-check). */
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores);
 int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);

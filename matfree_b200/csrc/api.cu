@@ -431,8 +431,8 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
 }
 
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores) {
-  if (variant < 0 || variant > 1) {
-    set_error("gemm_config: variant must be 0 or 1");
+  if (variant < 0 || variant > 2) {
+    set_error("gemm_config: variant must be 0, 1 or 2");
     return MF_ERR_INVALID_ARGUMENT;
   }
   g_gemm_variant.store(variant);

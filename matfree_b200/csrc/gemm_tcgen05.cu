@@ -15,16 +15,21 @@
 // Replaces the `dot_general` XLA emits for a user matvec `A @ v` / `A.T @ (A @ v)`
 // under vmap (matfree/stochtrace.py:47-49; tutorials/1_log_determinants.py:19-21).
 //
-// Kernel shape (one CTA per (probe batch, BM-row tile of op(A)), 192 threads):
+// Kernel shape (one CTA per (probe batch, 128-row tile of op(A)), 320 threads):
 //   warp 0      TMA producer  : cp.async.bulk.tensor into a ring of smem stages
-//   warp 1      MMA issuer    : one lane issues tcgen05.mma.kind::tf32 (3 per k-step per
-//                               128-row half), tcgen05.commit releases the stage
-//   warps 2..5  epilogue      : tcgen05.ld 32 lanes x 32 columns, scale, store (and
+//   warp 1      MMA issuer    : one lane issues tcgen05.mma.kind::tf32 (3 per k-step),
+//                               tcgen05.commit releases the stage / publishes a TMEM buffer
+//   warps 2..9  accumulate    : tcgen05.ld the finished TMEM buffer and add it to fp32
+//               + epilogue      registers (round-to-nearest), finally scale and store (and
 //                               optionally the TF32 planes of the result)
-// Shared-memory tiles are in the canonical UMMA layouts with SWB-byte swizzle:
-//   K-major  (A, trans=0):  [rows][SWB bytes], 8-row groups SBO = 8*SWB apart
-//   MN-major (A^T and B):   [MN/CH chunks][BK rows][SWB bytes], LBO = BK*SWB, SBO = 8*SWB
-// (CH = SWB/4 fp32 per swizzle row; BK = CH k-values per stage; UMMA_K = 8.)
+// Shared-memory tiles are in the canonical UMMA layouts:
+//   K-major  (A, trans=0):  [rows][SWB bytes] with SWB-byte swizzle (128 or 64), 8-row
+//                           groups SBO = 8*SWB apart; BK = SWB/4 k-values per stage
+//   MN-major (A^T and B):   [MN/32 chunks][BK rows][128 bytes] with the "128-byte swizzle,
+//                           32-byte atom" mode -- the only MN-major layout the TF32 MMA
+//                           accepts (any other one silently yields zeros): 4-row groups
+//                           SBO = 512 apart, chunks LBO = BK*128 apart
+// (UMMA_K = 8 k-values per instruction.)
 #include <cuda.h>
 
 #include <mutex>
@@ -47,6 +52,9 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -145,11 +153,13 @@ __device__ __forceinline__ float rna_tf32(float x) {
 // ------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor (64 bit): start address >> 4 in [0,14), leading
 // byte offset >> 4 in [16,30), stride byte offset >> 4 in [32,46), descriptor
-// version 1 in [46,48), swizzle mode in [61,64) (2 = 128 B, 4 = 64 B).
-template <int SWB>
+// version 1 in [46,48), swizzle mode in [61,64) (1 = 128 B with 32-byte atoms,
+// 2 = 128 B, 4 = 64 B).
+constexpr int kLayoutSw128Atom32 = 1, kLayoutSw128 = 2, kLayoutSw64 = 4;
+template <int LAYOUT>
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes) {
-  constexpr uint64_t layout = SWB == 128 ? 2 : (SWB == 64 ? 4 : 6);
+  constexpr uint64_t layout = LAYOUT;
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
@@ -172,10 +182,15 @@ struct TcParams {
   int M, K, ld;
 };
 
-template <int BM, int BN, int SWB>
+constexpr int kBM = 128;        // rows of op(A) per CTA = one TMEM accumulator
+constexpr int kTcThreads = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 accumulate + epilogue
+
+template <int BN, int SWB>
 struct TcCfg {
-  static constexpr int CH = SWB / 4;      // fp32 per swizzle row
-  static constexpr int BK = CH;           // k-values per stage
+  static constexpr int BM = kBM;
+  static constexpr int BK = SWB / 4;      // k-values per stage (one K-major swizzle row)
+  static constexpr int CH = 32;           // fp32 per MN-major chunk (128 bytes)
+  static constexpr int KL = SWB == 128 ? kLayoutSw128 : kLayoutSw64;  // K-major layout id
   static constexpr int KSTEPS = BK / 8;   // UMMA_K = 8 for TF32
   static constexpr int A_PLANE = BM * BK * 4;
   static constexpr int B_PLANE = BN * BK * 4;
@@ -185,21 +200,33 @@ struct TcCfg {
   static constexpr int NSTAGE_RAW = (kSmemMax - kAux) / STAGE;
   static constexpr int NSTAGE = NSTAGE_RAW > 8 ? 8 : NSTAGE_RAW;
   static constexpr int SMEM = NSTAGE * STAGE + kAux;
-  static constexpr int TMEM_COLS = (BM / 128) * BN < 32 ? 32 : (BM / 128) * BN;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;  // two accumulator buffers
   static_assert(NSTAGE >= 2, "need at least two pipeline stages");
-  static_assert(BM == 128 || BM == 256, "BM is one or two 128-row accumulators");
   static_assert(TMEM_COLS <= 512, "accumulators exceed TMEM");
+  static_assert(BN % 64 == 0 || BN == 32, "each epilogue warp owns BN/2 columns in x32 pieces");
 };
 
-template <int BM, int BN, int SWB, bool A_MN>
-__global__ void __launch_bounds__(192, 1)
+// The tensor core adds into its fp32 accumulator with truncation, so a long K loop in one
+// TMEM accumulator drifts toward zero by ~(K/8) * 2^-24 relative (measured 8e-6 at K = 1000;
+// it would be 1e-4 at C3's K = 16384 -- far outside the 1e-5 budget of the log-determinant).
+// Hence the accumulation is split: the tensor core only sums FLUSH stages (FLUSH*BK k-values)
+// into one of two TMEM buffers; warps 2..9 drain the finished buffer with tcgen05.ld and add
+// it to fp32 registers with round-to-nearest while the tensor core fills the other buffer.
+template <int BN, int SWB, bool A_MN, int FLUSH>
+__global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const TcParams p) {
-  using Cfg = TcCfg<BM, BN, SWB>;
-  constexpr int CH = Cfg::CH, BK = Cfg::BK, KSTEPS = Cfg::KSTEPS, NSTAGE = Cfg::NSTAGE;
-  constexpr uint32_t kSbo = 8 * SWB;        // 8-row group stride
-  constexpr uint32_t kLboMn = BK * SWB;     // MN-major: stride between CH-wide chunks
+  using Cfg = TcCfg<BN, SWB>;
+  constexpr int BM = kBM, CH = Cfg::CH, BK = Cfg::BK, KSTEPS = Cfg::KSTEPS, NSTAGE = Cfg::NSTAGE;
+  constexpr uint32_t kSboK = 8 * SWB;       // K-major: 8-row group stride
+  constexpr uint32_t kLboMn = BK * 128;     // MN-major: stride between 32-wide chunks
+  constexpr uint32_t kSboMn = 512;          // MN-major: stride between 4-row groups
+  constexpr uint32_t kStepMn = 8 * 128;     // MN-major: 8 k-rows per MMA
+  constexpr int KL = Cfg::KL, ML = kLayoutSw128Atom32;
   constexpr uint32_t kIdesc = instr_desc_tf32(128, BN, A_MN, true);
+  // columns each epilogue warp owns: warps of the same lane quarter split the BN columns
+  constexpr int NCOLW = BN >= 64 ? BN / 2 : BN;  // BN = 32: second warp set idles
+  constexpr int NPIECE = NCOLW / 32;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -208,15 +235,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t bars = base + NSTAGE * Cfg::STAGE;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
-  const uint32_t acc_bar = bars + 8u * (2 * NSTAGE);
-  const uint32_t slot = bars + 8u * (2 * NSTAGE + 1);
+  auto accf_bar = [&](int b) { return bars + 8u * (2 * NSTAGE + b); };      // buffer b complete
+  auto acce_bar = [&](int b) { return bars + 8u * (2 * NSTAGE + 2 + b); };  // buffer b drained
+  const uint32_t slot = bars + 8u * (2 * NSTAGE + 4);
   volatile uint32_t* slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + NSTAGE * Cfg::STAGE + 8 * (2 * NSTAGE + 1));
+      reinterpret_cast<volatile uint32_t*>(base_ptr + NSTAGE * Cfg::STAGE + 8 * (2 * NSTAGE + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int batch = blockIdx.x;
   const int m0 = blockIdx.y * BM;
   const int num_it = (p.K + BK - 1) / BK;
+  const int num_chunks = (num_it + FLUSH - 1) / FLUSH;
+  constexpr int kDrainWarps = BN >= 64 ? 8 : 4;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -225,7 +255,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar(b), 1);
+      mbar_init(acce_bar(b), kDrainWarps);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(slot, Cfg::TMEM_COLS);
@@ -267,80 +300,94 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int it = 0; it < num_it; ++it) {
         const int s = it % NSTAGE;
         const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+        const int chunk = it / FLUSH;
+        const int buf = chunk & 1;
+        const bool chunk_first = it % FLUSH == 0;
+        const bool chunk_last = (it % FLUSH == FLUSH - 1) || it == num_it - 1;
+        if (chunk_first) {
+          // the drain warps must have emptied this buffer (two chunks ago)
+          mbar_wait(acce_bar(buf), ((uint32_t)(chunk >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+        }
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t sA = base + s * Cfg::STAGE;
         const uint32_t sB = sA + 2 * Cfg::A_PLANE;
+        const uint32_t d = tmem + buf * BN;
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk) {
-          // one k-step = 8 k-values: 32 bytes along a K-major row, one 8-row group MN-major
-          const uint32_t b_off = kk * kSbo;
-          const uint64_t bhi = smem_desc<SWB>(sB + b_off, kLboMn, kSbo);
-          const uint64_t blo = smem_desc<SWB>(sB + Cfg::B_PLANE + b_off, kLboMn, kSbo);
-#pragma unroll
-          for (int h = 0; h < BM / 128; ++h) {
-            uint64_t ahi, alo;
-            if (!A_MN) {
-              const uint32_t a_off = h * 128 * SWB + kk * 32;
-              ahi = smem_desc<SWB>(sA + a_off, 16, kSbo);
-              alo = smem_desc<SWB>(sA + Cfg::A_PLANE + a_off, 16, kSbo);
-            } else {
-              const uint32_t a_off = h * (128 / CH) * kLboMn + kk * kSbo;
-              ahi = smem_desc<SWB>(sA + a_off, kLboMn, kSbo);
-              alo = smem_desc<SWB>(sA + Cfg::A_PLANE + a_off, kLboMn, kSbo);
-            }
-            const uint32_t d = tmem + h * BN;
-            // small cross terms first, then the leading term
-            umma_tf32(d, alo, bhi, kIdesc, (it | kk) != 0 ? 1u : 0u);
-            umma_tf32(d, ahi, blo, kIdesc, 1u);
-            umma_tf32(d, ahi, bhi, kIdesc, 1u);
+          // one k-step = 8 k-values: 32 bytes along a K-major row, 8 rows of an MN-major chunk
+          const uint32_t b_off = kk * kStepMn;
+          const uint64_t bhi = smem_desc<ML>(sB + b_off, kLboMn, kSboMn);
+          const uint64_t blo = smem_desc<ML>(sB + Cfg::B_PLANE + b_off, kLboMn, kSboMn);
+          uint64_t ahi, alo;
+          if (!A_MN) {
+            const uint32_t a_off = kk * 32;
+            ahi = smem_desc<KL>(sA + a_off, 16, kSboK);
+            alo = smem_desc<KL>(sA + Cfg::A_PLANE + a_off, 16, kSboK);
+          } else {
+            const uint32_t a_off = kk * kStepMn;
+            ahi = smem_desc<ML>(sA + a_off, kLboMn, kSboMn);
+            alo = smem_desc<ML>(sA + Cfg::A_PLANE + a_off, kLboMn, kSboMn);
           }
+          // small cross terms first, then the leading term
+          umma_tf32(d, alo, bhi, kIdesc, (chunk_first && kk == 0) ? 0u : 1u);
+          umma_tf32(d, ahi, blo, kIdesc, 1u);
+          umma_tf32(d, ahi, bhi, kIdesc, 1u);
         }
-        umma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+        umma_commit(empty_bar(s));              // frees the stage when these MMAs have read it
+        if (chunk_last) umma_commit(accf_bar(buf));  // this buffer's partial sum is complete
       }
-      umma_commit(acc_bar);  // accumulators complete
     }
-  } else {
-    // epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31; lane = output row
+  } else if (warp - 2 < kDrainWarps) {
+    // accumulate + epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31 (lane = output row);
+    // the two warps of a lane quarter take the lower / upper half of the columns
     const int q = warp & 3;
-    mbar_wait<true>(acc_bar, 0);
-    tc_fence_after();
-    const float* cs = p.colscale ? p.colscale + (int64_t)batch * p.ld : nullptr;
-#pragma unroll 1
-    for (int h = 0; h < BM / 128; ++h) {
-      const int row = m0 + h * 128 + q * 32 + lane;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+    const int col0 = ((warp - 2) >> 2) * NCOLW;
+    float sum[NCOLW];
+#pragma unroll
+    for (int j = 0; j < NCOLW; ++j) sum[j] = 0.f;
+    for (int chunk = 0; chunk < num_chunks; ++chunk) {
+      const int buf = chunk & 1;
+      mbar_wait<true>(accf_bar(buf), (uint32_t)(chunk >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int pc = 0; pc < NPIECE; ++pc) {
         uint32_t r[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * BN + c0), r);
-        if (row < p.M) {
-          float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + col0 + pc * 32), r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(r[j]);
-            if (cs) v[j] *= __ldg(cs + c0 + j);
+        for (int j = 0; j < 32; ++j) sum[pc * 32 + j] += __uint_as_float(r[j]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce_bar(buf));
+    }
+    const int row = m0 + q * 32 + lane;
+    if (row < p.M) {
+      const float* cs = p.colscale ? p.colscale + (int64_t)batch * p.ld + col0 : nullptr;
+      if (cs) {
+#pragma unroll
+        for (int j = 0; j < NCOLW; ++j) sum[j] *= __ldg(cs + j);
+      }
+      if (p.C) {
+        float4* dst = reinterpret_cast<float4*>(p.C + ((int64_t)batch * p.M + row) * p.ld + col0);
+#pragma unroll
+        for (int j = 0; j < NCOLW / 4; ++j)
+          dst[j] = make_float4(sum[4 * j], sum[4 * j + 1], sum[4 * j + 2], sum[4 * j + 3]);
+      }
+      if (p.Csplit) {
+        float* hi_row = p.Csplit + (((int64_t)batch * 2) * p.M + row) * p.ld + col0;
+        float* lo_row = hi_row + (int64_t)p.M * p.ld;
+#pragma unroll
+        for (int j = 0; j < NCOLW / 4; ++j) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            hi[e] = rna_tf32(sum[4 * j + e]);
+            lo[e] = rna_tf32(sum[4 * j + e] - hi[e]);
           }
-          if (p.C) {
-            float4* dst = reinterpret_cast<float4*>(p.C + ((int64_t)batch * p.M + row) * p.ld + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.Csplit) {
-            float* hi_row = p.Csplit + (((int64_t)batch * 2) * p.M + row) * p.ld + c0;
-            float* lo_row = hi_row + (int64_t)p.M * p.ld;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                hi[e] = rna_tf32(v[4 * j + e]);
-                lo[e] = rna_tf32(v[4 * j + e] - hi[e]);
-              }
-              reinterpret_cast<float4*>(hi_row)[j] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-              reinterpret_cast<float4*>(lo_row)[j] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
-          }
+          reinterpret_cast<float4*>(hi_row)[j] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          reinterpret_cast<float4*>(lo_row)[j] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
     }
@@ -365,9 +412,9 @@ split_tf32_kernel(const float* __restrict__ src, float* __restrict__ hi, float* 
     reinterpret_cast<float4*>(hi)[i] = h;
     reinterpret_cast<float4*>(lo)[i] = l;
   }
-  // tail (count not a multiple of 4)
-  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {
-    const int64_t i = count4 * 4 + threadIdx.x;
+  // scalar path (count not a multiple of 4: the lo plane is not 16-byte aligned)
+  for (int64_t i = count4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += stride) {
     const float x = src[i];
     const float h = rna_tf32(x);
     hi[i] = h;
@@ -397,8 +444,10 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// swz: 128 / 64 = plain 128-byte / 64-byte swizzle (K-major tiles); 32 = 128-byte swizzle
+// with 32-byte atoms (MN-major TF32 tiles)
 int32_t make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                 const uint64_t* strides_bytes, const uint32_t* box, int swb) {
+                 const uint64_t* strides_bytes, const uint32_t* box, int swz) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("gemm_tcgen05: cuTensorMapEncodeTiled is not available from the driver");
@@ -413,7 +462,9 @@ int32_t make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
     es[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  const CUtensorMapSwizzle sw = swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = swz == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                            : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
                    gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -424,12 +475,12 @@ int32_t make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* d
   return MF_OK;
 }
 
-template <int BM, int BN, int SWB, bool A_MN>
+template <int BN, int SWB, bool A_MN, int FLUSH>
 int32_t launch_cfg(const float* Aplanes, int64_t lda, int64_t a_rows, int64_t M, int64_t K,
                    const float* Bplanes, int64_t nbatch, const float* colscale, float* C,
                    float* Csplit, int64_t ld, cudaStream_t st) {
-  using Cfg = TcCfg<BM, BN, SWB>;
-  constexpr int CH = Cfg::CH, BK = Cfg::BK;
+  using Cfg = TcCfg<BN, SWB>;
+  constexpr int CH = Cfg::CH, BK = Cfg::BK, BM = kBM;
   CUtensorMap tmA, tmB;
   const uint64_t a_plane_bytes = (uint64_t)a_rows * (uint64_t)lda * 4u;
   if (!A_MN) {
@@ -439,11 +490,11 @@ int32_t launch_cfg(const float* Aplanes, int64_t lda, int64_t a_rows, int64_t M,
     const uint32_t box[3] = {(uint32_t)BK, (uint32_t)BM, 1};
     MF_TRY(make_map(&tmA, Aplanes, 3, dims, str, box, SWB));
   } else {
-    // A[K][M] row-major: dims (M, K, plane); one CH-wide chunk per copy
+    // A[K][M] row-major: dims (M, K, plane); one 32-wide chunk per copy
     const uint64_t dims[3] = {(uint64_t)M, (uint64_t)K, 2};
     const uint64_t str[2] = {(uint64_t)lda * 4u, a_plane_bytes};
     const uint32_t box[3] = {(uint32_t)CH, (uint32_t)BK, 1};
-    MF_TRY(make_map(&tmA, Aplanes, 3, dims, str, box, SWB));
+    MF_TRY(make_map(&tmA, Aplanes, 3, dims, str, box, 32));
   }
   {
     // B planes [batch][2][K][ld]: dims (ld, K, plane, batch)
@@ -451,9 +502,9 @@ int32_t launch_cfg(const float* Aplanes, int64_t lda, int64_t a_rows, int64_t M,
     const uint64_t dims[4] = {(uint64_t)ld, (uint64_t)K, 2, (uint64_t)nbatch};
     const uint64_t str[3] = {(uint64_t)ld * 4u, plane, 2 * plane};
     const uint32_t box[4] = {(uint32_t)CH, (uint32_t)BK, 1, 1};
-    MF_TRY(make_map(&tmB, Bplanes, 4, dims, str, box, SWB));
+    MF_TRY(make_map(&tmB, Bplanes, 4, dims, str, box, 32));
   }
-  auto kernel = gemm_tf32x3_kernel<BM, BN, SWB, A_MN>;
+  auto kernel = gemm_tf32x3_kernel<BN, SWB, A_MN, FLUSH>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [&] {
@@ -467,27 +518,27 @@ int32_t launch_cfg(const float* Aplanes, int64_t lda, int64_t a_rows, int64_t M,
   }
   TcParams p{C, Csplit, colscale, (int)M, (int)K, (int)ld};
   dim3 grid((unsigned)nbatch, (unsigned)((M + BM - 1) / BM));
-  kernel<<<grid, 192, Cfg::SMEM, st>>>(tmA, tmB, p);
+  kernel<<<grid, kTcThreads, Cfg::SMEM, st>>>(tmA, tmB, p);
   return check_launch("gemm_tf32x3");
 }
 
-template <int BM, int SWB, bool A_MN>
+template <bool A_MN, int FLUSH>
 int32_t launch_bn(int64_t ld, const float* Aplanes, int64_t lda, int64_t a_rows, int64_t M,
                   int64_t K, const float* Bplanes, int64_t nbatch, const float* colscale, float* C,
                   float* Csplit, cudaStream_t st) {
   switch (ld) {
     case 32:
-      return launch_cfg<BM, 32, SWB, A_MN>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale, C,
-                                           Csplit, ld, st);
+      return launch_cfg<32, 128, A_MN, FLUSH>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale,
+                                              C, Csplit, ld, st);
     case 64:
-      return launch_cfg<BM, 64, SWB, A_MN>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale, C,
-                                           Csplit, ld, st);
+      return launch_cfg<64, 128, A_MN, FLUSH>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale,
+                                              C, Csplit, ld, st);
     case 128:
-      return launch_cfg<BM, 128, SWB, A_MN>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale,
-                                            C, Csplit, ld, st);
+      return launch_cfg<128, 128, A_MN, FLUSH>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch,
+                                               colscale, C, Csplit, ld, st);
     case 256:
-      return launch_cfg<BM, 256, SWB, A_MN>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch, colscale,
-                                            C, Csplit, ld, st);
+      return launch_cfg<256, 128, A_MN, FLUSH>(Aplanes, lda, a_rows, M, K, Bplanes, nbatch,
+                                               colscale, C, Csplit, ld, st);
   }
   set_error("gemm_tcgen05: ld=%lld unsupported", (long long)ld);
   return MF_ERR_UNSUPPORTED;
@@ -508,8 +559,9 @@ int32_t launch_split_tf32(const void* src, void* planes, int64_t count, cudaStre
   if (count <= 0) return MF_OK;
   float* hi = (float*)planes;
   float* lo = hi + count;
-  const int64_t count4 = count / 4;
-  int64_t blocks = (count4 + 255) / 256;
+  // the lo plane starts at hi + count: vector stores need count % 4 == 0
+  const int64_t count4 = (count % 4 == 0) ? count / 4 : 0;
+  int64_t blocks = ((count4 ? count4 : count) + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -521,7 +573,8 @@ int32_t launch_split_tf32(const void* src, void* planes, int64_t count, cudaStre
 //   Aplanes: [2][a_rows][lda] (hi, lo) of A; a_rows = M (trans=0) or K (trans=1)
 //   Bplanes: [batch][2][K][ld] (hi, lo) of the probe blocks
 //   C and/or Csplit ([batch][2][M][ld]) receive the result
-// variant: 0 = 128-row tiles, 128-byte swizzle; 1 = 256-row tiles (two accumulators), 64-byte swizzle
+// variant: how many 32-k stages the tensor core sums before the partial result is moved to
+// the fp32 register accumulators: 0 -> 2 stages (default), 1 -> 1 stage, 2 -> 4 stages
 int32_t launch_gemm_tcgen05(const void* Aplanes, int64_t lda, bool trans, int64_t M, int64_t K,
                             const void* Bplanes, int64_t nbatch, const void* colscale, void* C,
                             void* Csplit, int64_t ld, int variant, cudaStream_t st) {
@@ -530,18 +583,12 @@ int32_t launch_gemm_tcgen05(const void* Aplanes, int64_t lda, bool trans, int64_
   const float* B = (const float*)Bplanes;
   const float* cs = (const float*)colscale;
   const int64_t a_rows = trans ? K : M;
-  if (variant == 1) {
-    if (trans)
-      return launch_bn<256, 64, true>(ld, A, lda, a_rows, M, K, B, nbatch, cs, (float*)C,
-                                      (float*)Csplit, st);
-    return launch_bn<256, 64, false>(ld, A, lda, a_rows, M, K, B, nbatch, cs, (float*)C,
-                                     (float*)Csplit, st);
-  }
-  if (trans)
-    return launch_bn<128, 128, true>(ld, A, lda, a_rows, M, K, B, nbatch, cs, (float*)C,
-                                     (float*)Csplit, st);
-  return launch_bn<128, 128, false>(ld, A, lda, a_rows, M, K, B, nbatch, cs, (float*)C,
-                                    (float*)Csplit, st);
+#define MF_TC(TR, FL) \
+  launch_bn<TR, FL>(ld, A, lda, a_rows, M, K, B, nbatch, cs, (float*)C, (float*)Csplit, st)
+  if (variant == 1) return trans ? MF_TC(true, 1) : MF_TC(false, 1);
+  if (variant == 2) return trans ? MF_TC(true, 4) : MF_TC(false, 4);
+  return trans ? MF_TC(true, 2) : MF_TC(false, 2);
+#undef MF_TC
 }
 
 }  // namespace mf

@@ -32,7 +32,7 @@ def rel_err(got, want):
     return float(np.abs(got - want).max() / np.abs(want).max())
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("n,P", [(256, 32), (200, 64), (1000, 128), (520, 256), (1000, 300)])
 def test_dense_tcgen05_matches_fp64(variant, n, P):
     from matfree_b200 import _lib
@@ -57,7 +57,7 @@ def test_dense_tcgen05_matches_fp64(variant, n, P):
     assert e_tc < 8 * max(e_simt, 1e-7), (e_tc, e_simt)
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("mrows,n,P", [(300, 200, 64), (1031, 512, 256), (4096, 96, 32)])
 def test_gram_tcgen05_matches_fp64(variant, mrows, n, P):
     from matfree_b200 import _lib
