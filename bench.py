@@ -53,6 +53,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default, the headline): CSR Laplacian; c3: dense Gram operator A^T A "
+                         "(tensor-core path), reported as a supplementary line")
+    ap.add_argument("--gram-rows", type=int, default=65536)
+    ap.add_argument("--gram-cols", type=int, default=16384)
     ap.add_argument("--grid", type=int, default=4096, help="grid side m (n = m*m rows)")
     ap.add_argument("--depth", type=int, default=30)
     ap.add_argument("--probes-per-gpu", type=int, default=1024)
@@ -65,6 +70,11 @@ def parse_args():
 
 
 def workload_name(a, world):
+    if a.workload == "c3":
+        return (f"C3: SLQ logdet, dense Gram operator A^T A, A {a.gram_rows}x{a.gram_cols} fp32 "
+                f"(jax.random.normal(PRNGKey(2)) / sqrt(rows)), depth {a.depth}, reortho=none, "
+                f"{a.probes_per_gpu} Rademacher probes per GPU ({a.probes_per_gpu * world} total), "
+                f"key PRNGKey(1)")
     return (f"C2: SLQ logdet, 2-D 5-pt Laplacian {a.grid}^2 (n={a.grid * a.grid}) CSR + 1.0*I, fp32, "
             f"depth {a.depth}, reortho=none, {a.probes_per_gpu} Rademacher probes per GPU "
             f"({a.probes_per_gpu * world} total), key PRNGKey(1)")
@@ -167,31 +177,74 @@ def cpu_sample(csr, probes, depth):
     return time.perf_counter() - t0
 
 
+def gram_matrix_host(a):
+    """C3's A on the host (NumPy restatement of jax.random.normal, oracle/prng.py), chunked."""
+    import numpy as np
+
+    from oracle import prng as oprng
+
+    rows, cols = a.gram_rows, a.gram_cols
+    A = np.empty((rows, cols), np.float32)
+    step = max(1, (1 << 24) // cols)
+    key = oprng.prng_key(2)
+    scale = np.float32(1.0 / np.sqrt(rows))
+    for r0 in range(0, rows, step):
+        r1 = min(rows, r0 + step)
+        A[r0:r1] = oprng.normal(key, (r1 - r0, cols), np.float32, offset=r0 * cols) * scale
+    return A
+
+
+def cpu_sample_gram(A, probes, depth):
+    """Bounded CPU sample of the Gram SLQ path through the NumPy oracle; returns seconds."""
+    import numpy as np
+
+    from oracle import prng as oprng
+    from oracle import ref
+
+    V = oprng.rademacher(oprng.prng_key(1), (probes, A.shape[1]), np.float32)
+    t0 = time.perf_counter()
+    ref.slq_batched(lambda X: (X @ A.T) @ A, V, depth, reortho="none")
+    return time.perf_counter() - t0
+
+
 def run_reference(a, rank, world):
     """`--impl reference`: the CPU implementation of the path on the host cores (rank 0 only)."""
     if rank != 0:
         return
     from oracle import port
 
-    port.build()
-    csr = cpu_csr_arrays(a.grid)
-    probes = min(a.cpu_probes, 8)
-    for _ in range(a.warmup):
-        cpu_sample(csr, probes, a.depth)
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        cpu_sample(csr, probes, a.depth)
-    dt = (time.perf_counter() - t0) / max(a.steps, 1)
+    if a.workload == "c3":
+        A = gram_matrix_host(a)
+        probes = min(a.cpu_probes, 8)
+        for _ in range(min(a.warmup, 1)):
+            cpu_sample_gram(A, probes, a.depth)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            cpu_sample_gram(A, probes, a.depth)
+        dt = (time.perf_counter() - t0) / max(a.steps, 1)
+        cores, kind_note = os.cpu_count(), "oracle/ref.py slq_batched over NumPy/BLAS sgemm"
+        sample = f"{probes} probes x depth {a.depth} on the full {a.gram_rows}x{a.gram_cols} operator per step"
+    else:
+        port.build()
+        csr = cpu_csr_arrays(a.grid)
+        probes = min(a.cpu_probes, 8)
+        for _ in range(a.warmup):
+            cpu_sample(csr, probes, a.depth)
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            cpu_sample(csr, probes, a.depth)
+        dt = (time.perf_counter() - t0) / max(a.steps, 1)
+        cores, kind_note = port.num_threads(), "oracle/slq_port.c (OpenMP C restatement)"
+        sample = f"{probes} probes x depth {a.depth} on the full {a.grid}^2 operator per step"
     value = probes * a.depth / dt
-    sample = f"{probes} probes x depth {a.depth} on the full {a.grid}^2 operator per step"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, world), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample,
-                         "note": "oracle/slq_port.c (OpenMP C restatement); the JAX reference is not installable here"},
+                         "note": kind_note + "; the JAX reference is not installable here"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -381,11 +434,164 @@ def run_ours(a, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_ours_c3(a, rank, local_rank, world):
+    """Supplementary workload C3: dense Gram operator on the tcgen05 tensor cores."""
+    import numpy as np
+    import torch
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import matfree_b200 as m
+    from matfree_b200 import _lib
+
+    lib = _lib.load()
+    dist = None
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
+        import torch.distributed as dist  # noqa: F811
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    rows, n = a.gram_rows, a.gram_cols
+    P_local, P_total, k = a.probes_per_gpu, a.probes_per_gpu * world, a.depth
+    ld = min(a.tile, P_local)
+    A = m.prng.normal(m.prng.prng_key(2), shape=(rows, n), dtype=np.float32)
+    A.mul_(1.0 / float(np.sqrt(rows)))
+    op = m.ops.gram(A)
+    key = m.prng.prng_key(1)
+    sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1.0), (n,)), num=P_total)
+    integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+    estimate = m.stochtrace.estimator_monte_carlo_mean_and_sem(integrand, sampler)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with m.stochtrace.probe_sharding():
+            return estimate(op, key)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / max(steps, 1), out
+
+    _lib.timing_enable(True)
+    warmup = a.warmup if a.profile else max(a.warmup, 3)
+    for _ in range(warmup):
+        out = step_resident()
+    torch.cuda.synchronize()
+    _lib.timing_collect()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = lib.mf_launch_count()
+    ms_step, out = timed(step_resident, a.steps)
+    launches = lib.mf_launch_count() - launches0
+    clk = clocks.stop()
+    per_class = _lib.timing_collect()
+    _lib.timing_enable(False)
+    mean, sem = float(out[0]), float(out[1])
+    value = P_total * k / (ms_step * 1e-3)
+
+    e2e = None
+    if not a.no_e2e:
+        h_A = A.cpu().pin_memory()
+        del op
+        torch.cuda.empty_cache()
+
+        def step_e2e():
+            op_h = m.ops.gram(h_A.to(dev, non_blocking=True))  # H2D + TF32 planes inside the timed region
+            with m.stochtrace.probe_sharding():
+                mean_, sem_ = estimate(op_h, key)
+            return float(mean_), float(sem_)
+
+        step_e2e()
+        ms_e2e, _ = timed(step_e2e, max(1, min(a.steps, 2)))
+        e2e = {"value": P_total * k / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(rows * n * 4),
+               "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e,
+               "what": "ops.gram(host pinned A) [H2D + TF32 split] -> estimate(op, key) -> float(mean), float(sem)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    src = ("derived: TF32 dense = measured sustained bf16 (MEASURED_PEAKS.json) / 2" if peaks
+           else "derived: TF32 dense = fallback sustained bf16 1400 TFLOP/s / 2")
+    tf32_peak = bf16 / 2.0
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    total_ms = sum(v[0] for v in per_class.values()) or 1.0
+    kernels = {}
+    for cls, (ms, cnt) in sorted(per_class.items(), key=lambda kv: -kv[1][0]):
+        ent = {"ms_per_launch": ms / cnt, "launches": int(cnt), "share": ms / total_ms}
+        if cls == "gemm":
+            fl = 2.0 * rows * n * ld  # fp32 flops of one of the two contractions
+            ent["fp32_tflops"] = fl / (ms / cnt * 1e-3) / 1e12
+            ent["tf32_tflops_issued"] = 3 * ent["fp32_tflops"]
+            ent["frac_of_peak"] = ent["tf32_tflops_issued"] / tf32_peak
+            ent["hbm_gbs"] = (2.0 * rows * n * 4) / (ms / cnt * 1e-3) / 1e9  # both TF32 planes of A, once
+        kernels[cls] = ent
+    g = kernels.get("gemm", {})
+    roofline = {"bound": "tensor", "kernel": "gemm_tf32x3 (tcgen05, 3xTF32)", "achieved": g.get("tf32_tflops_issued"),
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": g.get("frac_of_peak"), "traffic": None,
+                "peak_source": src, "share_of_step": g.get("share"),
+                "algorithmic_flops_per_launch": 2.0 * rows * n * ld, "tensor_flops_issued_per_launch": 6.0 * rows * n * ld,
+                "hbm_gbs_for_planes": g.get("hbm_gbs"), "hbm_peak_gbs": hbm}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulation)", "data": "synthetic",
+        "config": {"workload": workload_name(a, world), "tile": ld,
+                   "l2": "A's TF32 planes (8.6 GB) stream from HBM every contraction >> 126 MB L2; no flush needed",
+                   "parallelism": f"probe-sharded x{world}"},
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "kernels": kernels,
+        "result": {"logdet_estimate": mean, "sem": sem},
+        "fp32_equivalent_tflops_whole_step": value / world * 4.0 * rows * n / 1e12,
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        try:
+            del A
+            torch.cuda.empty_cache()
+            Ah = h_A.numpy() if not a.no_e2e else gram_matrix_host(a)
+            probes = min(a.cpu_probes, 8)
+            dt = cpu_sample_gram(Ah, probes, k)
+            line["cpu_baseline"] = {"value": probes * k / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"{probes} probes x depth {k} on the full operator, {dt:.1f} s",
+                                    "note": "oracle/ref.py slq_batched over NumPy/BLAS sgemm; the JAX reference cannot be installed here"}
+        except Exception as exc:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.workload == "c3" and a.probes_per_gpu == 1024 and a.depth == 30:
+        a.probes_per_gpu, a.depth = 2048, 20  # C3's own numbers (16384 probes over 8 GPUs)
     if a.impl == "reference":
         run_reference(a, rank, world)
         return
@@ -394,7 +600,10 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
         raise SystemExit(subprocess.call(cmd))
-    run_ours(a, rank, local_rank, world)
+    if a.workload == "c3":
+        run_ours_c3(a, rank, local_rank, world)
+    else:
+        run_ours(a, rank, local_rank, world)
 
 
 if __name__ == "__main__":
