@@ -191,6 +191,39 @@ int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t 
                    int32_t reortho, void* alphas, void* betas, void* init_len, void* Q,
                    void* residual, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Building blocks of a ROW-SHARDED decomposition (operators too large for one GPU, or
+ * BASELINE config 4): the same kernels mf_lanczos chains, one call each, with every
+ * reduction stopping at THIS device's fp64 partial sums so the driver can all-reduce
+ * them across the row shards (NCCL) before the next call.  `n` is the number of LOCAL
+ * rows; block vectors are [n][ld] as everywhere.  Replaces, per shard,
+ * matfree/decomp.py:454-477 (Arnoldi step with CGS twice) and :286-292 (three-term step).
+ *   mf_block_dot      sums[c]    = sum_r X[r][c] * Y[r][c]
+ *   mf_reorth_dots    sums[j][c] = sum_r Q[j][r][c] * V[r][c],  j < nq   (decomp.py:463,468)
+ *   mf_reorth_update  V -= sum_j Q[j] * h[j];  optional sqnorm[c] = sum_r V[r][c]^2 (:464,468,471)
+ *   mf_lanczos_update out = (W - a (Rc*sc)) - bprev (Rp*sp);  sqnorm[c] = sum_r out^2 (:289-290)
+ *   mf_block_scale    out = X * s  or  X / s  per column                (:456-457)
+ *   mf_sums_finalize  value = sums or sqrt(sums), inv = 1/value, cast to dtype
+ *   mf_full_offdiag   offdiag = (offdiag + h) / 2          (T = (H + H^T)/2, :133-135) */
+int64_t mf_blockvec_workspace_bytes(int64_t ld, int64_t max_nq);
+int32_t mf_block_dot(const void* X, const void* Y, int32_t dtype, int64_t n, int64_t ld,
+                     double* sums, void* workspace, int64_t workspace_bytes, void* stream);
+int32_t mf_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
+                       int64_t ld, double* sums, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+int32_t mf_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
+                         int64_t n, int64_t ld, double* sqnorm, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+int32_t mf_lanczos_update(const void* W, const void* Rc, const void* sc, const void* a,
+                          const void* Rp, const void* sp, const void* bprev, void* out,
+                          int32_t dtype, int64_t n, int64_t ld, double* sqnorm, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+int32_t mf_block_scale(const void* X, const void* s, void* out, int32_t divide, int32_t dtype,
+                       int64_t n, int64_t ld, void* stream);
+int32_t mf_sums_finalize(const double* sums, int64_t count, int32_t take_sqrt, void* value,
+                         void* inv, int32_t dtype, void* stream);
+int32_t mf_full_offdiag(void* offdiag_row, const void* h_row, int32_t dtype, int64_t ld,
+                        void* stream);
+
 /* K5 -- Gauss quadrature of the tridiagonal matrices of a probe block:
  * replaces eigh + V f(L) V^T + e1^T(.)e1 of matfree/funm.py:239-241,330-333.
  * One lane per probe, implicit-QL with the first eigenvector row only.

@@ -62,6 +62,21 @@ SIGNATURES = {
     "mf_lanczos_workspace_bytes": (c_int64, [_OP, c_int64, c_int64, c_int32, c_int32]),
     "mf_lanczos": (c_int32, [_OP, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mf_blockvec_workspace_bytes": (c_int64, [c_int64, c_int64]),
+    "mf_block_dot": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p,
+                               c_int64, c_void_p]),
+    "mf_reorth_dots": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                                 c_void_p, c_int64, c_void_p]),
+    "mf_reorth_update": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int64, c_int64,
+                                   c_void_p, c_void_p, c_int64, c_void_p]),
+    "mf_lanczos_update": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p,
+                                    c_void_p, c_int64, c_void_p]),
+    "mf_block_scale": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64,
+                                 c_void_p]),
+    "mf_sums_finalize": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32,
+                                   c_void_p]),
+    "mf_full_offdiag": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
     "mf_tridiag_quad_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "mf_tridiag_quad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
                                   c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -231,6 +231,7 @@ struct LanczosBufs {
   void *inv;                   // [k+1][ld] 1/len, 1/beta_j
   void *h, *h2;                // [k][ld] CGS coefficients
   double* partial;             // per-CTA partial rows of the reductions
+  int64_t partial_rows;        // accumulator rows `partial` holds
   unsigned int* counter;       // ticket counter of the fused finalize (zeroed per call)
   OpScratch scr;               // operator scratch
 };
@@ -251,7 +252,8 @@ int32_t carve_lanczos(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, 
     b->V = a.take(blk);
     b->h = a.take((k + 1) * ld * es);
     b->h2 = a.take((k + 1) * ld * es);
-    b->partial = (double*)a.take(partial_bytes(ld, 4));
+    b->partial_rows = reorth_partial_rows(ld, k);
+    b->partial = (double*)a.take(partial_bytes(ld, (int)b->partial_rows));
   }
   carve_op_scratch(a, op, ld, &b->scr);
   if (!a.dry && a.used > a.size) {
@@ -350,7 +352,8 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
     bool fused = false;
     MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.scr, nullptr, b.counter + 8, &fused, st));  // :460
-    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st));  // :463
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st, nullptr,
+                              b.partial_rows));  // :463
     if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
                         cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
       set_error("alpha copy failed");
@@ -358,7 +361,8 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     }
     if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
     MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, st));  // :464
-    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st));  // :468
+    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st, nullptr,
+                              b.partial_rows));  // :468
     const Reduce red_n{b.partial, Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr}};
     MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, &red_n, st));  // :468,471
     length = row(betas, i, ld, dt);
@@ -643,6 +647,136 @@ int32_t mf_mc_reduce(const void* values, int32_t dtype, int64_t num, double* sta
     return MF_ERR_INVALID_ARGUMENT;
   }
   return launch_mc_reduce(values, dtype, num, stats_out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ row-sharded building blocks
+// The kernels of mf_lanczos, one call each, with every reduction stopping at this device's
+// fp64 partial sums: a row-sharded driver all-reduces them between the calls.
+
+int64_t mf_blockvec_workspace_bytes(int64_t ld, int64_t max_nq) {
+  if (!valid_ld(ld) || max_nq < 0) return -1;
+  return 256 + partial_bytes(ld, (int)reorth_partial_rows(ld, max_nq)) + 256;
+}
+
+namespace {
+struct BvScratch {
+  unsigned int* counter;
+  double* partial;
+  int64_t partial_rows;
+};
+int32_t carve_bv(void* ws, int64_t bytes, int64_t ld, BvScratch* b, cudaStream_t st) {
+  if (!valid_ld(ld)) {
+    set_error("ld=%lld must be a power of two in [1, 256]", (long long)ld);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  Arena a(ws, bytes, false);
+  b->counter = (unsigned int*)a.take(256);
+  b->partial = (double*)a.take(partial_bytes(ld, 4));
+  // whatever the caller provided beyond the minimum holds more accumulator rows
+  b->partial_rows = 4;
+  if (ws != nullptr && bytes > a.used)
+    b->partial_rows = 4 + (bytes - a.used) / partial_bytes(ld, 1);
+  if (ws == nullptr || a.used > a.size) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used, (long long)bytes);
+    return MF_ERR_WORKSPACE;
+  }
+  if (cudaMemsetAsync(b->counter, 0, 256, st) != cudaSuccess) {
+    set_error("counter memset failed");
+    return MF_ERR_CUDA;
+  }
+  return MF_OK;
+}
+}  // namespace
+
+int32_t mf_block_dot(const void* X, const void* Y, int32_t dtype, int64_t n, int64_t ld,
+                     double* sums, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!X || !Y || !sums || n < 0) {
+    set_error("block_dot: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  BvScratch b;
+  MF_TRY(carve_bv(workspace, workspace_bytes, ld, &b, st));
+  const Reduce red{b.partial, Finalize{b.counter, 0, nullptr, nullptr, sums}};
+  return launch_dot(X, nullptr, Y, dtype, n, ld, red, st);
+}
+
+int32_t mf_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
+                       int64_t ld, double* sums, void* workspace, int64_t workspace_bytes,
+                       void* stream) {
+  if (!Q || !V || !sums || nq <= 0 || n < 0) {
+    set_error("reorth_dots: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  BvScratch b;
+  MF_TRY(carve_bv(workspace, workspace_bytes, ld, &b, st));
+  return launch_reorth_dots(Q, nq, V, dtype, n, ld, b.partial, b.counter, nullptr, st, sums,
+                            b.partial_rows);
+}
+
+int32_t mf_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
+                         int64_t n, int64_t ld, double* sqnorm, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  if (!Q || !V || !h || nq <= 0 || n < 0) {
+    set_error("reorth_update: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sqnorm == nullptr) {
+    if (!valid_ld(ld)) {
+      set_error("ld=%lld must be a power of two in [1, 256]", (long long)ld);
+      return MF_ERR_INVALID_ARGUMENT;
+    }
+    return launch_reorth_update(Q, nq, h, V, dtype, n, ld, nullptr, st);
+  }
+  BvScratch b;
+  MF_TRY(carve_bv(workspace, workspace_bytes, ld, &b, st));
+  const Reduce red{b.partial, Finalize{b.counter, 0, nullptr, nullptr, sqnorm}};
+  return launch_reorth_update(Q, nq, h, V, dtype, n, ld, &red, st);
+}
+
+int32_t mf_lanczos_update(const void* W, const void* Rc, const void* sc, const void* a,
+                          const void* Rp, const void* sp, const void* bprev, void* out,
+                          int32_t dtype, int64_t n, int64_t ld, double* sqnorm, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  if (!W || !Rc || !a || !out || !sqnorm || n < 0) {
+    set_error("lanczos_update: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  BvScratch b;
+  MF_TRY(carve_bv(workspace, workspace_bytes, ld, &b, st));
+  const Reduce red{b.partial, Finalize{b.counter, 0, nullptr, nullptr, sqnorm}};
+  return launch_lanczos_update(W, Rc, sc, a, Rp, sp, bprev, out, dtype, n, ld, red, st);
+}
+
+int32_t mf_block_scale(const void* X, const void* s, void* out, int32_t divide, int32_t dtype,
+                       int64_t n, int64_t ld, void* stream) {
+  if (!X || !out || !valid_ld(ld) || n < 0) {
+    set_error("block_scale: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_scale(X, s, out, divide ? 1 : 0, dtype, n, ld, (cudaStream_t)stream);
+}
+
+int32_t mf_sums_finalize(const double* sums, int64_t count, int32_t take_sqrt, void* value,
+                         void* inv, int32_t dtype, void* stream) {
+  if (!sums || count < 0 || (dtype != MF_F32 && dtype != MF_F64)) {
+    set_error("sums_finalize: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_sums_finalize(sums, count, take_sqrt ? 1 : 0, value, inv, dtype,
+                              (cudaStream_t)stream);
+}
+
+int32_t mf_full_offdiag(void* offdiag_row, const void* h_row, int32_t dtype, int64_t ld,
+                        void* stream) {
+  if (!offdiag_row || !h_row || ld <= 0) {
+    set_error("full_offdiag: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_full_offdiag(offdiag_row, h_row, dtype, ld, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ fused estimator

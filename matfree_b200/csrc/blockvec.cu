@@ -21,6 +21,19 @@ __device__ __forceinline__ void load_chunk(const T* __restrict__ p, int64_t f, T
     vec_load<T>(p + f, v);
   }
 }
+// streaming (evict-first) variant for data read exactly once, so that re-read operands stay in L2
+template <typename T, int VEC>
+__device__ __forceinline__ void load_chunk_stream(const T* __restrict__ p, int64_t f, T (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = __ldcs(p + f);
+  } else {
+    using V = typename Vec<T>::type;
+    V t = __ldcs(reinterpret_cast<const V*>(p + f));
+    const T* e = reinterpret_cast<const T*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) v[i] = e[i];
+  }
+}
 template <typename T, int VEC>
 __device__ __forceinline__ void store_chunk(T* __restrict__ p, int64_t f, const T (&v)[VEC]) {
   if constexpr (VEC == 1) {
@@ -132,6 +145,64 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
     }
   }
   cta_reduce_finalize<T, VEC, JB>(acc, ld, partial, partial_stride, nj, fin);
+}
+
+// All nq basis vectors in ONE launch (narrow tiles: the per-CTA partial rows of all nq sums fit
+// the workspace).  Groups of JB vectors are accumulated in registers; V is re-read per group but
+// stays L2-resident because the basis -- read exactly once -- is loaded with evict-first hints.
+template <typename T, int VEC, int JB>
+__global__ void __launch_bounds__(kBlock, 3)
+reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ V,
+                       int64_t total, int ld, double* __restrict__ partial, int64_t partial_stride,
+                       Finalize fin) {
+  for (int j0 = 0; j0 < nq; j0 += JB) {
+    const int nj = (nq - j0) < JB ? (nq - j0) : JB;
+    double acc[JB][VEC];
+#pragma unroll
+    for (int j = 0; j < JB; ++j)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
+    // software-pipelined: the loads of the next chunk are issued before the current one is
+    // consumed (two chunks of V + JB basis vectors in flight per thread)
+    const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
+    int64_t f = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC;
+    T v[VEC], q[JB][VEC];
+    if (f < total) {
+      load_chunk<T, VEC>(V, f, v);
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j < nj) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, f, q[j]);
+    }
+    while (f < total) {
+      const int64_t fn = f + stride;
+      T vn[VEC], qn[JB][VEC];
+      if (fn < total) {
+        load_chunk<T, VEC>(V, fn, vn);
+#pragma unroll
+        for (int j = 0; j < JB; ++j)
+          if (j < nj) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, fn, qn[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j < nj) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[j][i] * (double)v[i];
+        }
+      if (fn < total) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = vn[i];
+#pragma unroll
+        for (int j = 0; j < JB; ++j)
+          if (j < nj) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) q[j][i] = qn[j][i];
+          }
+      }
+      f = fn;
+    }
+    cta_reduce_columns<VEC, JB>(acc, ld, partial + (int64_t)j0 * partial_stride, partial_stride);
+  }
+  finalize_if_last<T>(ld, partial, partial_stride, nq, fin);
 }
 
 template <typename T, int VEC, bool NORM>
@@ -246,18 +317,44 @@ __global__ void full_offdiag_kernel(T* __restrict__ beta_prev, const T* __restri
   if (c < ld) beta_prev[c] = T(0.5) * (h_row[c] + beta_prev[c]);
 }
 
+// value = sum or sqrt(sum), inv = 1 / value, from fp64 sums (after an all-reduce)
+template <typename T>
+__global__ void sums_finalize_kernel(const double* __restrict__ sums, int64_t count, int mode,
+                                     T* __restrict__ value, T* __restrict__ inv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double s = sums[i];
+  const T v = mode == 0 ? (T)s : (T)sqrt(s);
+  if (value) value[i] = v;
+  if (inv) inv[i] = T(1) / v;
+}
+
 inline int vec_for(int32_t dtype, int64_t ld) {
   const int nv = dtype == MF_F64 ? 2 : 4;
   return ld >= nv ? nv : 1;
 }
 
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+// all of the (possibly null) pointers 16-byte aligned and the element count a whole number of
+// 16-byte chunks
+inline bool wide_ok(int32_t dtype, int64_t total, const void* a, const void* b = nullptr,
+                    const void* c = nullptr, const void* d = nullptr) {
+  const int64_t per = dtype == MF_F64 ? 2 : 4;
+  return total % per == 0 && al16(a) && al16(b) && al16(c) && al16(d);
+}
+
 }  // namespace
 
+// Vector width of the flat mapping: 16-byte chunks whenever a row holds at least one
+// (ld >= 4 fp32 / 2 fp64).  Narrow tiles (ld = 1, 2 -- single start vectors, config 4) still
+// get 16-byte accesses when `mf_wide` (set by the launcher: element count a multiple of the
+// chunk and all pointers 16-byte aligned): a chunk then spans several rows of the same
+// columns, which the column masks (& (ld - 1)) already handle.
 #define MF_DISPATCH_TV(dtype, ld, ...)                     \
   do {                                                     \
     if ((dtype) == MF_F32) {                               \
       using T = float;                                     \
-      if ((ld) >= 4) {                                     \
+      if ((ld) >= 4 || mf_wide) {                          \
         constexpr int VEC = 4;                             \
         __VA_ARGS__;                                            \
       } else {                                             \
@@ -266,7 +363,7 @@ inline int vec_for(int32_t dtype, int64_t ld) {
       }                                                    \
     } else {                                               \
       using T = double;                                    \
-      if ((ld) >= 2) {                                     \
+      if ((ld) >= 2 || mf_wide) {                          \
         constexpr int VEC = 2;                             \
         __VA_ARGS__;                                            \
       } else {                                             \
@@ -284,6 +381,7 @@ int32_t launch_dot(const void* X, const void* sx, const void* Y, int32_t dtype, 
                    int64_t ld, const Reduce& red, cudaStream_t st) {
   MF_KSCOPE(MF_KC_DOT, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, X, Y);
   MF_DISPATCH_TV(dtype, ld, {
     auto kern = dot_kernel<T, VEC>;
     const int grid = MF_STREAM_GRID(kern, total, VEC);
@@ -299,6 +397,7 @@ int32_t launch_lanczos_update(const void* W, const void* Rc, const void* sc, con
                               cudaStream_t st) {
   MF_KSCOPE(MF_KC_LANCZOS_UPDATE, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, W, Rc, Rp, out);
   if (Rp != nullptr) {
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = lanczos_update_kernel<T, VEC, true>;
@@ -323,6 +422,7 @@ int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t 
                      int64_t n, int64_t ld, cudaStream_t st) {
   MF_KSCOPE(MF_KC_SCALE, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, X, out);
   MF_DISPATCH_TV(dtype, ld, {
     auto kern = scale_kernel<T, VEC>;
     const int grid = MF_STREAM_GRID(kern, total, VEC);
@@ -333,14 +433,28 @@ int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t 
 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
-                           cudaStream_t st) {
+                           cudaStream_t st, double* dbl_out, int64_t partial_rows) {
   MF_KSCOPE(MF_KC_REORTH_DOTS, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, Q, V);
   const int64_t pstride = (int64_t)kMaxPartialCtas * ld;
   constexpr int JB = 4;
+  if (nq > JB && partial_rows >= (nq + JB - 1) / JB * JB) {
+    // one launch for all nq sums
+    Finalize fin{counter, 0, h_out, nullptr, dbl_out};
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = reorth_dots_all_kernel<T, VEC, JB>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)Q, total, (int)nq, (const T*)V, total, (int)ld,
+                                    partial, pstride, fin);
+    });
+    return check_launch("reorth_dots_all");
+  }
   for (int64_t j0 = 0; j0 < nq; j0 += JB) {
     const int nj = (int)((nq - j0) < JB ? (nq - j0) : JB);
-    Finalize fin{counter, 0, (char*)h_out + j0 * ld * (int64_t)dtype_size(dtype), nullptr, nullptr};
+    Finalize fin{counter, 0,
+                 h_out ? (void*)((char*)h_out + j0 * ld * (int64_t)dtype_size(dtype)) : nullptr,
+                 nullptr, dbl_out ? dbl_out + j0 * ld : nullptr};
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_kernel<T, VEC, JB>;
       const int grid = MF_STREAM_GRID(kern, total, VEC);
@@ -356,6 +470,7 @@ int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, 
                              int64_t n, int64_t ld, const Reduce* red, cudaStream_t st) {
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, Q, V);
   const size_t smem = (size_t)nq * ld * dtype_size(dtype);
   if (smem > 160 * 1024) {
     set_error("reorth_update: %lld basis vectors x %lld probes exceed the shared-memory budget; "
@@ -392,6 +507,7 @@ int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scal
                              cudaStream_t st) {
   MF_KSCOPE(MF_KC_OTHER, st);
   const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, Q, out);
   MF_DISPATCH_TV(dtype, ld, {
     auto kern = basis_combine_kernel<T, VEC>;
     const int grid = MF_STREAM_GRID(kern, total, VEC);
@@ -423,6 +539,21 @@ int32_t launch_transpose(const void* src, void* dst, int32_t dtype, int64_t n,
                                                               num_probes, ld);
   }
   return check_launch("transpose");
+}
+
+int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* value, void* inv,
+                             int32_t dtype, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_FINALIZE, st);
+  if (count <= 0) return MF_OK;
+  const int threads = 128;
+  const int blocks = (int)((count + threads - 1) / threads);
+  if (dtype == MF_F32)
+    sums_finalize_kernel<float><<<blocks, threads, 0, st>>>(sums, count, mode, (float*)value,
+                                                            (float*)inv);
+  else
+    sums_finalize_kernel<double><<<blocks, threads, 0, st>>>(sums, count, mode, (double*)value,
+                                                             (double*)inv);
+  return check_launch("sums_finalize");
 }
 
 int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dtype, int64_t ld,

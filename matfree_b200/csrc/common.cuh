@@ -110,10 +110,26 @@ struct Geo {
   }
 };
 
+// Lanes that cooperate on one (accumulator, column) pair of a reduction: 1 for wide tiles (one
+// thread per column is already parallel enough), up to a full warp for narrow ones (ld = 1:
+// a single start vector, BASELINE config 4), where a serial sum would dominate the kernel.
+__device__ __forceinline__ int lanes_per_pair(int npairs) {
+  int l = kBlock / (npairs > 0 ? npairs : 1);
+  if (l >= 32) return 32;
+  int p = 1;
+  while (p * 2 <= l) p *= 2;
+  return p;
+}
+// fixed-shape xor tree over the L lanes of a group (L a power of two <= 32): deterministic
+__device__ __forceinline__ double group_sum(double s, int L) {
+  for (int off = L >> 1; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  return s;
+}
+
 // Deterministic CTA-level reduction of per-thread column accumulators.
-// acc[VEC] of thread t belongs to columns col0..col0+VEC-1; threads with equal
-// col0 are summed in increasing thread order.  Result is written to
-// partial[blockIdx.x * ld + col].
+// acc[VEC] of thread t belongs to columns col0..col0+VEC-1; the contributions to a column are
+// summed in a fixed order (strided over the lanes of a group, then an xor tree).  Result is
+// written to partial[blockIdx.x * ld + col].
 template <int VEC, int NACC = 1>
 __device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int ld,
                                                    double* __restrict__ partial,
@@ -125,11 +141,19 @@ __device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int
     for (int i = 0; i < VEC; ++i) sh[a][threadIdx.x * VEC + i] = acc[a][i];
   __syncthreads();
   // flat element index e = t*VEC+i maps to column e % ld
-  for (int idx = threadIdx.x; idx < NACC * ld; idx += kBlock) {
-    int a = idx / ld, c = idx % ld;
+  const int npairs = NACC * ld;
+  const int L = lanes_per_pair(npairs);
+  const int lane = threadIdx.x & (L - 1);
+  const int groups = kBlock / L;
+  for (int base = 0; base < npairs; base += groups) {
+    const int idx = base + threadIdx.x / L;
+    const bool live = idx < npairs;
+    const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     double s = 0.0;
-    for (int e = c; e < kBlock * VEC; e += ld) s += sh[a][e];
-    partial[a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
+    if (live)
+      for (int e = c + lane * ld; e < kBlock * VEC; e += L * ld) s += sh[a][e];
+    s = group_sum(s, L);
+    if (live && lane == 0) partial[a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
   }
   __syncthreads();
 }
@@ -148,12 +172,12 @@ struct Finalize {
   double* dbl;            // optional double[nacc][ld]: the fp64 sums
 };
 
-template <typename T, int VEC, int NACC = 1>
-__device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], int ld,
-                                                    double* __restrict__ partial,
-                                                    int64_t partial_stride, int nacc_live,
-                                                    const Finalize& fin) {
-  cta_reduce_columns<VEC, NACC>(acc, ld, partial, partial_stride);
+// Second half of a reducing kernel: take a ticket; the CTA drawing the last one adds the
+// partial rows of all CTAs (fixed order) for `nacc_live` accumulators and writes the results.
+template <typename T>
+__device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ partial,
+                                                 int64_t partial_stride, int nacc_live,
+                                                 const Finalize& fin) {
   if (fin.counter == nullptr) return;
   __shared__ bool is_last;
   __threadfence();
@@ -166,11 +190,20 @@ __device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], in
   if (!is_last) return;
   __threadfence();
   const int grid = gridDim.x;
-  for (int idx = threadIdx.x; idx < nacc_live * ld; idx += kBlock) {
-    const int a = idx / ld, c = idx % ld;
+  const int npairs = nacc_live * ld;
+  const int L = lanes_per_pair(npairs);
+  const int lane = threadIdx.x & (L - 1);
+  const int groups = kBlock / L;
+  for (int base = 0; base < npairs; base += groups) {
+    const int idx = base + threadIdx.x / L;
+    const bool live = idx < npairs;
+    const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     const double* p = partial + a * partial_stride + c;
     double s = 0.0;
-    for (int b = 0; b < grid; ++b) s += __ldcg(p + (int64_t)b * ld);
+    if (live)
+      for (int b = lane; b < grid; b += L) s += __ldcg(p + (int64_t)b * ld);
+    s = group_sum(s, L);
+    if (!live || lane != 0) continue;
     if (fin.dbl) fin.dbl[(int64_t)a * ld + c] = s;
     if (fin.mode == 0) {
       if (fin.value) reinterpret_cast<T*>(fin.value)[(int64_t)a * ld + c] = (T)s;
@@ -181,6 +214,15 @@ __device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], in
     }
   }
   if (threadIdx.x == 0) *fin.counter = 0u;
+}
+
+template <typename T, int VEC, int NACC = 1>
+__device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], int ld,
+                                                    double* __restrict__ partial,
+                                                    int64_t partial_stride, int nacc_live,
+                                                    const Finalize& fin) {
+  cta_reduce_columns<VEC, NACC>(acc, ld, partial, partial_stride);
+  finalize_if_last<T>(ld, partial, partial_stride, nacc_live, fin);
 }
 
 }  // namespace mf

@@ -44,9 +44,20 @@ int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t 
                      int64_t n, int64_t ld, cudaStream_t st);
 // CGS pass, dots: h[j][c] = sum_r Q[j][r][c] * V[r][c], j = 0..nq-1
 // (matfree/decomp.py:463,468).  partial: double[4][kMaxPartialCtas*ld]
+// dbl_out (optional): the fp64 sums [nq][ld] (row-sharded drivers all-reduce these)
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
-                           cudaStream_t st);
+                           cudaStream_t st, double* dbl_out = nullptr, int64_t partial_rows = 4);
+// Accumulator rows the partial buffer of the CGS dots gets: all k sums in one launch when
+// that costs at most 8 MB (narrow tiles), otherwise 4 (groups of four basis vectors per launch).
+inline int64_t reorth_partial_rows(int64_t ld, int64_t k) {
+  const int64_t k4 = (k + 3) / 4 * 4;
+  const int64_t row_bytes = (int64_t)kMaxPartialCtas * ld * 8;
+  return (k4 > 4 && k4 * row_bytes <= (8ll << 20)) ? k4 : 4;
+}
+// value[i] = sums[i] (mode 0) or sqrt(sums[i]) (mode 1); inv[i] = 1 / value[i]
+int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* value, void* inv,
+                             int32_t dtype, cudaStream_t st);
 // CGS pass, update: V <- V - sum_j Q[j] * h[j]  (decomp.py:464,468); optional
 // column sums of the new V^2 -> red->fin (norm fused).
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,

@@ -58,6 +58,14 @@ def lanczos_blocked(op: ops.Operator, V0b, k: int, reortho: str, *, want_Q: bool
     """
     import torch
 
+    from matfree_b200 import _rowshard
+
+    if isinstance(op, _rowshard.RowShardedCsr):
+        # rows (and vectors) are partitioned over the ranks of op.group: V0b is this rank's slab
+        if reortho == "full":
+            return _rowshard.lanczos_full_sharded(op, V0b.contiguous(), k, want_residual=want_residual)
+        return _rowshard.lanczos_none_sharded(op, V0b.contiguous(), k, want_Q=want_Q,
+                                              want_residual=want_residual)
     lib = _lib.load()
     n, ld = V0b.shape
     dt = V0b.dtype
@@ -104,8 +112,9 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
         op = ops.require_operator(matvec, "tridiag_sym")
         vec_t = _device.as_device(vec, op.dtype).reshape(-1)
         n = vec_t.shape[0]
-        if k < 0 or k > n:
-            raise ValueError(_error_num_matvecs(k, maxval=n, minval=0))
+        n_total = getattr(op, "n_global", n)  # row-sharded operators: vec is this rank's slab
+        if k < 0 or k > n_total:
+            raise ValueError(_error_num_matvecs(k, maxval=n_total, minval=0))
         if n != op.n:
             raise ValueError(f"vector has length {n}, operator dimension is {op.n}")
         V0b = vec_t.reshape(n, 1)

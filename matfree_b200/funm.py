@@ -170,8 +170,9 @@ def monte_carlo_funm_sym(dense_funm, tridiag_sym, /):
         op = ops.require_operator(matvec, "monte_carlo_funm_sym")
         v = _device.as_device(v0, op.dtype).reshape(-1)
         k = spec["num_matvecs"]
-        if k < 0 or k > v.shape[0]:
-            raise ValueError(decomp._error_num_matvecs(k, maxval=v.shape[0], minval=0))
+        n_total = getattr(op, "n_global", v.shape[0])
+        if k < 0 or k > n_total:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=n_total, minval=0))
         alphas, betas, init_len, _, _ = decomp.lanczos_blocked(
             op, v.reshape(-1, 1), k, spec["reortho"], want_Q=False, want_residual=False)
         return quadrature_blocked(alphas, betas, init_len, 1, matfun)[0]
@@ -220,8 +221,9 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
         v = _device.as_device(vec, op.dtype).reshape(-1)
         n = v.shape[0]
         k = spec["num_matvecs"]
-        if k < 0 or k > n:
-            raise ValueError(decomp._error_num_matvecs(k, maxval=n, minval=0))
+        n_total = getattr(op, "n_global", n)
+        if k < 0 or k > n_total:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=n_total, minval=0))
         alphas, betas, init_len, Q, _ = decomp.lanczos_blocked(
             op, v.reshape(n, 1), k, spec["reortho"], want_Q=True, want_residual=False)
         known = None

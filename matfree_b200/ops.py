@@ -176,6 +176,16 @@ def csr_from_scipy(mat, dtype=None) -> CsrOperator:
     return CsrOperator(mat.indptr.astype(np.int32), mat.indices.astype(np.int32), data, mat.shape[0])
 
 
+def csr_row_sharded(indptr, indices, data, n, row_start, group=None):
+    """Rows ``[row_start, row_start + len(indptr) - 1)`` of a global ``n x n`` CSR operator; the
+    other rows live on the other ranks of `group` (`matfree_b200._rowshard`).  `indptr` is local
+    (starts at 0), `indices` are global column ids.  Vectors passed to / returned by the
+    decompositions are this rank's row slab."""
+    from matfree_b200 import _rowshard
+
+    return _rowshard.RowShardedCsr(indptr, indices, data, n, row_start, group)
+
+
 def gram(A) -> GramOperator:
     """Gram operator ``v -> A^T (A v)``."""
     return GramOperator(A)

@@ -55,6 +55,41 @@ def laplacian_csr(shape, shift=1.0, dtype="float32", device="cpu"):
     return indptr.to(torch.int32), indices, data
 
 
+def laplacian_csr_rows(shape, r0, r1, shift=1.0, dtype="float32", device="cpu"):
+    """Rows ``[r0, r1)`` of `laplacian_csr(shape, shift)`: local `indptr` (starting at 0), GLOBAL
+    column indices (int64), `data` -- what one rank of a row-sharded run builds, without ever
+    materialising the other rows."""
+    import torch
+
+    shape = tuple(int(s) for s in shape)
+    d = len(shape)
+    dev = torch.device(device)
+    tdt = torch.float64 if str(dtype).endswith("64") else torch.float32
+    idx = torch.arange(int(r0), int(r1), dtype=torch.int64, device=dev)
+    nloc = idx.numel()
+    strides = [int(np.prod(shape[a + 1:])) for a in range(d)]
+    coords = [(idx // strides[a]) % shape[a] for a in range(d)]
+    cols, masks, vals = [], [], []
+    for a in range(d):
+        cols.append(idx - strides[a])
+        masks.append(coords[a] > 0)
+        vals.append(-1.0)
+    cols.append(idx)
+    masks.append(torch.ones(nloc, dtype=torch.bool, device=dev))
+    vals.append(2.0 * d + shift)
+    for a in reversed(range(d)):
+        cols.append(idx + strides[a])
+        masks.append(coords[a] < shape[a] - 1)
+        vals.append(-1.0)
+    mask = torch.stack(masks, dim=1)
+    indptr = torch.zeros(nloc + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(mask.sum(dim=1), dim=0)
+    indices = torch.stack(cols, dim=1)[mask]
+    valrow = torch.tensor(vals, dtype=tdt, device=dev)
+    data = valrow.expand(nloc, -1)[mask].contiguous()
+    return indptr.to(torch.int32), indices, data
+
+
 def laplacian_eigenvalues(shape, shift=1.0):
     """Closed-form spectrum of `laplacian_csr(shape, shift)` (fp64, unsorted)."""
     lam = np.zeros((1,), dtype=np.float64)

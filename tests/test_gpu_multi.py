@@ -65,3 +65,62 @@ def test_probe_sharding_nccl_matches_single_gpu(tmp_path):
         env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("ok") == world
+
+
+_ROW_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MF_ROOT"])
+import matfree_b200 as m
+from matfree_b200 import workloads, _rowshard
+from oracle import prng as oprng
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+world = dist.get_world_size()
+shape = (24, 16, 16)
+n = int(np.prod(shape)); plane = shape[1] * shape[2]
+k = 20
+dev = f"cuda:{local}"
+r0, r1 = _rowshard.slab_range(n, world, rank, align=plane)
+ip, ix, d = workloads.laplacian_csr_rows(shape, r0, r1, shift=1.0, device=dev)
+sop = m.ops.csr_row_sharded(ip, ix, d, n, r0)
+assert sop.plan.lo == (plane if rank > 0 else 0) and sop.plan.hi == (plane if rank < world - 1 else 0)
+ipf, ixf, df = workloads.laplacian_csr(shape, shift=1.0, device=dev)
+op = m.ops.csr(ipf, ixf, df)
+v = oprng.rademacher(oprng.prng_key(1), (1, n), np.float32)[0]   # probe 0 of PRNGKey(1)
+for reortho in ("full", "none"):
+    tri = m.decomp.tridiag_sym(k, reortho=reortho, materialize=False)
+    Q1, (d1, e1), res1, c1 = tri(op, v)                 # whole operator on this GPU
+    Q2, (d2, e2), res2, c2 = tri(sop, v[r0:r1])         # my slab of the row-sharded run
+    assert np.allclose(d2.cpu(), d1.cpu(), rtol=1e-5, atol=1e-5), reortho
+    assert np.allclose(e2.cpu(), e1.cpu(), rtol=1e-5, atol=1e-5), reortho
+    assert np.allclose(float(c2), float(c1), rtol=1e-6)
+    if reortho == "full":
+        assert np.allclose(Q2.cpu(), Q1[:, r0:r1].cpu(), atol=1e-4)
+        assert np.allclose(res2.cpu(), res1[r0:r1].cpu(), atol=1e-3)
+# sharded matvec == slab of the full matvec, bit for bit (same kernel, same row order)
+w1 = op(v)[r0:r1]; w2 = sop(v[r0:r1])
+assert torch.equal(w1, w2)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_row_sharded_tridiag_nccl_matches_single_gpu(tmp_path):
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs >= 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    script = tmp_path / "row_worker.py"
+    script.write_text(_ROW_WORKER)
+    env = dict(os.environ, MF_ROOT=ROOT)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29543", str(script)],
+        env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("ok") == world
