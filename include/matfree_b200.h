@@ -95,6 +95,9 @@ typedef struct mf_operator {
                              * of `values` made by mf_operator_split.  With them the
                              * operator runs on the tcgen05 tensor cores (3xTF32);
                              * without them on the CUDA-core kernel.                */
+  int32_t csr_max_row_nnz; /* CSR, optional hint: longest row.  Above 128 the product takes
+                            * the load-balanced route for irregular matrices (long rows cut
+                            * into 512-non-zero segments, one CTA each); 0 = unknown/regular */
 } mf_operator_t;
 
 const char* mf_last_error(void);
@@ -288,6 +291,18 @@ int32_t mf_tridiag_funm_e1(const void* alphas, const void* betas, int32_t dtype,
                            void* stream);
 int32_t mf_basis_combine(const void* Q, const void* coeffs, const void* scale, int32_t dtype,
                          int64_t n, int64_t ld, int64_t k, void* out, void* stream);
+
+/* funm.funm_lanczos_sym (matfree/funm.py:114-147) WITHOUT a stored basis, for sizes where
+ * Q[k][n][ld] does not fit (BASELINE config 5: n = 1e7, k = 30, 256 probes per tile would
+ * need 307 GB): the three-term recurrence (reortho = "none") is run twice -- pass 1 yields
+ * T, from which y = f(T) e1 per probe; pass 2 repeats the (deterministic, hence bit-identical)
+ * recurrence and accumulates out[n][ld] = |v0| * sum_j y_j v_j on the way.  Twice the
+ * matvecs, three block vectors of memory.  Columns num_probes..ld-1 of V0 must be valid
+ * (e.g. zero) but their output is unspecified. */
+int64_t mf_funm_lanczos_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k);
+int32_t mf_funm_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t num_probes,
+                        int64_t k, int32_t fn, double fn_param, void* out, void* workspace,
+                        int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

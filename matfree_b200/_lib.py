@@ -7,7 +7,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmatfree_b200.so")
+LIB_PATH = os.environ.get("MF_LIB_PATH") or os.path.join(_HERE, "_lib", "libmatfree_b200.so")
 
 MF_F32, MF_F64 = 0, 1
 MF_SAMPLER_SIGNS, MF_SAMPLER_NORMAL = 0, 1
@@ -33,6 +33,7 @@ class MfOperator(Structure):
         ("indices", c_void_p),
         ("lda", c_int64),
         ("split_planes", c_void_p),
+        ("csr_max_row_nnz", c_int32),
     ]
 
 
@@ -98,6 +99,9 @@ SIGNATURES = {
                                        c_int32, c_uint32, c_uint32, c_int64, c_int64, c_int64,
                                        c_int64, c_int32, c_int32, c_double, c_void_p, c_void_p,
                                        c_int64, c_void_p]),
+    "mf_funm_lanczos_workspace_bytes": (c_int64, [_OP, c_int64, c_int64]),
+    "mf_funm_lanczos": (c_int32, [_OP, c_void_p, c_int64, c_int64, c_int64, c_int32, c_double,
+                                  c_void_p, c_void_p, c_int64, c_void_p]),
     "mf_tridiag_funm_e1": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
                                      c_int32, c_double, c_void_p, c_void_p, c_int64, c_void_p]),
     "mf_basis_combine": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64,

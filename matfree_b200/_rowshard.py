@@ -169,12 +169,13 @@ class RowShardedCsr(ops.Operator):
             cmin, cmax = self.r0, self.r1
         self.plan = make_plan(self.r0, self.r1, min(cmin, self.r0), max(cmax, self.r1), group)
         self.indices = (gidx + (self.plan.pad - self.plan.c0)).to(torch.int32)  # extended-block columns
+        self.max_row_nnz = int((self.indptr[1:] - self.indptr[:-1]).max()) if self.n > 0 else 0
 
     def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
-                               lda=0, split_planes=None)
+                               lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz)
 
     @property
     def shape(self):
@@ -193,8 +194,14 @@ class RowShardedCsr(ops.Operator):
         """``W[n_loc][ld] = A[r0:r1, :] @ X`` with `Xext` the extended block (halo filled)."""
         lib = _lib.load()
         st = self._struct()
-        _lib.check(lib.mf_matmat(ctypes.byref(st), Xext.data_ptr(), W.data_ptr(), Xext.shape[1],
-                                 None, 0, _device.stream()))
+        ld = Xext.shape[1]
+        ws = getattr(self, "_mm_ws", None)
+        if ws is None or ws[0] != ld:
+            nbytes = lib.mf_matmat_workspace_bytes(ctypes.byref(st), ld)
+            ws = (ld, _device.workspace(nbytes))
+            self._mm_ws = ws
+        _lib.check(lib.mf_matmat(ctypes.byref(st), Xext.data_ptr(), W.data_ptr(), ld,
+                                 ws[1].data_ptr(), ws[1].numel(), _device.stream()))
 
     def matmat_blocked(self, X):
         import torch

@@ -147,6 +147,7 @@ int32_t validate_op(const mf_operator_t* op) {
 
 // Scratch an operator application needs (carved from the caller's workspace).
 struct OpScratch {
+  void* spmm;    // CSR with very long rows: segment list + partial sums of the irregular route
   void* gram;    // SIMT Gram path: Y = A X, m*ld elements
   void* xsplit;  // tcgen05 path: TF32 planes of X, 2*n*ld floats
   void* tsplit;  // tcgen05 Gram path: TF32 planes of A X, 2*m*ld floats
@@ -172,9 +173,17 @@ bool use_tc(const mf_operator_t* op, int64_t ld) {
   return tc_gemm_supported(op->lda, rows, op->n, ld, op->dtype);
 }
 
+bool csr_irregular(const mf_operator_t* op) {
+  return op->kind == MF_OP_CSR && op->csr_max_row_nnz > kSpmmLongRow;
+}
+
 void carve_op_scratch(Arena& a, const mf_operator_t* op, int64_t ld, OpScratch* s) {
   memset(s, 0, sizeof(*s));
   const int64_t es = (int64_t)dtype_size(op->dtype);
+  if (csr_irregular(op)) {
+    s->spmm = a.take(spmm_irregular_scratch_bytes(op->nnz, ld, op->dtype));
+    return;
+  }
   if (use_tc(op, ld)) {
     s->xsplit = a.take(2 * op->n * ld * 4);
     if (op->kind == MF_OP_GRAM) s->tsplit = a.take(2 * op->m * ld * 4);
@@ -190,6 +199,15 @@ int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W,
                  cudaStream_t st) {
   *fused = false;
   if (op->kind == MF_OP_CSR) {
+    if (csr_irregular(op)) {
+      if (scr.spmm == nullptr) {
+        set_error("csr operator with long rows: workspace for the segment list is missing");
+        return MF_ERR_WORKSPACE;
+      }
+      // the caller forms the alpha dot with a separate kernel on this route
+      return launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X, s,
+                             W, ld, nullptr, nullptr, st, scr.spmm);
+    }
     MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X, s, W,
                            ld, red, tickets, st));
     *fused = red != nullptr;
@@ -281,9 +299,17 @@ inline void* row(void* base, int64_t j, int64_t ld, int32_t dtype) {
 // and v_j = r_j / beta_{j-1} is formed on the fly by the consumers.
 //   v0_owned: V0 may be overwritten (fused estimator) -> one buffer less.
 //   have_len: init_len and inv[0] were already written (by the probe generator).
+// What the second pass of the two-pass f(A)v accumulates while the recurrence is re-run:
+// out += (coeffs[j] * len) * v_j  (matfree/funm.py:145 without the stored basis).
+struct BasisAccum {
+  const void* coeffs;  // [k][ld]  y = f(T) e1 per probe
+  void* out;           // [n][ld]
+};
+
 int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have_len, int64_t ld,
                      int64_t k, void* alphas, void* betas, void* init_len, void* Q,
-                     void* residual, const LanczosBufs& b, cudaStream_t st) {
+                     void* residual, const LanczosBufs& b, cudaStream_t st,
+                     const BasisAccum* accum = nullptr) {
   const int32_t dt = op->dtype;
   const int64_t n = op->n;
   const int64_t blk = n * ld * (int64_t)dtype_size(dt);
@@ -303,6 +329,9 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have
       X = Qj;
       sx = nullptr;
     }
+    if (accum != nullptr)  // v_j = Rc * sc
+      MF_TRY(launch_axpy_cols(Rc, row(const_cast<void*>(accum->coeffs), j, ld, dt), sc, init_len,
+                              accum->out, j == 0, dt, n, ld, st));
     void* aj = row(alphas, j, ld, dt);
     const Reduce red_a{b.partial, Finalize{b.counter, 0, aj, nullptr, nullptr}};
     bool fused = false;
@@ -777,6 +806,67 @@ int32_t mf_full_offdiag(void* offdiag_row, const void* h_row, int32_t dtype, int
     return MF_ERR_INVALID_ARGUMENT;
   }
   return launch_full_offdiag(offdiag_row, h_row, dtype, ld, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ two-pass f(A) v
+
+struct FunmBufs {
+  void *alphas, *betas, *len, *coeffs;
+  double* qwork;
+  LanczosBufs lb;
+};
+
+static int32_t carve_funm(Arena& a, const mf_operator_t* op, int64_t ld, int64_t k, FunmBufs* f) {
+  const int64_t es = (int64_t)dtype_size(op->dtype);
+  memset(f, 0, sizeof(*f));
+  f->alphas = a.take((k + 1) * ld * es);
+  f->betas = a.take((k + 1) * ld * es);
+  f->len = a.take(ld * es);
+  f->coeffs = a.take((k + 1) * ld * es);
+  f->qwork = (double*)a.take((2 + k) * k * ld * 8);
+  MF_TRY(carve_lanczos(a, op, ld, k, MF_REORTHO_NONE, &f->lb));
+  if (!a.dry && a.used > a.size) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+              (long long)a.size);
+    return MF_ERR_WORKSPACE;
+  }
+  return MF_OK;
+}
+
+int64_t mf_funm_lanczos_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k) {
+  if (check_lanczos_args(op, ld, k, MF_REORTHO_NONE) != MF_OK) return -1;
+  Arena a(nullptr, 0, true);
+  FunmBufs f;
+  carve_funm(a, op, ld, k, &f);
+  return a.used + 256;
+}
+
+int32_t mf_funm_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t num_probes,
+                        int64_t k, int32_t fn, double fn_param, void* out, void* workspace,
+                        int64_t workspace_bytes, void* stream) {
+  MF_TRY(check_lanczos_args(op, ld, k, MF_REORTHO_NONE));
+  if (V0 == nullptr || out == nullptr || k < 1 || num_probes < 1 || num_probes > ld ||
+      fn == MF_FN_NONE) {
+    set_error("funm_lanczos: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena a(workspace, workspace_bytes, false);
+  FunmBufs f;
+  MF_TRY(carve_funm(a, op, ld, k, &f));
+  MF_TRY(zero_counter(f.lb, st));
+  const int32_t dt = op->dtype;
+  // pass 1: the tridiagonal matrix (no basis kept)
+  MF_TRY(lanczos_none(op, (void*)V0, false, false, ld, k, f.alphas, f.betas, f.len, nullptr,
+                      nullptr, f.lb, st));
+  // y = f(T) e1 per probe
+  MF_TRY(launch_tridiag_quad(f.alphas, f.betas, nullptr, dt, ld, num_probes, k, fn, fn_param,
+                             nullptr, nullptr, nullptr, f.coeffs, f.qwork, st));
+  // pass 2: the same recurrence again (bit-identical: the kernels are deterministic),
+  // accumulating |v0| * sum_j y_j v_j on the way
+  const BasisAccum acc{f.coeffs, out};
+  return lanczos_none(op, (void*)V0, false, true, ld, k, f.alphas, f.betas, f.len, nullptr, nullptr,
+                      f.lb, st, &acc);
 }
 
 // ------------------------------------------------------------------ fused estimator

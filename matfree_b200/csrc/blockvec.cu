@@ -120,6 +120,33 @@ scale_kernel(const T* __restrict__ X, const T* __restrict__ s, T* __restrict__ o
   }
 }
 
+// out (+)= (coef * s1 * s2)[column] * X : one term of  |v| * sum_j v_j y_j  (matfree/funm.py:145)
+// accumulated while the Lanczos recurrence is re-run (two-pass f(A)v, no stored basis)
+template <typename T, int VEC, bool FIRST>
+__global__ void __launch_bounds__(kBlock)
+axpy_cols_kernel(const T* __restrict__ X, const T* __restrict__ coef, const T* __restrict__ s1,
+                 const T* __restrict__ s2, T* __restrict__ out, int64_t total, int ld) {
+  T c[VEC], a[VEC], b[VEC];
+  load_cols<T, VEC>(coef, ld, c, T(1));
+  load_cols<T, VEC>(s1, ld, a, T(1));
+  load_cols<T, VEC>(s2, ld, b, T(1));
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) c[i] = c[i] * a[i] * b[i];
+  MF_FLAT_LOOP(total) {
+    T x[VEC], o[VEC];
+    load_chunk<T, VEC>(X, f, x);
+    if (FIRST) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] = c[i] * x[i];
+    } else {
+      load_chunk<T, VEC>(out, f, o);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o[i] += c[i] * x[i];
+    }
+    store_chunk<T, VEC>(out, f, o);
+  }
+}
+
 // CGS dots for JB basis vectors at a time; V is re-read once per group of JB.
 template <typename T, int VEC, int JB>
 __global__ void __launch_bounds__(kBlock)
@@ -429,6 +456,29 @@ int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t 
     kern<<<grid, kBlock, 0, st>>>((const T*)X, (const T*)s, (T*)out, mode, total, (int)ld);
   });
   return check_launch("scale");
+}
+
+int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const void* s2, void* out,
+                         bool first, int32_t dtype, int64_t n, int64_t ld, cudaStream_t st) {
+  MF_KSCOPE(MF_KC_OTHER, st);
+  const int64_t total = n * ld;
+  const bool mf_wide = wide_ok(dtype, total, X, out);
+  if (first) {
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = axpy_cols_kernel<T, VEC, true>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)X, (const T*)coef, (const T*)s1, (const T*)s2, (T*)out,
+                                    total, (int)ld);
+    });
+  } else {
+    MF_DISPATCH_TV(dtype, ld, {
+      auto kern = axpy_cols_kernel<T, VEC, false>;
+      const int grid = MF_STREAM_GRID(kern, total, VEC);
+      kern<<<grid, kBlock, 0, st>>>((const T*)X, (const T*)coef, (const T*)s1, (const T*)s2, (T*)out,
+                                    total, (int)ld);
+    });
+  }
+  return check_launch("axpy_cols");
 }
 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,

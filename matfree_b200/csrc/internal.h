@@ -42,6 +42,9 @@ int32_t launch_lanczos_update(const void* W, const void* Rc, const void* sc, con
 // out = X * s (mode 0) or X / s (mode 1), per column; s may be null (copy)
 int32_t launch_scale(const void* X, const void* s, void* out, int mode, int32_t dtype,
                      int64_t n, int64_t ld, cudaStream_t st);
+// out (+)= (coef .* s1 .* s2)[column] * X   (null scalars = 1; first: out is overwritten)
+int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const void* s2, void* out,
+                         bool first, int32_t dtype, int64_t n, int64_t ld, cudaStream_t st);
 // CGS pass, dots: h[j][c] = sum_r Q[j][r][c] * V[r][c], j = 0..nq-1
 // (matfree/decomp.py:463,468).  partial: double[4][kMaxPartialCtas*ld]
 // dbl_out (optional): the fp64 sums [nq][ld] (row-sharded drivers all-reduce these)
@@ -77,10 +80,16 @@ int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dty
 // of (X*s) * W -> red->fin   (the Lanczos alpha, decomp.py:288).
 // tickets (optional): two zeroed unsigned ints; chunks of rows are then handed out in
 // global row order (re-armed by the kernel itself).
+// irregular_scratch (optional, spmm_irregular_scratch_bytes): the route for matrices with very
+// long rows (mf_operator_t::csr_max_row_nnz > kSpmmLongRow): rows above that length are cut into
+// segments of kSpmmSegNnz non-zeros, one CTA each; no fused dot on that route (red must be null).
+constexpr int kSpmmLongRow = 128;
+constexpr int kSpmmSegNnz = 512;
+int64_t spmm_irregular_scratch_bytes(int64_t nnz, int64_t ld, int32_t dtype);
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
-                        cudaStream_t st);
+                        cudaStream_t st, void* irregular_scratch = nullptr);
 
 // ---- gemm.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)

@@ -81,6 +81,27 @@ __device__ __forceinline__ void stw(T* __restrict__ W, int64_t off, const T (&v)
   }
 }
 
+// Irregular matrices (power-law graphs, BASELINE config 5): rows longer than kLongRow are not
+// multiplied by the row-group that meets them; they are cut into segments of kSegNnz non-zeros
+// and appended to a work list that spmm_long_rows_kernel (one CTA per segment) drains afterwards.
+constexpr int kLongRow = kSpmmLongRow;
+constexpr int kSegNnz = kSpmmSegNnz;
+struct LongSeg {
+  int32_t row;       // global row
+  int32_t j0, j1;    // non-zero range of this segment
+  int32_t nseg;      // segments of this row
+  int32_t seg;       // index of this segment within the row
+  int32_t slot0;     // first partial-sum slot of the row (multi-segment rows), else -1
+  int32_t head;      // list index of the row's first segment (its `ticket` counts arrivals)
+  unsigned int ticket;
+};
+struct LongList {
+  LongSeg* segs;          // capacity max_segs
+  unsigned int* counts;   // [0] segments, [1] slots   (zeroed before the launch)
+  int64_t max_segs, max_slots;
+};
+static_assert(sizeof(LongSeg) == 32, "scratch sizing assumes 32-byte list entries");
+
 struct SpmmParams {
   int ld;              // tile width (power of two)
   int rows_per_chunk;  // R, a multiple of the CTA sweep
@@ -127,13 +148,13 @@ __device__ __forceinline__ void prefetch_row_l1(const int32_t* __restrict__ ptrb
 // LD > 0: the tile width is a compile-time constant (address arithmetic folds into one
 // IMAD.WIDE per gather); LD == 0: any power of two, read from p.ld.
 // PIPE: the gathers of the next row are issued before the current row is multiplied.
-template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT>
-__global__ void __launch_bounds__(kBlock, PIPE ? 3 : 4)
+template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT, bool DEFER = false>
+__global__ void __launch_bounds__(kBlock, (PIPE || DEFER) ? 3 : 4)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
                 unsigned int* __restrict__ progress, double* __restrict__ partial,
-                Finalize fin) {
+                Finalize fin, LongList longs) {
   __shared__ int32_t s_ptr[3][kMaxRows + 1];
   __shared__ int32_t s_col[2][kCap];
   __shared__ T s_val[2][kCap];
@@ -195,6 +216,30 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     }
   };
 
+  // hand a long row to the segment list (one thread of the row-group)
+  auto defer_row = [&](int64_t row, int32_t jb, int32_t je) {
+    if ((threadIdx.x % tpr) != 0) return;
+    const int len = je - jb;
+    const int nseg = (len + kSegNnz - 1) / kSegNnz;
+    const unsigned int first = atomicAdd(longs.counts, (unsigned int)nseg);
+    int slot0 = -1;
+    if (nseg > 1) slot0 = (int)atomicAdd(longs.counts + 1, (unsigned int)nseg);
+    if ((int64_t)first + nseg > longs.max_segs || (nseg > 1 && (int64_t)slot0 + nseg > longs.max_slots))
+      __trap();  // cannot happen: capacities are upper bounds derived from nnz
+    for (int q = 0; q < nseg; ++q) {
+      LongSeg e;
+      e.row = (int32_t)row;
+      e.j0 = jb + q * kSegNnz;
+      e.j1 = e.j0 + kSegNnz < je ? e.j0 + kSegNnz : je;
+      e.nseg = nseg;
+      e.seg = q;
+      e.slot0 = slot0;
+      e.head = (int32_t)first;
+      e.ticket = 0u;
+      longs.segs[first + q] = e;
+    }
+  };
+
   int64_t ch = blockIdx.x;
   issue_ptr(ch, 0);
   issue_ptr(ch + G, 1);
@@ -244,10 +289,34 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     if (total > kCap) {
       // oversized chunk (very long rows): plain serial loop over global metadata
       for (int lr = my_row; lr < nr; lr += rps) {
+        const int32_t jb = ptrb[lr], je = ptrb[lr + 1];
+        if (DEFER && je - jb > kLongRow) {
+          defer_row(r0 + lr, jb, je);
+          continue;
+        }
         T sum[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) sum[i] = T(0);
-        for (int j = ptrb[lr]; j < ptrb[lr + 1]; ++j) {
+        int32_t j = jb;
+        if constexpr (DEFER) {
+          for (; j + 8 <= je; j += 8) {  // eight independent gathers in flight
+            int32_t c[8];
+            T a[8], x[8][VEC];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              c[u] = __ldg(indices + j + u);
+              a[u] = __ldg(data + j + u);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ldx<T, VEC>(Xc, (int64_t)c[u] * ld, x[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) sum[i] += a[u] * x[u][i];
+            }
+          }
+        }
+        for (; j < je; ++j) {
           const int32_t c = __ldg(indices + j);
           const T a = __ldg(data + j);
           T x[VEC];
@@ -271,7 +340,21 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
             for (int i = 0; i < VEC; ++i) sum[i] += a * r.x[u][i];
           }
         }
-        for (int u = SEGL; u < r.len; ++u) {
+        int u = SEGL;
+        if constexpr (DEFER) {
+          for (; u + 8 <= r.len; u += 8) {  // long tail: eight independent gathers in flight
+            T x[8][VEC];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ldx<T, VEC>(Xc, (int64_t)colb[r.jb + u + q] * ld, x[q]);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const T a = valb[r.jb + u + q];
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) sum[i] += a * x[q][i];
+            }
+          }
+        }
+        for (; u < r.len; ++u) {
           const T a = valb[r.jb + u];
           T x[VEC];
           ldx<T, VEC>(Xc, (int64_t)colb[r.jb + u] * ld, x);
@@ -296,6 +379,10 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
         }
       } else {
         for (int lr = my_row; lr < nr; lr += rps) {
+          if (DEFER && ptrb[lr + 1] - ptrb[lr] > kLongRow) {
+            defer_row(r0 + lr, ptrb[lr], ptrb[lr + 1]);
+            continue;
+          }
           RowRegs<T, VEC, SEGL> ra;
           issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra);
           if (p.l1pf) {
@@ -323,6 +410,99 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     }
   }
   if (FUSE_DOT) cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
+}
+
+// One CTA per segment of a long row: the CTA's row-groups take the segment's non-zeros
+// round-robin (eight gathers in flight each), their sums are added in group order in shared
+// memory; a multi-segment row parks its segment sums in `slots` and the CTA that completes the
+// row (ticket on the row's first list entry) adds them in segment order -> deterministic.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+spmm_long_rows_kernel(const int32_t* __restrict__ indices, const T* __restrict__ data,
+                      const T* __restrict__ X, const T* __restrict__ s, T* __restrict__ W, int ld,
+                      LongList longs, T* __restrict__ slots) {
+  __shared__ T red[kBlock * VEC];
+  __shared__ bool last;
+  const int tpr = ld / VEC;
+  const int rps = kBlock / tpr;
+  const int g = threadIdx.x / tpr;
+  const int c0 = (threadIdx.x % tpr) * VEC;
+  const T* __restrict__ Xc = X + c0;
+  const unsigned int nsegs = *reinterpret_cast<volatile unsigned int*>(longs.counts);
+  for (unsigned int e = blockIdx.x; e < nsegs; e += gridDim.x) {
+    const LongSeg sg = longs.segs[e];
+    T sum[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) sum[i] = T(0);
+    int32_t j = sg.j0 + g;
+    for (; j + 7 * rps < sg.j1; j += 8 * rps) {
+      int32_t c[8];
+      T a[8], x[8][VEC];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        c[u] = __ldg(indices + j + u * rps);
+        a[u] = __ldg(data + j + u * rps);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ldx<T, VEC>(Xc, (int64_t)c[u] * ld, x[u]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sum[i] += a[u] * x[u][i];
+      }
+    }
+    for (; j < sg.j1; j += rps) {
+      const int32_t c = __ldg(indices + j);
+      const T a = __ldg(data + j);
+      T x[VEC];
+      ldx<T, VEC>(Xc, (int64_t)c * ld, x);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) sum[i] += a * x[i];
+    }
+    __syncthreads();  // previous iteration's readers of `red` are done
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) red[threadIdx.x * VEC + i] = sum[i];
+    __syncthreads();
+    // group 0 adds the groups in order: element (g, c0 + i) sits at red[(g * tpr + c0 / VEC) * VEC + i]
+    if (g == 0) {
+      for (int q = 1; q < rps; ++q) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) sum[i] += red[(q * tpr + threadIdx.x) * VEC + i];
+      }
+      if (sg.nseg == 1) {
+        T w[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) w[i] = sum[i] * (s ? s[c0 + i] : T(1));
+        stw<T, VEC>(W + c0, (int64_t)sg.row * ld, w);
+      } else {
+        T* slot = slots + (int64_t)(sg.slot0 + sg.seg) * ld + c0;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) slot[i] = sum[i];
+      }
+    }
+    if (sg.nseg > 1) {
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0)
+        last = atomicAdd(&longs.segs[sg.head].ticket, 1u) == (unsigned int)sg.nseg - 1;
+      __syncthreads();
+      if (last && g == 0) {
+        __threadfence();
+        T tot[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) tot[i] = T(0);
+        for (int q = 0; q < sg.nseg; ++q) {
+          const T* slot = slots + (int64_t)(sg.slot0 + q) * ld + c0;
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) tot[i] += __ldcg(slot + i);
+        }
+        T w[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) w[i] = tot[i] * (s ? s[c0 + i] : T(1));
+        stw<T, VEC>(W + c0, (int64_t)sg.row * ld, w);
+      }
+    }
+  }
 }
 
 int env_int(const char* name, int dflt) {
@@ -359,12 +539,85 @@ int resident_grid(const void* kernel, int block, size_t smem, int64_t want) {
   return (int)g;
 }
 
+int64_t spmm_irregular_scratch_bytes(int64_t nnz, int64_t ld, int32_t dtype) {
+  const int64_t max_segs = nnz / kSegNnz + nnz / kLongRow + 2;
+  const int64_t max_slots = 2 * (nnz / kSegNnz) + 2;
+  return 256 + align_up(max_segs * (int64_t)sizeof(LongSeg), 256) +
+         max_slots * ld * (int64_t)dtype_size(dtype) + 256;
+}
+
+namespace {
+// Irregular route: the row-group kernel with long rows deferred, then the segment kernel.
+template <typename T, int VEC>
+int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T* data, int64_t n,
+                         int64_t nnz, const T* X, const T* s, T* W, int64_t ld, void* scratch,
+                         cudaStream_t st) {
+  char* base = (char*)scratch;
+  LongList longs;
+  longs.counts = (unsigned int*)base;
+  longs.max_segs = nnz / kSegNnz + nnz / kLongRow + 2;
+  longs.max_slots = 2 * (nnz / kSegNnz) + 2;
+  longs.segs = (LongSeg*)(base + 256);
+  T* slots = (T*)(base + 256 + align_up(longs.max_segs * (int64_t)sizeof(LongSeg), 256));
+  if (cudaMemsetAsync(longs.counts, 0, 256, st) != cudaSuccess) {
+    set_error("spmm: counter memset failed");
+    return MF_ERR_CUDA;
+  }
+  const int rps = kBlock / (int)(ld / VEC);
+  // chunks sized for the average row; chunks that still overflow the staging buffer take the
+  // direct-from-global path of the kernel
+  const double avg = (double)nnz / (double)n;
+  int64_t R = 64;
+  const int64_t fit = (int64_t)(kCap / (avg > 1.0 ? avg : 1.0));
+  if (R > fit) R = fit;
+  R = R / rps * rps;
+  if (R < rps) R = rps;
+  const int64_t nchunks = (n + R - 1) / R;
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0};
+  {
+    auto kern = spmm_csr_kernel<T, VEC, 0, 8, false, false, true>;
+    const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);
+    kern<<<grid, kBlock, 0, st>>>(indptr, indices, data, n, X, s, W, prm, nullptr, nullptr,
+                                  Finalize{}, longs);
+    MF_TRY(check_launch("spmm_csr (irregular)"));
+  }
+  {
+    auto kern = spmm_long_rows_kernel<T, VEC>;
+    const int grid = resident_grid((const void*)kern, kBlock, 0, 1 << 20);
+    kern<<<grid, kBlock, 0, st>>>(indices, data, X, s, W, (int)ld, longs, slots);
+  }
+  return check_launch("spmm_long_rows");
+}
+}  // namespace
+
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* progress,
-                        cudaStream_t st) {
+                        cudaStream_t st, void* irregular_scratch) {
   MF_KSCOPE(MF_KC_SPMM_CSR, st);
   if (n <= 0) return MF_OK;
+  if (irregular_scratch != nullptr) {
+    if (red != nullptr) {
+      set_error("spmm: the irregular route does not fuse the dot product");
+      return MF_ERR_INVALID_ARGUMENT;
+    }
+    if (dtype == MF_F32) {
+      if (ld >= 4)
+        return launch_irregular<float, 4>(indptr, indices, (const float*)data, n, nnz,
+                                          (const float*)X, (const float*)s, (float*)W, ld,
+                                          irregular_scratch, st);
+      return launch_irregular<float, 1>(indptr, indices, (const float*)data, n, nnz,
+                                        (const float*)X, (const float*)s, (float*)W, ld,
+                                        irregular_scratch, st);
+    }
+    if (ld >= 2)
+      return launch_irregular<double, 2>(indptr, indices, (const double*)data, n, nnz,
+                                         (const double*)X, (const double*)s, (double*)W, ld,
+                                         irregular_scratch, st);
+    return launch_irregular<double, 1>(indptr, indices, (const double*)data, n, nnz,
+                                       (const double*)X, (const double*)s, (double*)W, ld,
+                                       irregular_scratch, st);
+  }
   const int nv = dtype == MF_F64 ? 2 : 4;
   const int vec = ld >= nv ? nv : 1;
   const int rps = kBlock / (int)(ld / vec);
@@ -398,7 +651,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                     \
     prm.window = grid + (env_slack > 0 ? env_slack : (grid / 4 > 8 ? grid / 4 : 8));           \
     kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,             \
-                                  (const T*)s, (T*)W, prm, progress, partial, fin);            \
+                                  (const T*)s, (T*)W, prm, progress, partial, fin, LongList{}); \
   } while (0)
 #define MF_SPMM_D(T, VEC, LD, SEGL, PIPE)                     \
   do {                                                        \

@@ -205,9 +205,51 @@ integrand_funm_sym_logdet = monte_carlo_funm_sym_logdet
 
 
 def funm_lanczos_sym(dense_funm, tridiag_sym, /):
-    """Matrix-function-vector product ``f(A) v`` via Lanczos (`funm.py:114-147`)."""
+    """Matrix-function-vector product ``f(A) v`` via Lanczos (`funm.py:114-147`).
+
+    With ``reortho="none"`` and a recognised `matfun` the product is formed by the two-pass
+    kernel chain `mf_funm_lanczos` (no stored basis: what makes BASELINE config 5 -- 1e7 rows,
+    4096 probes -- fit at all); otherwise the basis is stored and contracted
+    (`mf_tridiag_funm_e1` + `mf_basis_combine`).  ``estimate.batched(matvec, V)`` applies it to
+    every row of ``V (P, n)`` with all probes of a tile advancing together (what `jax.vmap` of
+    the reference's function does)."""
     spec = getattr(tridiag_sym, "_mf_spec", None)
     matfun = getattr(dense_funm, "_mf_matfun", None)
+
+    def _known():
+        if matfun is not None and (not callable(matfun) or _is_hashable(matfun)):
+            return _known_fn(matfun)
+        return None
+
+    def _check(op, n):
+        k = spec["num_matvecs"]
+        n_total = getattr(op, "n_global", n)
+        if k < 0 or k > n_total:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=n_total, minval=0))
+        return k
+
+    def _two_pass_blocked(op, V0b, num_probes, known):
+        import torch
+
+        lib = _lib.load()
+        n, ld = V0b.shape
+        k = spec["num_matvecs"]
+        st = op._struct()
+        nbytes = lib.mf_funm_lanczos_workspace_bytes(ctypes.byref(st), ld, k)
+        if nbytes < 0:
+            _lib.check(-1)
+        ws = _device.workspace(nbytes)
+        out = torch.empty_like(V0b)
+        _lib.check(lib.mf_funm_lanczos(ctypes.byref(st), V0b.data_ptr(), ld, num_probes, k, known[0],
+                                       known[1], out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                       _device.stream()))
+        return out
+
+    def _use_two_pass(op, known):
+        from matfree_b200 import _rowshard
+
+        return (known is not None and spec["reortho"] == "none" and spec["num_matvecs"] >= 1
+                and not isinstance(op, _rowshard.RowShardedCsr))
 
     def estimate(matvec, vec, *parameters):
         import torch
@@ -220,15 +262,12 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
         lib = _lib.load()
         v = _device.as_device(vec, op.dtype).reshape(-1)
         n = v.shape[0]
-        k = spec["num_matvecs"]
-        n_total = getattr(op, "n_global", n)
-        if k < 0 or k > n_total:
-            raise ValueError(decomp._error_num_matvecs(k, maxval=n_total, minval=0))
+        k = _check(op, n)
+        known = _known()
+        if _use_two_pass(op, known):
+            return _two_pass_blocked(op, v.reshape(n, 1).contiguous(), 1, known)[:, 0]
         alphas, betas, init_len, Q, _ = decomp.lanczos_blocked(
             op, v.reshape(n, 1), k, spec["reortho"], want_Q=True, want_residual=False)
-        known = None
-        if matfun is not None and (not callable(matfun) or _is_hashable(matfun)):
-            known = _known_fn(matfun)
         ld = 1
         if known is not None:
             coeffs = torch.empty((k, ld), dtype=op.dtype, device=v.device)
@@ -246,4 +285,45 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
                                         _device.stream()))
         return out[:, 0]
 
+    def batched(matvec, V, *, tile=None):
+        """``f(A) V[p]`` for every row of ``V (P, n)``; returns ``(P, n)``."""
+        import torch
+
+        if spec is None:
+            raise TypeError("funm_lanczos_sym: tridiag_sym must come from matfree_b200.decomp.tridiag_sym")
+        op = ops.require_operator(matvec, "funm_lanczos_sym")
+        lib = _lib.load()
+        V = _device.as_device(V, op.dtype)
+        P, n = V.shape
+        _check(op, n)
+        known = _known()
+        if not _use_two_pass(op, known):
+            return torch.stack([estimate(op, V[p]) for p in range(P)])
+        ld = int(tile) if tile else _device.ld_for(P)
+        mfdt = _device.mf_dtype(op.dtype)
+        out = torch.empty_like(V)
+        Xb = torch.zeros((n, ld), dtype=op.dtype, device=V.device)
+        for p0 in range(0, P, ld):
+            npb = min(ld, P - p0)
+            if npb < ld:
+                Xb.zero_()
+            _lib.check(lib.mf_to_blocked(V[p0:p0 + npb].data_ptr(), Xb.data_ptr(), mfdt, n, npb, ld,
+                                         _device.stream()))
+            Wb = _two_pass_blocked(op, Xb, npb, known)
+            _lib.check(lib.mf_from_blocked(Wb.data_ptr(), out[p0:p0 + npb].data_ptr(), mfdt, n, npb, ld,
+                                           _device.stream()))
+        return out
+
+    def blocked(matvec, V0b, num_probes=None):
+        """Blocked entry for callers that already hold the probes as ``V0b[n][ld]``: returns
+        ``f(A) V0b`` in the same layout (two-pass route only)."""
+        op = ops.require_operator(matvec, "funm_lanczos_sym")
+        known = _known()
+        if spec is None or not _use_two_pass(op, known):
+            raise TypeError("funm_lanczos_sym.blocked needs reortho='none' and a recognised matfun")
+        _check(op, V0b.shape[0])
+        return _two_pass_blocked(op, V0b, V0b.shape[1] if num_probes is None else num_probes, known)
+
+    estimate.batched = batched
+    estimate.blocked = blocked
     return estimate

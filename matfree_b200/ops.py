@@ -130,12 +130,14 @@ class CsrOperator(Operator):
         self.nnz = int(self.data.shape[0])
         if self.indices.shape[0] != self.nnz:
             raise ValueError("ops.csr: indices and data must have the same length")
+        # longest row: above 128 non-zeros the SpMM takes its load-balanced route
+        self.max_row_nnz = int((self.indptr[1:] - self.indptr[:-1]).max()) if self.n > 0 else 0
 
     def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
-                               lda=0, split_planes=None)
+                               lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz)
 
 
 class GramOperator(Operator):

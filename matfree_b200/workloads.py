@@ -114,6 +114,51 @@ def laplacian_logdet(shape, shift=1.0):
     return total
 
 
+def powerlaw_laplacian_csr(n, num_edges, gamma=2.3, i0=10.0, seed=5, dtype="float32", device="cpu"):
+    """Config 5: graph Laplacian ``L = D - W`` of a Chung-Lu random graph with power-law expected
+    degrees, ``w_i ~ (i + i0)^(-1/(gamma-1))``: `num_edges` endpoint pairs
+    are drawn i.i.d. from the weight distribution, self-loops and duplicates dropped, the rest
+    symmetrised.  Returns ``(indptr, indices, data, d_max)`` as torch tensors on `device` (CSR,
+    int32, columns ascending, diagonal = degree, off-diagonals -1).  The stream is torch's
+    generator with `seed` (a workload generator, not reference functionality)."""
+    import torch
+
+    dev = torch.device(device)
+    n = int(n)
+    tdt = torch.float64 if str(dtype).endswith("64") else torch.float32
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(seed))
+    w = (torch.arange(n, dtype=torch.float64, device=dev) + float(i0)) ** (-1.0 / (gamma - 1.0))
+    cdf = torch.cumsum(w, 0)
+    cdf /= cdf[-1].clone()
+    del w
+    keys = []
+    chunk = 1 << 24
+    for e0 in range(0, int(num_edges), chunk):
+        m = min(chunk, int(num_edges) - e0)
+        src = torch.searchsorted(cdf, torch.rand(m, dtype=torch.float64, device=dev, generator=gen)).clamp_(max=n - 1)
+        dst = torch.searchsorted(cdf, torch.rand(m, dtype=torch.float64, device=dev, generator=gen)).clamp_(max=n - 1)
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        keys.append(src * n + dst)
+        keys.append(dst * n + src)
+    del cdf
+    keys = torch.unique(torch.cat(keys))           # sorted, duplicates removed
+    rows = keys // n
+    deg = torch.bincount(rows, minlength=n)
+    del rows
+    diag = torch.arange(n, dtype=torch.int64, device=dev)
+    keys = torch.sort(torch.cat([keys, diag * n + diag])).values
+    rows = keys // n
+    cols = keys - rows * n
+    del keys
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(deg + 1, 0)
+    is_diag = rows == cols
+    data = torch.where(is_diag, deg[rows].to(tdt), torch.tensor(-1.0, dtype=tdt, device=dev))
+    return indptr.to(torch.int32), cols.to(torch.int32), data, int(deg.max())
+
+
 def tutorial1_dense(n=1000, nrows=1200, dtype=np.float32):
     """Config 1: ``M = A0^T A0 + I`` with ``A0 = reshape(arange(1, 1+nrows*n)) / (nrows*n)``
     (tutorials/1_log_determinants.py:14-21, scaled to n=1000).  Returns (M, A0)."""

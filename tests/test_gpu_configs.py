@@ -107,3 +107,40 @@ def test_c3_scaled_gram_logdet(reortho):
     assert abs(float(mean) - want) <= 1e-5 * abs(want), (float(mean), want)
     truth = np.linalg.slogdet(A64.T @ A64)[1]
     assert abs(float(mean) - truth) <= 4 * float(sem) + 2e-2 * abs(truth)
+
+
+def test_c5_scaled_powerlaw_expm_action():
+    """configs[4] scaled: exp(-t L) v on a power-law graph Laplacian (20 000 nodes, heavy hub
+    rows = the load-imbalance case of the CSR kernel), normal probes, depth 30, two-pass
+    `funm_lanczos_sym`; against dense fp64 eigendecomposition and the stored-basis route."""
+    import scipy.sparse as sp
+
+    from matfree_b200 import workloads
+
+    m = mfb()
+    n, P, k = 20000, 24, 30
+    ip, ix, d, dmax = workloads.powerlaw_laplacian_csr(n, 100_000, device="cuda")
+    assert dmax > 200  # hubs: mean degree is ~10
+    op = m.ops.csr(ip, ix, d)
+    L = sp.csr_matrix((d.cpu().numpy().astype(np.float64), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+    assert abs(L - L.T).max() == 0 and np.allclose(L @ np.ones(n), 0.0)
+    t = 1.0 / dmax
+    V = oprng.normal(oprng.prng_key(1), (P, n), np.float32)
+    tri = m.decomp.tridiag_sym(k, reortho="none")
+    fun = m.funm.funm_lanczos_sym(m.funm.dense_funm_sym_eigh(("exp", -t)), tri)
+    got = fun.batched(op, V).cpu().numpy()
+    # fp64 truth: exp(-tL) V via scipy
+    from scipy.sparse.linalg import expm_multiply
+
+    want = expm_multiply(-t * L, V.T.astype(np.float64)).T
+    err = np.abs(got - want).max() / np.abs(want).max()
+    assert err < 2e-5, err
+    # single-vector call (two-pass) == row of the batched call; stored-basis route agrees
+    one = fun(op, V[3]).cpu().numpy()
+    assert np.allclose(one, got[3], rtol=1e-5, atol=1e-6)
+    full = m.funm.funm_lanczos_sym(m.funm.dense_funm_sym_eigh(("exp", -t)), m.decomp.tridiag_sym(k, reortho="full"))
+    assert np.allclose(full(op, V[3]).cpu().numpy(), want[3], rtol=1e-4, atol=2e-5)
+    # the oracle's funm_lanczos_sym on the same vector
+    ofun = ref.funm_lanczos_sym(ref.dense_funm_sym_eigh(lambda x: np.exp(-t * x)), ref.tridiag_sym(k, reortho="none"))
+    L32 = L.astype(np.float32)
+    assert np.allclose(one, ofun(lambda x: L32 @ x, V[3]), rtol=1e-4, atol=2e-5)

@@ -410,3 +410,44 @@ def test_full_size_properties_laplacian_2d_1024():
     tr = m.stochtrace.estimator_monte_carlo_mean_and_sem(m.stochtrace.monte_carlo_trace(), sampler)
     tmean, tsem = tr(op, m.prng.prng_key(1))
     assert abs(float(tmean) - 5.0 * n) <= 4 * float(tsem) + 1e-5 * n
+
+
+# ------------------------------------------------------------------ irregular CSR (long rows)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("P", [1, 3, 64, 300])
+def test_matmat_csr_long_rows(dtype, P):
+    """Rows far above the 128-non-zero threshold (one of them spanning several 512-non-zero
+    segments, one empty row) take the load-balanced route: result equals SciPy's, and it is
+    deterministic run to run."""
+    import scipy.sparse as sp
+
+    m = mfb()
+    rng = np.random.default_rng(0)
+    n = 3000
+    B = sp.random(n, n, density=0.002, random_state=rng, format="lil", dtype=np.float64)
+    B[5, :] = rng.standard_normal(n)            # 3000 non-zeros: 6 segments
+    B[17, ::3] = 1.5                            # 1000 non-zeros: 2 segments
+    B[40, :300] = -2.0                          # 300 non-zeros: one segment
+    B[41, :] = 0.0                              # empty row
+    A = B.tocsr().astype(dtype)
+    A.sort_indices()
+    op = m.ops.csr_from_scipy(A)
+    assert op.max_row_nnz == n
+    V = oprng.normal(oprng.prng_key(2), (P, n), dtype)
+    got = to_np(op.matmat(V))
+    want = (A.astype(np.float64) @ V.T.astype(np.float64)).T
+    tol = 200 * np.finfo(dtype).eps
+    assert np.allclose(got, want, rtol=tol, atol=tol * np.abs(want).max())
+    assert np.array_equal(got, to_np(op.matmat(V)))
+    # Lanczos on top of it (alpha is formed by the separate dot kernel on this route)
+    S = (A + A.T + sp.identity(n) * 80.0).tocsr().astype(dtype)
+    S.sort_indices()
+    sop = m.ops.csr_from_scipy(S)
+    v = oprng.normal(oprng.prng_key(3), (n,), dtype)
+    _, (d1, e1), _, _ = m.decomp.tridiag_sym(8, reortho="none", materialize=False)(sop, v)
+    od, oe, _ = ref.lanczos_none_batched(lambda X: (S @ X.T).T, v[None, :], 8)
+    rt = 2e-5 if dtype == np.float32 else 1e-10
+    assert np.allclose(to_np(d1), od[0], rtol=rt, atol=rt)
+    assert np.allclose(to_np(e1), oe[0][:7], rtol=rt, atol=rt)
