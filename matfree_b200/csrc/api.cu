@@ -229,17 +229,18 @@ int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W,
     return launch_gemm_tcgen05(op->split_planes, op->lda, true, op->n, op->m, scr.tsplit, 1, s, W,
                                nullptr, ld, variant, st);
   }
+  // fp64 (DMMA when the shape qualifies) and everything the tcgen05 kernel does not take;
+  // mf_gemm_config(.., use_tensor_cores = 0) forces the CUDA-core kernel for cross-checks
+  const auto gemm = g_gemm_tc.load(std::memory_order_relaxed) ? launch_gemm_blocked : launch_gemm_simt;
   if (op->kind == MF_OP_DENSE)
-    return launch_gemm_simt(op->values, op->lda, false, op->n, op->n, X, s, W, ld, op->dtype, st);
+    return gemm(op->values, op->lda, false, op->n, op->n, X, s, W, ld, op->dtype, st);
   if (op->kind == MF_OP_GRAM) {
     if (scr.gram == nullptr) {
       set_error("gram operator needs a scratch block of m*ld elements");
       return MF_ERR_WORKSPACE;
     }
-    MF_TRY(launch_gemm_simt(op->values, op->lda, false, op->m, op->n, X, nullptr, scr.gram, ld,
-                            op->dtype, st));
-    return launch_gemm_simt(op->values, op->lda, true, op->n, op->m, scr.gram, s, W, ld, op->dtype,
-                            st);
+    MF_TRY(gemm(op->values, op->lda, false, op->m, op->n, X, nullptr, scr.gram, ld, op->dtype, st));
+    return gemm(op->values, op->lda, true, op->n, op->m, scr.gram, s, W, ld, op->dtype, st);
   }
   return MF_ERR_INVALID_ARGUMENT;
 }

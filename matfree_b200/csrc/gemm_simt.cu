@@ -107,6 +107,9 @@ int32_t launch_gemm_simt(const void* A, int64_t lda, bool trans, int64_t M, int6
 int32_t launch_gemm_blocked(const void* A, int64_t lda, bool trans, int64_t M, int64_t K,
                             const void* B, const void* colscale, void* C, int64_t ld,
                             int32_t dtype, cudaStream_t st) {
+  // x64 operators: FP64 tensor cores (gemm_dmma.cu) whenever the shape qualifies
+  if (dmma_gemm_supported(A, lda, M, K, B, C, ld, dtype))
+    return launch_gemm_dmma(A, lda, trans, M, K, B, colscale, C, ld, st);
   return launch_gemm_simt(A, lda, trans, M, K, B, colscale, C, ld, dtype, st);
 }
 

@@ -91,15 +91,24 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
                         void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
                         cudaStream_t st, void* irregular_scratch = nullptr);
 
-// ---- gemm.cu
+// ---- gemm_simt.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)
 // colscale (optional, [ld]): C[:, c] is multiplied by colscale[c] in the epilogue
+// launch_gemm_blocked: fp64 -> DMMA kernel when the shape qualifies, else the CUDA-core kernel
 int32_t launch_gemm_blocked(const void* A, int64_t lda, bool trans, int64_t M, int64_t K,
                             const void* B, const void* colscale, void* C, int64_t ld,
                             int32_t dtype, cudaStream_t st);
 int32_t launch_gemm_simt(const void* A, int64_t lda, bool trans, int64_t M, int64_t K,
                          const void* B, const void* colscale, void* C, int64_t ld,
                          int32_t dtype, cudaStream_t st);
+
+// ---- gemm_dmma.cu : fp64 on the FP64 tensor cores (mma.sync m8n8k4 -> DMMA.8x8x4)
+// fp64, ld a multiple of 32, lda even, 16-byte aligned pointers
+bool dmma_gemm_supported(const void* A, int64_t lda, int64_t M, int64_t K, const void* B,
+                         const void* C, int64_t ld, int32_t dtype);
+int32_t launch_gemm_dmma(const void* A, int64_t lda, bool trans, int64_t M, int64_t K,
+                         const void* B, const void* colscale, void* C, int64_t ld,
+                         cudaStream_t st);
 
 // ---- gemm_tcgen05.cu : fp32 via 3xTF32 on the tcgen05 tensor cores
 // Can the tensor-core kernel take this problem?  (fp32, ld in {32,64,128,256},
