@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 2
+#define MF_ABI_VERSION 3
 
 /* status codes */
 #define MF_OK 0
@@ -40,6 +40,7 @@ extern "C" {
 #define MF_ERR_CUDA (-2)
 #define MF_ERR_UNSUPPORTED (-3)
 #define MF_ERR_WORKSPACE (-4)
+#define MF_ERR_PEER_TIMEOUT (-5) /* a rank of a communicator did not arrive (mf_comm_status) */
 
 /* dtypes */
 #define MF_F32 0
@@ -303,6 +304,83 @@ int64_t mf_funm_lanczos_workspace_bytes(const mf_operator_t* op, int64_t ld, int
 int32_t mf_funm_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t num_probes,
                         int64_t k, int32_t fn, double fn_param, void* out, void* workspace,
                         int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ multi-GPU (row sharding)
+ * One process per GPU.  A communicator owns one device region per rank -- a control block plus
+ * a "heap" the caller places extended Lanczos blocks in -- that every rank maps into its own
+ * address space (CUDA IPC), so that kernels of this library reach the other GPUs with plain
+ * loads / stores over NVLink:
+ *   - every reduction of a sharded decomposition is all-reduced INSIDE the reducing kernel
+ *     (the last CTA pushes its fp64 sums to all ranks, flag handshake, sum in rank order:
+ *     deterministic and bit-identical on all ranks), replacing the all-reduce XLA inserts after
+ *     `linalg.inner` / `vector_norm` on a row-sharded array (matfree/decomp.py:288,290,463,468,471);
+ *   - the halo rows a rank's CSR rows reference are stored straight into the neighbours'
+ *     extended blocks before every product (the collective-permute before decomp.py:287,460).
+ * These are the only entry points that own device memory (mf_comm_create / mf_comm_destroy)
+ * or synchronise (mf_comm_status); they are set-up / tear-down calls, not on the per-step path.
+ *
+ * Set-up: mf_comm_create on every rank; exchange the MF_COMM_HANDLE_BYTES-byte handles of
+ * mf_comm_handle between the ranks by any host channel, in rank order; mf_comm_connect.
+ * All ranks must issue the same sequence of communicating calls (as with NCCL). */
+#define MF_COMM_HANDLE_BYTES 64
+typedef struct mf_comm mf_comm_t;
+int32_t mf_comm_create(int32_t world, int32_t rank, int64_t heap_bytes, mf_comm_t** comm);
+int32_t mf_comm_handle(const mf_comm_t* comm, void* h_handle);
+int32_t mf_comm_connect(mf_comm_t* comm, const void* h_handles /* [world][64] */);
+void* mf_comm_heap(const mf_comm_t* comm);
+int64_t mf_comm_heap_bytes(const mf_comm_t* comm);
+/* Synchronises `stream`; MF_ERR_PEER_TIMEOUT if an in-kernel wait gave up (20 s). */
+int32_t mf_comm_status(const mf_comm_t* comm, void* stream);
+int32_t mf_comm_barrier(const mf_comm_t* comm, void* stream);
+/* Tear-down in two phases: every rank unmaps its peers' regions (mf_comm_disconnect), the host
+ * layer synchronises the ranks, then every rank frees its own region (mf_comm_destroy). */
+int32_t mf_comm_disconnect(mf_comm_t* comm);
+int32_t mf_comm_destroy(mf_comm_t* comm);
+
+/* Halo plan of one rank.  Its extended block is `rows_alloc` rows [rows_alloc][ld]: padding,
+ * lower halo, the n owned rows starting at `mid_row`, upper halo.  `sends[i]`: `rows` rows
+ * starting at row `src_row` of MY extended block go to row `dst_row` of rank `peer`'s extended
+ * block (which has `dst_rows_alloc` rows).  `recv_peers`: the ranks that send to me. */
+typedef struct mf_halo_send {
+  int32_t peer;
+  int64_t src_row, rows, dst_row, dst_rows_alloc;
+} mf_halo_send_t;
+typedef struct mf_halo_plan {
+  int64_t rows_alloc, mid_row;
+  int32_t num_sends;
+  const mf_halo_send_t* sends; /* HOST array */
+  int32_t num_recv_peers;
+  const int32_t* recv_peers; /* HOST array */
+} mf_halo_plan_t;
+
+/* Fill the halo rows of extended block number `block_index` of the array of extended blocks
+ * that starts `heap_offset` bytes into every rank's heap.  `barrier_first`: pass 1 when the
+ * block's previous content may still be read by a peer's product that no reduction separates
+ * from this call. */
+int32_t mf_halo_exchange(const mf_comm_t* comm, const mf_halo_plan_t* plan, int64_t heap_offset,
+                         int64_t block_index, int64_t ld, int32_t dtype, int32_t barrier_first,
+                         void* stream);
+
+/* decomp.tridiag_sym on a ROW-SHARDED CSR operator, the whole k-step loop enqueued by one call
+ * (matfree/decomp.py:125-145,426-477 for MF_REORTHO_FULL, :220-292 for MF_REORTHO_NONE; same
+ * outputs as mf_lanczos, all scalars identical on every rank).  `op_local`: this rank's CSR
+ * rows, n = local rows, column ids relative to its extended block.  V0: the rank's rows of
+ * the start block [n][ld] (anywhere).  The extended blocks live in the communicator heap at
+ * `heap_offset` (the same on all ranks):
+ *   MF_REORTHO_FULL: k extended blocks -- the basis; vector i of the basis is rows
+ *                    [mid_row, mid_row + n) of block i;
+ *   MF_REORTHO_NONE: 2 extended blocks (ping-pong), plus k more when want_Q != 0.
+ * mf_lanczos_sharded_heap_bytes gives the size.  comm may be NULL (or a 1-rank communicator)
+ * together with ext != NULL pointing at ordinary device memory of that size. */
+int64_t mf_lanczos_sharded_heap_bytes(const mf_halo_plan_t* plan, int64_t ld, int64_t k,
+                                      int32_t reortho, int32_t want_Q, int32_t dtype);
+int64_t mf_lanczos_sharded_workspace_bytes(const mf_operator_t* op_local, int64_t ld, int64_t k,
+                                           int32_t reortho);
+int32_t mf_lanczos_sharded(const mf_comm_t* comm, const mf_operator_t* op_local,
+                           const mf_halo_plan_t* plan, const void* V0, int64_t ld, int64_t k,
+                           int32_t reortho, int32_t want_Q, int64_t heap_offset, void* ext,
+                           void* alphas, void* betas, void* init_len, void* residual,
+                           void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,19 @@ class MfOperator(Structure):
     ]
 
 
+class MfHaloSend(Structure):
+    _fields_ = [("peer", c_int32), ("src_row", c_int64), ("rows", c_int64), ("dst_row", c_int64),
+                ("dst_rows_alloc", c_int64)]
+
+
+class MfHaloPlan(Structure):
+    _fields_ = [("rows_alloc", c_int64), ("mid_row", c_int64), ("num_sends", c_int32),
+                ("sends", POINTER(MfHaloSend)), ("num_recv_peers", c_int32),
+                ("recv_peers", POINTER(c_int32))]
+
+
+MF_COMM_HANDLE_BYTES = 64
+
 # name -> (restype, argtypes); every symbol include/matfree_b200.h declares
 _OP = POINTER(MfOperator)
 SIGNATURES = {
@@ -106,6 +119,23 @@ SIGNATURES = {
                                      c_int32, c_double, c_void_p, c_void_p, c_int64, c_void_p]),
     "mf_basis_combine": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64,
                                    c_int64, c_void_p, c_void_p]),
+    "mf_comm_create": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_void_p)]),
+    "mf_comm_handle": (c_int32, [c_void_p, c_void_p]),
+    "mf_comm_connect": (c_int32, [c_void_p, c_void_p]),
+    "mf_comm_heap": (c_void_p, [c_void_p]),
+    "mf_comm_heap_bytes": (c_int64, [c_void_p]),
+    "mf_comm_status": (c_int32, [c_void_p, c_void_p]),
+    "mf_comm_barrier": (c_int32, [c_void_p, c_void_p]),
+    "mf_comm_disconnect": (c_int32, [c_void_p]),
+    "mf_comm_destroy": (c_int32, [c_void_p]),
+    "mf_halo_exchange": (c_int32, [c_void_p, POINTER(MfHaloPlan), c_int64, c_int64, c_int64,
+                                   c_int32, c_int32, c_void_p]),
+    "mf_lanczos_sharded_heap_bytes": (c_int64, [POINTER(MfHaloPlan), c_int64, c_int64, c_int32,
+                                                c_int32, c_int32]),
+    "mf_lanczos_sharded_workspace_bytes": (c_int64, [_OP, c_int64, c_int64, c_int32]),
+    "mf_lanczos_sharded": (c_int32, [c_void_p, _OP, POINTER(MfHaloPlan), c_void_p, c_int64, c_int64,
+                                     c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

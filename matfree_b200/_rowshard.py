@@ -81,11 +81,31 @@ class HaloPlan:
     @property
     def rows_alloc(self):
         """Rows of the extended block as allocated (padding + halo + slab + halo)."""
-        return self.pad + self.n_ext
+        return (self.pad + self.n_ext + 3) // 4 * 4
 
     def row(self, a: int) -> int:
         """Index of global row `a` in the extended block."""
         return self.pad + a - self.c0
+
+
+    def c_struct(self):
+        """`mf_halo_plan_t` of this rank (peer-memory exchange): every send names the row of the
+        RECEIVER's extended block it lands in, which this rank can compute because all slabs and
+        column ranges are known to everybody."""
+        if getattr(self, "_c", None) is None:
+            peers = {}
+            sends = (_lib.MfHaloSend * max(len(self.sends), 1))()
+            for i, (peer, a, b) in enumerate(self.sends):
+                pp = peers.get(peer) or peers.setdefault(peer, HaloPlan(peer, self.ranges, self.needs))
+                sends[i] = _lib.MfHaloSend(peer=peer, src_row=self.row(a), rows=b - a,
+                                           dst_row=pp.row(a), dst_rows_alloc=pp.rows_alloc)
+            srcs = sorted({peer for peer, _, _ in self.recvs})
+            recv = (ctypes.c_int32 * max(len(srcs), 1))(*srcs)
+            plan = _lib.MfHaloPlan(rows_alloc=self.rows_alloc, mid_row=self.row(self.r0),
+                                   num_sends=len(self.sends), sends=sends,
+                                   num_recv_peers=len(srcs), recv_peers=recv)
+            self._c = (plan, sends, recv)  # keep the arrays alive
+        return self._c[0]
 
 
 def make_plan(r0: int, r1: int, cmin: int, cmax_excl: int, group=None) -> HaloPlan:
@@ -138,6 +158,97 @@ def _all_reduce(t, group):
         dist.all_reduce(t, group=group)
 
 
+# ----------------------------------------------------------------------------- peer memory
+
+
+class _DevView:
+    """Raw device memory as a `__cuda_array_interface__` object (for `torch.as_tensor`)."""
+
+    def __init__(self, ptr, nbytes, owner):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+        self._owner = owner
+
+
+class PeerComm:
+    """`mf_comm_t` for the ranks of a process group: one peer-mapped region per rank (CUDA IPC),
+    over which the library's kernels exchange halos and all-reduce their sums (NVLink loads /
+    stores, no NCCL on the per-step path).  torch.distributed only carries the 64-byte handles."""
+
+    def __init__(self, group=None, heap_bytes=0):
+        import torch
+        import torch.distributed as dist
+
+        self.lib = _lib.load()
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.mf_comm_create(self.world, self.rank, int(heap_bytes), ctypes.byref(self._h)))
+        buf = (ctypes.c_ubyte * _lib.MF_COMM_HANDLE_BYTES)()
+        _lib.check(self.lib.mf_comm_handle(self._h, buf))
+        dev = _device.device()
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allh, mine, group=group)
+        raw = bytes(torch.stack(allh).cpu().numpy().tobytes())
+        _lib.check(self.lib.mf_comm_connect(self._h, raw))
+        dist.barrier(group=group)  # every rank has mapped every region before anyone uses it
+        self.heap_bytes = int(self.lib.mf_comm_heap_bytes(self._h))
+        self._heap_ptr = int(self.lib.mf_comm_heap(self._h) or 0)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def heap_view(self, offset, shape, dtype):
+        """Tensor view of the local heap (the memory stays owned by the communicator)."""
+        import torch
+
+        nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        assert offset + nbytes <= self.heap_bytes
+        flat = torch.as_tensor(_DevView(self._heap_ptr + offset, nbytes, self), device=_device.device())
+        return flat.view(dtype).view(*shape)
+
+    def check(self):
+        """Synchronise and raise if an in-kernel wait timed out."""
+        _lib.check(self.lib.mf_comm_status(self._h, _device.stream()))
+
+    def close(self, collective=True):
+        """Unmap the peers' regions, wait until every rank has done so, free the own region.
+        `collective=False` (interpreter shutdown) skips the rendezvous."""
+        if self._h:
+            import torch
+            import torch.distributed as dist
+
+            torch.cuda.synchronize()
+            self.lib.mf_comm_disconnect(self._h)
+            if collective and dist.is_available() and dist.is_initialized():
+                dist.barrier(group=self.group)
+            self.lib.mf_comm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close(collective=False)
+        except Exception:
+            pass
+
+
+def _use_peer_memory(group) -> bool:
+    """Peer-memory drivers need one CUDA process per rank on one node (NCCL group)."""
+    import os
+
+    import torch.distributed as dist
+
+    if os.environ.get("MF_ROWSHARD_NCCL"):
+        return False  # cross-check route: Python step loop + NCCL collectives
+    if not (dist.is_available() and dist.is_initialized()):
+        return True  # single process: native driver without a communicator
+    if dist.get_world_size(group) == 1:
+        return True
+    return dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 8
+
+
 # ----------------------------------------------------------------------------- operator
 
 
@@ -180,6 +291,30 @@ class RowShardedCsr(ops.Operator):
     @property
     def shape(self):
         return (self.n_global, self.n_global)
+
+    def peer_comm(self, need_bytes):
+        """The operator's communicator with a heap of at least `need_bytes` (collective: the
+        heap is (re)allocated when any rank needs more; sizes are cached per call signature)."""
+        import torch
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return None
+        comm = getattr(self, "_comm", None)
+        key = int(need_bytes)
+        agreed = getattr(self, "_comm_sizes", {})
+        if key not in agreed:
+            t = torch.tensor([key], dtype=torch.int64, device=self.data.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            agreed[key] = int(t.item())
+            self._comm_sizes = agreed
+        need = agreed[key]
+        if comm is None or comm.heap_bytes < need:
+            if comm is not None:
+                comm.close()
+            comm = PeerComm(self.group, need)
+            self._comm = comm
+        return comm
 
     def extended(self, ld, dtype=None):
         import torch
@@ -289,12 +424,57 @@ class CudaBackend:
 # ----------------------------------------------------------------------------- drivers
 
 
+def lanczos_sharded_native(op, V0, k, reortho, *, want_Q, want_residual):
+    """`mf_lanczos_sharded`: the whole k-step loop of a row-sharded decomposition in one call --
+    halos pushed into the neighbours' extended blocks and every reduction all-reduced over peer
+    memory inside the reducing kernel (no NCCL, no host work between the kernels)."""
+    import torch
+
+    lib = _lib.load()
+    nloc, ld = V0.shape
+    dt, dev = V0.dtype, V0.device
+    full = reortho == "full"
+    rflag = _lib.MF_REORTHO_FULL if full else _lib.MF_REORTHO_NONE
+    keep_Q = bool(want_Q or full)
+    plan = op.plan.c_struct()
+    st = op._struct()
+    mfdt = _device.mf_dtype(dt)
+    need = lib.mf_lanczos_sharded_heap_bytes(ctypes.byref(plan), ld, k, rflag, int(keep_Q), mfdt)
+    comm = op.peer_comm(need)
+    nblocks = max(k, 1) if keep_Q else 2
+    if comm is None:
+        ext = torch.empty((nblocks, op.plan.rows_alloc, ld), dtype=dt, device=dev)
+    else:
+        ext = comm.heap_view(0, (nblocks, op.plan.rows_alloc, ld), dt)
+    ws_bytes = lib.mf_lanczos_sharded_workspace_bytes(ctypes.byref(st), ld, k, rflag)
+    if ws_bytes < 0:
+        _lib.check(-1)
+    ws = _device.workspace(ws_bytes)
+    alphas = torch.empty((max(k, 1), ld), dtype=dt, device=dev)
+    betas = torch.empty((max(k, 1), ld), dtype=dt, device=dev)
+    init_len = torch.empty((ld,), dtype=dt, device=dev)
+    residual = torch.empty((nloc, ld), dtype=dt, device=dev) if want_residual else None
+    _lib.check(lib.mf_lanczos_sharded(None if comm is None else comm.handle, ctypes.byref(st),
+                                      ctypes.byref(plan), V0.data_ptr(), ld, k, rflag, int(keep_Q), 0,
+                                      ext.data_ptr(), alphas.data_ptr(), betas.data_ptr(),
+                                      init_len.data_ptr(),
+                                      None if residual is None else residual.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), _device.stream()))
+    Q = None
+    if keep_Q and k > 0:
+        m0 = op.plan.row(op.r0)
+        Q = ext[:k, m0:m0 + nloc].contiguous()  # the heap is reused by the next call
+    return alphas[:k], betas[:k], init_len, Q, residual
+
+
 def lanczos_full_sharded(op, V0, k, *, backend=None, want_residual=True):
     """Arnoldi with CGS twice and ``T = (H + H^T)/2`` on a row-sharded operator
     (`matfree/decomp.py:426-477,130-143`), for a block of `ld` start vectors `V0[n_loc][ld]`.
 
     Returns ``(alphas [k][ld], betas [k][ld], init_len [ld], Q [k][n_loc][ld], residual)`` with the
     same meaning as `mf_lanczos` (betas row k-1 = norm of the last residual)."""
+    if backend is None and _use_peer_memory(op.group):
+        return lanczos_sharded_native(op, V0, k, "full", want_Q=True, want_residual=want_residual)
     be = backend or CudaBackend(V0.shape[1], max_nq=k)
     group = op.group
     nloc, ld = V0.shape
@@ -340,6 +520,8 @@ def lanczos_full_sharded(op, V0, k, *, backend=None, want_residual=True):
 def lanczos_none_sharded(op, V0, k, *, backend=None, want_Q=False, want_residual=True):
     """Three-term Lanczos on a row-sharded operator (`matfree/decomp.py:220-292`, the operation
     order of the reference: normalise, matvec, alpha, update, beta)."""
+    if backend is None and _use_peer_memory(op.group):
+        return lanczos_sharded_native(op, V0, k, "none", want_Q=want_Q, want_residual=want_residual)
     be = backend or CudaBackend(V0.shape[1])
     group = op.group
     nloc, ld = V0.shape

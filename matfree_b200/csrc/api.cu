@@ -407,6 +407,123 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
   return MF_OK;
 }
 
+// ---------------------------------------------------------------- row-sharded drivers
+// The same two recurrences on ONE RANK's rows of a row-sharded CSR operator.  Differences to
+// the single-GPU drivers above: (1) the vector the operator is applied to lives in an
+// "extended block" (padding | lower halo | owned rows | upper halo) in the communicator's
+// peer-mapped heap, and its halo rows are filled by the neighbours' stores before every product
+// (launch_halo_exchange); (2) every reduction carries the communicator's descriptor, so its last
+// CTA all-reduces the fp64 sums over peer memory before writing the scalars (common.cuh) --
+// all ranks hold bit-identical alphas / betas / CGS coefficients; (3) vectors are normalised by
+// a true division as in the reference (decomp.py:227,291,456-457): v_j must exist in memory
+// anyway because the neighbours read its boundary rows.
+struct Shard {
+  const mf_comm* comm;
+  const PeerCtx* peer;
+  const mf_halo_plan_t* plan;
+  int64_t heap_offset;
+  unsigned char* ext;  // local address of the extended blocks
+};
+
+int32_t lanczos_full_sharded(const Shard& sh, const mf_operator_t* op, const void* V0, int64_t ld,
+                             int64_t k, void* alphas, void* betas, void* init_len, void* residual,
+                             const LanczosBufs& b, cudaStream_t st) {
+  const int32_t dt = op->dtype;
+  const int64_t n = op->n;  // local rows
+  const int64_t es = (int64_t)dtype_size(dt);
+  const int64_t blk = n * ld * es;
+  const int64_t ext_blk = sh.plan->rows_alloc * ld * es;
+  const int64_t q_stride = sh.plan->rows_alloc * ld;
+  unsigned char* Qmid = sh.ext + sh.plan->mid_row * ld * es;  // basis vector 0, owned rows
+  {
+    const Reduce red{b.partial, Finalize{b.counter, 1, init_len, nullptr, nullptr, sh.peer}};
+    MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, red, st));
+  }
+  const void* length = init_len;
+  for (int64_t i = 0; i < k; ++i) {
+    void* Qi = Qmid + i * ext_blk;
+    MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
+    MF_TRY(launch_halo_exchange(sh.comm, sh.plan, sh.heap_offset, i, ld, dt, st));
+    bool fused = false;
+    MF_TRY(apply_op(op, sh.ext + i * ext_blk, nullptr, b.V, ld, b.scr, nullptr, b.counter + 8,
+                    &fused, st));  // :460
+    MF_TRY(launch_reorth_dots(Qmid, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st, nullptr,
+                              b.partial_rows, q_stride, sh.peer));  // :463
+    if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("alpha copy failed");
+      return MF_ERR_CUDA;
+    }
+    if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
+    MF_TRY(launch_reorth_update(Qmid, i + 1, b.h, b.V, dt, n, ld, nullptr, st, q_stride));  // :464
+    MF_TRY(launch_reorth_dots(Qmid, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st, nullptr,
+                              b.partial_rows, q_stride, sh.peer));  // :468
+    const Reduce red_n{b.partial,
+                       Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr, sh.peer}};
+    MF_TRY(launch_reorth_update(Qmid, i + 1, b.h2, b.V, dt, n, ld, &red_n, st, q_stride));  // :468,471
+    length = row(betas, i, ld, dt);
+  }
+  if (residual != nullptr) {
+    const void* src = k > 0 ? b.V : V0;
+    if (cudaMemcpyAsync(residual, src, blk, cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("residual copy failed");
+      return MF_ERR_CUDA;
+    }
+  }
+  return MF_OK;
+}
+
+int32_t lanczos_none_sharded(const Shard& sh, const mf_operator_t* op, const void* V0, int64_t ld,
+                             int64_t k, bool want_Q, void* alphas, void* betas, void* init_len,
+                             void* residual, const LanczosBufs& b, cudaStream_t st) {
+  const int32_t dt = op->dtype;
+  const int64_t n = op->n;
+  const int64_t es = (int64_t)dtype_size(dt);
+  const int64_t blk = n * ld * es;
+  const int64_t ext_blk = sh.plan->rows_alloc * ld * es;
+  const int64_t mid_off = sh.plan->mid_row * ld * es;
+  {
+    const Reduce red{b.partial, Finalize{b.counter, 1, init_len, nullptr, nullptr, sh.peer}};
+    MF_TRY(launch_dot(V0, nullptr, V0, dt, n, ld, red, st));
+  }
+  const void* cur = V0;
+  const void* length = init_len;
+  const void* prev_mid = nullptr;
+  for (int64_t j = 0; j < k; ++j) {
+    const int64_t blkno = want_Q ? j : (j & 1);  // ping-pong unless the basis is kept
+    unsigned char* xe = sh.ext + blkno * ext_blk;
+    void* mid = xe + mid_off;
+    MF_TRY(launch_scale(cur, length, mid, 1, dt, n, ld, st));  // v_j = r / b (decomp.py:227,291)
+    MF_TRY(launch_halo_exchange(sh.comm, sh.plan, sh.heap_offset, blkno, ld, dt, st));
+    bool fused = false;
+    MF_TRY(apply_op(op, xe, nullptr, b.W, ld, b.scr, nullptr, b.counter + 8, &fused, st));  // :287
+    void* aj = row(alphas, j, ld, dt);
+    const Reduce red_a{b.partial, Finalize{b.counter, 0, aj, nullptr, nullptr, sh.peer}};
+    MF_TRY(launch_dot(mid, nullptr, b.W, dt, n, ld, red_a, st));  // :288
+    const Reduce red_b{b.partial,
+                       Finalize{b.counter, 1, row(betas, j, ld, dt), nullptr, nullptr, sh.peer}};
+    MF_TRY(launch_lanczos_update(b.W, mid, nullptr, aj, prev_mid, nullptr,
+                                 j > 0 ? row(betas, j - 1, ld, dt) : nullptr, b.R0, dt, n, ld,
+                                 red_b, st));  // :289-290
+    cur = b.R0;
+    length = row(betas, j, ld, dt);
+    prev_mid = mid;
+  }
+  if (residual != nullptr) {
+    if (cudaMemcpyAsync(residual, k > 0 ? b.R0 : V0, blk, cudaMemcpyDeviceToDevice, st) !=
+        cudaSuccess) {
+      set_error("residual copy failed");
+      return MF_ERR_CUDA;
+    }
+  }
+  return MF_OK;
+}
+
+int64_t sharded_blocks(int64_t k, int32_t reortho, bool want_Q) {
+  if (reortho == MF_REORTHO_FULL || want_Q) return k > 0 ? k : 1;
+  return 2;
+}
+
 }  // namespace
 }  // namespace mf
 
@@ -620,6 +737,88 @@ int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t 
     return lanczos_none(op, (void*)V0, false, false, ld, k, alphas, betas, init_len, Q, residual,
                         b, st);
   return lanczos_full(op, V0, false, ld, k, alphas, betas, init_len, Q, residual, b, st);
+}
+
+static int32_t check_sharded_args(const mf_operator_t* op, const mf_halo_plan_t* plan, int64_t ld,
+                                  int64_t k, int32_t reortho) {
+  MF_TRY(validate_op(op));
+  if (op->kind != MF_OP_CSR) {
+    set_error("lanczos_sharded: only CSR operators are row-sharded");
+    return MF_ERR_UNSUPPORTED;
+  }
+  if (!valid_ld(ld) || k < 0 ||
+      (reortho != MF_REORTHO_NONE && reortho != MF_REORTHO_FULL)) {
+    set_error("lanczos_sharded: bad ld / k / reortho");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (plan != nullptr && (plan->mid_row < 0 || plan->mid_row + op->n > plan->rows_alloc)) {
+    set_error("lanczos_sharded: the halo plan does not cover the %lld local rows",
+              (long long)op->n);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return MF_OK;
+}
+
+int64_t mf_lanczos_sharded_heap_bytes(const mf_halo_plan_t* plan, int64_t ld, int64_t k,
+                                      int32_t reortho, int32_t want_Q, int32_t dtype) {
+  if (plan == nullptr || !valid_ld(ld) || k < 0) return -1;
+  return sharded_blocks(k, reortho, want_Q != 0) * plan->rows_alloc * ld *
+         (int64_t)dtype_size(dtype);
+}
+
+int64_t mf_lanczos_sharded_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k,
+                                           int32_t reortho) {
+  if (check_sharded_args(op, nullptr, ld, k, reortho) != MF_OK) return -1;
+  Arena a(nullptr, 0, true);
+  LanczosBufs b;
+  carve_lanczos(a, op, ld, k, reortho, &b);
+  return a.used + 256;
+}
+
+int32_t mf_lanczos_sharded(const mf_comm_t* comm, const mf_operator_t* op,
+                           const mf_halo_plan_t* plan, const void* V0, int64_t ld, int64_t k,
+                           int32_t reortho, int32_t want_Q, int64_t heap_offset, void* ext,
+                           void* alphas, void* betas, void* init_len, void* residual,
+                           void* workspace, int64_t workspace_bytes, void* stream) {
+  if (plan == nullptr) {
+    set_error("lanczos_sharded: the halo plan is missing");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  MF_TRY(check_sharded_args(op, plan, ld, k, reortho));
+  if (V0 == nullptr || init_len == nullptr || (k > 0 && (alphas == nullptr || betas == nullptr))) {
+    set_error("lanczos_sharded: V0, init_len, alphas, betas must be non-null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  const int64_t need = mf_lanczos_sharded_heap_bytes(plan, ld, k, reortho, want_Q, op->dtype);
+  Shard sh{comm, comm_ctx(comm), plan, heap_offset, nullptr};
+  if (sh.peer != nullptr) {
+    if (heap_offset < 0 || heap_offset % 16 != 0 ||
+        heap_offset + need > mf_comm_heap_bytes(comm)) {
+      set_error("lanczos_sharded: the communicator heap holds %lld bytes, the extended blocks "
+                "need %lld at offset %lld", (long long)mf_comm_heap_bytes(comm), (long long)need,
+                (long long)heap_offset);
+      return MF_ERR_WORKSPACE;
+    }
+    sh.ext = (unsigned char*)comm_heap(comm) + heap_offset;
+  } else {
+    // one rank: no exchange; the blocks may live anywhere
+    sh.ext = ext != nullptr ? (unsigned char*)ext
+                            : (comm != nullptr ? (unsigned char*)comm_heap(comm) + heap_offset
+                                               : nullptr);
+    if (sh.ext == nullptr) {
+      set_error("lanczos_sharded: without a communicator `ext` must point at the extended blocks");
+      return MF_ERR_INVALID_ARGUMENT;
+    }
+  }
+  Arena a(workspace, workspace_bytes, false);
+  LanczosBufs b;
+  MF_TRY(carve_lanczos(a, op, ld, k, reortho, &b));
+  cudaStream_t st = (cudaStream_t)stream;
+  MF_TRY(zero_counter(b, st));
+  if (reortho == MF_REORTHO_NONE)
+    return lanczos_none_sharded(sh, op, V0, ld, k, want_Q != 0, alphas, betas, init_len, residual,
+                                b, st);
+  return lanczos_full_sharded(sh, op, V0, ld, k, alphas, betas, init_len, residual, b, st);
 }
 
 int64_t mf_tridiag_quad_workspace_bytes(int64_t ld, int64_t k) {

@@ -483,19 +483,21 @@ int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const 
 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
-                           cudaStream_t st, double* dbl_out, int64_t partial_rows) {
+                           cudaStream_t st, double* dbl_out, int64_t partial_rows,
+                           int64_t q_stride, const PeerCtx* peer) {
   MF_KSCOPE(MF_KC_REORTH_DOTS, st);
   const int64_t total = n * ld;
-  const bool mf_wide = wide_ok(dtype, total, Q, V);
+  if (q_stride <= 0) q_stride = total;
+  const bool mf_wide = wide_ok(dtype, total, Q, V) && q_stride % (dtype == MF_F64 ? 2 : 4) == 0;
   const int64_t pstride = (int64_t)kMaxPartialCtas * ld;
   constexpr int JB = 4;
   if (nq > JB && partial_rows >= (nq + JB - 1) / JB * JB) {
     // one launch for all nq sums
-    Finalize fin{counter, 0, h_out, nullptr, dbl_out};
+    Finalize fin{counter, 0, h_out, nullptr, dbl_out, peer};
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_all_kernel<T, VEC, JB>;
       const int grid = MF_STREAM_GRID(kern, total, VEC);
-      kern<<<grid, kBlock, 0, st>>>((const T*)Q, total, (int)nq, (const T*)V, total, (int)ld,
+      kern<<<grid, kBlock, 0, st>>>((const T*)Q, q_stride, (int)nq, (const T*)V, total, (int)ld,
                                     partial, pstride, fin);
     });
     return check_launch("reorth_dots_all");
@@ -504,11 +506,11 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
     const int nj = (int)((nq - j0) < JB ? (nq - j0) : JB);
     Finalize fin{counter, 0,
                  h_out ? (void*)((char*)h_out + j0 * ld * (int64_t)dtype_size(dtype)) : nullptr,
-                 nullptr, dbl_out ? dbl_out + j0 * ld : nullptr};
+                 nullptr, dbl_out ? dbl_out + j0 * ld : nullptr, peer};
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_kernel<T, VEC, JB>;
       const int grid = MF_STREAM_GRID(kern, total, VEC);
-      kern<<<grid, kBlock, 0, st>>>((const T*)Q, total, (int)j0, nj, (const T*)V, total, (int)ld,
+      kern<<<grid, kBlock, 0, st>>>((const T*)Q, q_stride, (int)j0, nj, (const T*)V, total, (int)ld,
                                     partial, pstride, fin);
     });
     MF_TRY(check_launch("reorth_dots"));
@@ -517,10 +519,12 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
 }
 
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
-                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st) {
+                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st,
+                             int64_t q_stride) {
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
-  const bool mf_wide = wide_ok(dtype, total, Q, V);
+  if (q_stride <= 0) q_stride = total;
+  const bool mf_wide = wide_ok(dtype, total, Q, V) && q_stride % (dtype == MF_F64 ? 2 : 4) == 0;
   const size_t smem = (size_t)nq * ld * dtype_size(dtype);
   if (smem > 160 * 1024) {
     set_error("reorth_update: %lld basis vectors x %lld probes exceed the shared-memory budget; "
@@ -540,7 +544,7 @@ int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, 
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
     const int grid = resident_grid((const void*)kern, kBlock, smem,                       \
                                    (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC)); \
-    kern<<<grid, kBlock, smem, st>>>((const T*)Q, total, (int)nq, (const T*)h, (T*)V, total,  \
+    kern<<<grid, kBlock, smem, st>>>((const T*)Q, q_stride, (int)nq, (const T*)h, (T*)V, total, \
                                      (int)ld, partial, fin);                                  \
   })
   if (red != nullptr) {

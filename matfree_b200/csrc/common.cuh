@@ -158,6 +158,60 @@ __device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int
   __syncthreads();
 }
 
+// ---------------------------------------------------------------- peer memory (multi-GPU)
+// One process per GPU; every rank allocates one region [control | heap] with cudaMalloc, exports
+// it with cudaIpcGetMemHandle and maps the regions of all peers (peer.cu, mf_comm_*).  Kernels of
+// this library then talk to the other GPUs with plain loads / stores over NVLink:
+//   * all-reduce fused into the reducing kernels: the last CTA of a reduction pushes its fp64
+//     sums into a slot of every peer, signals, waits for the peers' signals and adds the slots in
+//     rank order (one-shot, deterministic, identical bits on every rank) -- no NCCL launch,
+//     no host round trip between the dot product and its consumers;
+//   * halo exchange: boundary rows are stored straight into the neighbours' extended blocks.
+constexpr int kMaxPeers = 8;
+constexpr int kPeerSlotDoubles = 32768;  // capacity of one exchange (accumulators x probes)
+struct PeerControl {                      // at offset 0 of every rank's region
+  unsigned int red_flag[kMaxPeers];       // [src rank] = sequence number of its last pushed reduction
+  unsigned int halo_flag[kMaxPeers];      // [src rank] = sequence number of its last pushed halo
+  unsigned int bar_flag[kMaxPeers];       // [src rank] = sequence number of its last barrier arrival
+  unsigned int red_seq, halo_seq, bar_seq;  // local: exchanges completed so far
+  unsigned int error;                     // local: 1 after a wait timed out (mf_comm_status)
+  unsigned int halo_ticket;               // local: CTA ticket of the halo kernel
+  unsigned int pad[3];
+  double slots[2][kMaxPeers][kPeerSlotDoubles];  // [seq & 1][src rank][pair]
+};
+struct PeerCtx {  // device-resident descriptor (one per communicator)
+  int world, rank;
+  PeerControl* ctl[kMaxPeers];  // ctl[p]: rank p's control block, mapped into this process
+  unsigned char* heap[kMaxPeers];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t));
+  return t;
+}
+// spin until *flag has reached `seq` (wrap-safe); gives up after 20 s and raises the error flag
+// so that a missing peer turns into an error code instead of a hung GPU
+__device__ __forceinline__ void wait_flag(const unsigned int* flag, unsigned int seq,
+                                          unsigned int* error) {
+  const unsigned long long t0 = global_ns();
+  while ((int)(ld_acquire_sys(flag) - seq) < 0) {
+    if (global_ns() - t0 > 20000000000ull) {
+      *error = 1u;
+      break;
+    }
+    __nanosleep(64);
+  }
+}
+
 // What the LAST CTA of a reducing kernel does with the column sums ("fused
 // finalize"): every CTA writes its partial row, takes a ticket on `counter`, and
 // the CTA that draws the last ticket adds the partial rows in the fixed order
@@ -170,7 +224,21 @@ struct Finalize {
   void* value;            // T[nacc][ld] (row a at value + a*ld), may be null
   void* inv;              // T[ld], mode 1 only, may be null
   double* dbl;            // optional double[nacc][ld]: the fp64 sums
+  const PeerCtx* peer;    // optional: the sums are all-reduced over the communicator's ranks
+                          // (peer memory, in this kernel) before value / inv / dbl are written
 };
+
+template <typename T>
+__device__ __forceinline__ void finalize_write(const Finalize& fin, int64_t i, double s) {
+  if (fin.dbl) fin.dbl[i] = s;
+  if (fin.mode == 0) {
+    if (fin.value) reinterpret_cast<T*>(fin.value)[i] = (T)s;
+  } else {
+    const T v = (T)sqrt(s);
+    if (fin.value) reinterpret_cast<T*>(fin.value)[i] = v;
+    if (fin.inv) reinterpret_cast<T*>(fin.inv)[i] = T(1) / v;
+  }
+}
 
 // Second half of a reducing kernel: take a ticket; the CTA drawing the last one adds the
 // partial rows of all CTAs (fixed order) for `nacc_live` accumulators and writes the results.
@@ -194,6 +262,17 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
   const int L = lanes_per_pair(npairs);
   const int lane = threadIdx.x & (L - 1);
   const int groups = kBlock / L;
+  // multi-GPU: the local sums go to slot [seq & 1][my rank] of every rank instead
+  const PeerCtx* pc = fin.peer;
+  const bool xch = pc != nullptr && pc->world > 1;
+  int world = 1, rank = 0, buf = 0;
+  unsigned int seq = 0;
+  if (xch) {
+    world = pc->world;
+    rank = pc->rank;
+    seq = *(volatile unsigned int*)&pc->ctl[rank]->red_seq + 1u;
+    buf = (int)(seq & 1u);
+  }
   for (int base = 0; base < npairs; base += groups) {
     const int idx = base + threadIdx.x / L;
     const bool live = idx < npairs;
@@ -204,14 +283,28 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
       for (int b = lane; b < grid; b += L) s += __ldcg(p + (int64_t)b * ld);
     s = group_sum(s, L);
     if (!live || lane != 0) continue;
-    if (fin.dbl) fin.dbl[(int64_t)a * ld + c] = s;
-    if (fin.mode == 0) {
-      if (fin.value) reinterpret_cast<T*>(fin.value)[(int64_t)a * ld + c] = (T)s;
+    if (xch) {
+      for (int q = 0; q < world; ++q) pc->ctl[q]->slots[buf][rank][idx] = s;  // NVLink stores
     } else {
-      const T v = (T)sqrt(s);
-      if (fin.value) reinterpret_cast<T*>(fin.value)[(int64_t)a * ld + c] = v;
-      if (fin.inv) reinterpret_cast<T*>(fin.inv)[(int64_t)a * ld + c] = T(1) / v;
+      finalize_write<T>(fin, (int64_t)a * ld + c, s);
     }
+  }
+  if (xch) {
+    PeerControl* mine = pc->ctl[rank];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < world) {
+      st_release_sys(&pc->ctl[threadIdx.x]->red_flag[rank], seq);
+      wait_flag(&mine->red_flag[threadIdx.x], seq, &mine->error);
+    }
+    __syncthreads();
+    // every rank adds the same numbers in the same (rank) order: identical bits everywhere
+    for (int idx = threadIdx.x; idx < npairs; idx += kBlock) {
+      double s = 0.0;
+      for (int q = 0; q < world; ++q) s += __ldcv(&mine->slots[buf][q][idx]);
+      finalize_write<T>(fin, idx, s);
+    }
+    if (threadIdx.x == 0) mine->red_seq = seq;
   }
   if (threadIdx.x == 0) *fin.counter = 0u;
 }

@@ -48,9 +48,12 @@ int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const 
 // CGS pass, dots: h[j][c] = sum_r Q[j][r][c] * V[r][c], j = 0..nq-1
 // (matfree/decomp.py:463,468).  partial: double[4][kMaxPartialCtas*ld]
 // dbl_out (optional): the fp64 sums [nq][ld] (row-sharded drivers all-reduce these)
+// q_stride: elements between consecutive basis vectors (0: n*ld; larger when the basis lives in
+// extended blocks with halo rows); peer: all-reduce the sums over peer memory inside the kernel
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
-                           cudaStream_t st, double* dbl_out = nullptr, int64_t partial_rows = 4);
+                           cudaStream_t st, double* dbl_out = nullptr, int64_t partial_rows = 4,
+                           int64_t q_stride = 0, const PeerCtx* peer = nullptr);
 // Accumulator rows the partial buffer of the CGS dots gets: all k sums in one launch when
 // that costs at most 8 MB (narrow tiles), otherwise 4 (groups of four basis vectors per launch).
 inline int64_t reorth_partial_rows(int64_t ld, int64_t k) {
@@ -64,7 +67,8 @@ int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* 
 // CGS pass, update: V <- V - sum_j Q[j] * h[j]  (decomp.py:464,468); optional
 // column sums of the new V^2 -> red->fin (norm fused).
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
-                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st);
+                             int64_t n, int64_t ld, const Reduce* red, cudaStream_t st,
+                             int64_t q_stride = 0);
 // out[r][c] = scale[c] * sum_j Q[j][r][c] * coeff[j][c]
 int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scale,
                              int32_t dtype, int64_t n, int64_t ld, int64_t k, void* out,
@@ -121,6 +125,14 @@ int32_t launch_split_tf32(const void* src, void* planes, int64_t count, cudaStre
 int32_t launch_gemm_tcgen05(const void* Aplanes, int64_t lda, bool trans, int64_t M, int64_t K,
                             const void* Bplanes, int64_t nbatch, const void* colscale, void* C,
                             void* Csplit, int64_t ld, int variant, cudaStream_t st);
+
+// ---- peer.cu : peer-memory communicator (mf_comm_*), halo push, barrier
+constexpr int kMaxHaloSends = 16;
+const PeerCtx* comm_ctx(const mf_comm* c);  // device descriptor, null for 1 rank / no comm
+void* comm_heap(const mf_comm* c);
+int32_t launch_halo_exchange(const mf_comm* c, const mf_halo_plan_t* plan, int64_t heap_offset,
+                             int64_t block_index, int64_t ld, int32_t dtype, cudaStream_t st);
+int32_t launch_peer_barrier(const mf_comm* c, cudaStream_t st);
 
 // ---- tridiag_quad.cu
 int32_t launch_tridiag_quad(const void* alphas, const void* betas, const void* init_len,

@@ -102,6 +102,31 @@ for reortho in ("full", "none"):
 # sharded matvec == slab of the full matvec, bit for bit (same kernel, same row order)
 w1 = op(v)[r0:r1]; w2 = sop(v[r0:r1])
 assert torch.equal(w1, w2)
+# the peer-memory drivers (mf_lanczos_sharded: halo pushed by stores over NVLink, all-reduce fused
+# into the reducing kernels) against the NCCL route (Python step loop), on a block of 8 vectors
+assert _rowshard._use_peer_memory(None)
+V = torch.as_tensor(oprng.normal(oprng.prng_key(9), (n, 8), np.float32)).to(dev)
+Vloc = V[r0:r1].contiguous()
+for reortho in ("full", "none"):
+    a1, b1, l1, Q1, res1 = m.decomp.lanczos_blocked(op, V, k, reortho, want_Q=True, want_residual=True)
+    a2, b2, l2, Q2, res2 = m.decomp.lanczos_blocked(sop, Vloc, k, reortho, want_Q=True, want_residual=True)
+    sop._comm.check()   # no in-kernel wait timed out
+    os.environ["MF_ROWSHARD_NCCL"] = "1"
+    a3, b3, l3, Q3, res3 = m.decomp.lanczos_blocked(sop, Vloc, k, reortho, want_Q=True, want_residual=True)
+    del os.environ["MF_ROWSHARD_NCCL"]
+    for x2, x1, x3 in ((a2, a1, a3), (b2, b1, b3), (l2, l1, l3)):
+        assert np.allclose(x2.cpu(), x1.cpu(), rtol=2e-5, atol=2e-5), reortho
+        assert np.allclose(x2.cpu(), x3.cpu(), rtol=2e-5, atol=2e-5), reortho
+    assert np.allclose(Q2.cpu(), Q1[:, r0:r1].cpu(), atol=2e-4), reortho
+    assert np.allclose(res2.cpu(), res1[r0:r1].cpu(), atol=2e-3), reortho
+    # the fused all-reduce adds the ranks' sums in rank order on every rank: identical bits
+    mine = torch.cat([a2.flatten(), b2.flatten(), l2.flatten()])
+    allv = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    assert all(torch.equal(t, allv[0]) for t in allv), reortho
+    # and is reproducible run to run
+    a4, b4, l4, _, _ = m.decomp.lanczos_blocked(sop, Vloc, k, reortho, want_Q=False, want_residual=False)
+    assert torch.equal(a4, a2) and torch.equal(b4, b2), reortho
 dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
