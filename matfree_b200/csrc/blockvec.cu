@@ -177,57 +177,109 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
 // All nq basis vectors in ONE launch (narrow tiles: the per-CTA partial rows of all nq sums fit
 // the workspace).  Groups of JB vectors are accumulated in registers; V is re-read per group but
 // stays L2-resident because the basis -- read exactly once -- is loaded with evict-first hints.
+// The (group, chunk) iteration space is walked as ONE software-pipelined stream per warp: the
+// loads of the next chunk -- also across a group boundary -- are in flight while the current
+// one is consumed, and a finished group is folded with warp shuffles into a per-warp
+// shared-memory row, so there is no CTA-wide barrier (and no pipeline drain) between groups.
+// Requires ld < 32 * VEC (narrow tiles) and nq4 * ld * 8 warps doubles of dynamic shared memory.
 template <typename T, int VEC, int JB>
-__global__ void __launch_bounds__(kBlock, 3)
+__global__ void __launch_bounds__(kBlock, 2)
 reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ V,
                        int64_t total, int ld, double* __restrict__ partial, int64_t partial_stride,
                        Finalize fin) {
-  for (int j0 = 0; j0 < nq; j0 += JB) {
-    const int nj = (nq - j0) < JB ? (nq - j0) : JB;
+  extern __shared__ double wsum[];  // [nq][kBlock / 32][ld]
+  constexpr int NW = kBlock / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
+  const int64_t f0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC;
+  // warp-uniform trip count (lane 0 owns the smallest offset): every lane takes part in the
+  // shuffles, lanes past the end contribute zeros
+  const int64_t fw = ((int64_t)blockIdx.x * kBlock + warp * 32) * VEC;
+  const int iters = fw < total ? (int)((total - fw + stride - 1) / stride) : 0;
+  const int ngroups = (nq + JB - 1) / JB;
+
+  T v[VEC], q[JB][VEC];
+  auto issue = [&](int g, int it, T (&vv)[VEC], T (&qq)[JB][VEC]) {
+    const int64_t f = f0 + (int64_t)it * stride;
+    const int j0 = g * JB;
+    if (f < total) {
+      load_chunk<T, VEC>(V, f, vv);
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j0 + j < nq) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, f, qq[j]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) vv[i] = T(0);
+    }
+  };
+  if (iters > 0) issue(0, 0, v, q);
+  for (int g = 0; g < ngroups && iters > 0; ++g) {
+    const int j0 = g * JB;
     double acc[JB][VEC];
 #pragma unroll
     for (int j = 0; j < JB; ++j)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
-    // software-pipelined: the loads of the next chunk are issued before the current one is
-    // consumed (two chunks of V + JB basis vectors in flight per thread)
-    const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
-    int64_t f = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC;
-    T v[VEC], q[JB][VEC];
-    if (f < total) {
-      load_chunk<T, VEC>(V, f, v);
-#pragma unroll
-      for (int j = 0; j < JB; ++j)
-        if (j < nj) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, f, q[j]);
-    }
-    while (f < total) {
-      const int64_t fn = f + stride;
+    for (int it = 0; it < iters; ++it) {
       T vn[VEC], qn[JB][VEC];
-      if (fn < total) {
-        load_chunk<T, VEC>(V, fn, vn);
-#pragma unroll
-        for (int j = 0; j < JB; ++j)
-          if (j < nj) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, fn, qn[j]);
-      }
+      const bool last_it = it + 1 == iters;
+      const bool more = !last_it || g + 1 < ngroups;
+      if (more) issue(last_it ? g + 1 : g, last_it ? 0 : it + 1, vn, qn);
+      const bool live = f0 + (int64_t)it * stride < total;
 #pragma unroll
       for (int j = 0; j < JB; ++j)
-        if (j < nj) {
+        if (live && j0 + j < nq) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[j][i] * (double)v[i];
         }
-      if (fn < total) {
+      if (more) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) v[i] = vn[i];
 #pragma unroll
         for (int j = 0; j < JB; ++j)
-          if (j < nj) {
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) q[j][i] = qn[j][i];
-          }
+          for (int i = 0; i < VEC; ++i) q[j][i] = qn[j][i];
       }
-      f = fn;
     }
-    cta_reduce_columns<VEC, JB>(acc, ld, partial + (int64_t)j0 * partial_stride, partial_stride);
+    // fold the group: lanes whose chunks cover the same columns are ld / VEC lanes apart
+    // (all lanes when ld <= VEC); fixed xor tree => deterministic
+    const int lanes_per_row = ld >= VEC ? ld / VEC : 1;
+#pragma unroll
+    for (int j = 0; j < JB; ++j) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        double s = acc[j][i];
+        for (int off = 16; off >= lanes_per_row; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        acc[j][i] = s;
+      }
+      if constexpr (VEC == 4) {  // the elements of a chunk wrap around ld < VEC columns
+        if (ld == 1) acc[j][0] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+        if (ld == 2) {
+          acc[j][0] += acc[j][2];
+          acc[j][1] += acc[j][3];
+        }
+      } else if constexpr (VEC == 2) {
+        if (ld == 1) acc[j][0] += acc[j][1];
+      }
+      if (j0 + j < nq && lane < lanes_per_row) {
+        double* dst = wsum + ((int64_t)(j0 + j) * NW + warp) * ld;
+        const int c0 = (threadIdx.x * VEC) & (ld - 1);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i)
+          if (i < ld) dst[(c0 + i) & (ld - 1)] = acc[j][i];
+      }
+    }
+  }
+  __syncthreads();
+  // per-CTA partial row: the warps' sums in warp order
+  for (int idx = threadIdx.x; idx < nq * ld; idx += kBlock) {
+    const int a = idx / ld, c = idx - a * ld;
+    double s = 0.0;
+    for (int w = 0; w < NW; ++w) {  // warps past the end of the block never wrote their row
+      const int64_t fww = ((int64_t)blockIdx.x * kBlock + w * 32) * VEC;
+      if (fww < total) s += wsum[((int64_t)a * NW + w) * ld + c];
+    }
+    partial[(int64_t)a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
   }
   finalize_if_last<T>(ld, partial, partial_stride, nq, fin);
 }
@@ -496,9 +548,11 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
     Finalize fin{counter, 0, h_out, nullptr, dbl_out, peer};
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_all_kernel<T, VEC, JB>;
-      const int grid = MF_STREAM_GRID(kern, total, VEC);
-      kern<<<grid, kBlock, 0, st>>>((const T*)Q, q_stride, (int)nq, (const T*)V, total, (int)ld,
-                                    partial, pstride, fin);
+      const size_t smem = (size_t)nq * (kBlock / 32) * ld * sizeof(double);
+      const int grid = resident_grid((const void*)kern, kBlock, smem,
+                                     (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC));
+      kern<<<grid, kBlock, smem, st>>>((const T*)Q, q_stride, (int)nq, (const T*)V, total, (int)ld,
+                                       partial, pstride, fin);
     });
     return check_launch("reorth_dots_all");
   }

@@ -85,6 +85,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     Q, (diag, off), res, c = out
+    route = "peer memory (mf_lanczos_sharded: halo stores + all-reduce fused into the reducing kernels)" \
+        if _rowshard._use_peer_memory(None) else "NCCL (Python step loop: send/recv halo, all-reduce per reduction)"
+    if getattr(op, "_comm", None) is not None:
+        op._comm.check()  # raises if an in-kernel wait timed out
     if rank == 0:
         peaks = {}
         try:
@@ -108,7 +112,7 @@ def main():
         line = {
             "workload": f"C4: tridiag_sym(reortho=full), depth {k}, 3-D 7-pt Laplacian {g}^3 (n={n}) + 1.0*I, fp32, "
                         f"row-sharded x{world} (slabs of {nloc // plane} planes, halo {op.plan.halo_rows} rows)",
-            "n_gpus": world, "ms_per_decomposition": ms, "steps": a.steps, "warmup": a.warmup,
+            "n_gpus": world, "route": route, "ms_per_decomposition": ms, "steps": a.steps, "warmup": a.warmup,
             "algorithmic_bytes_per_gpu": alg, "achieved_gbs_per_gpu": alg / (ms * 1e-3) / 1e9,
             "hbm_peak_gbs": hbm, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / hbm,
             "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6650 GB/s",
