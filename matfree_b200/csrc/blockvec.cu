@@ -177,13 +177,13 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
 // All nq basis vectors in ONE launch (narrow tiles: the per-CTA partial rows of all nq sums fit
 // the workspace).  Groups of JB vectors are accumulated in registers; V is re-read per group but
 // stays L2-resident because the basis -- read exactly once -- is loaded with evict-first hints.
-// The (group, chunk) iteration space is walked as ONE software-pipelined stream per warp: the
-// loads of the next chunk -- also across a group boundary -- are in flight while the current
-// one is consumed, and a finished group is folded with warp shuffles into a per-warp
-// shared-memory row, so there is no CTA-wide barrier (and no pipeline drain) between groups.
+// A finished group is folded with warp shuffles into a per-warp shared-memory row, so there is
+// no CTA-wide barrier between groups: the 32 warps of an SM (4 CTAs) drift apart and cover
+// each other's group boundaries; 80 bytes of loads in flight per thread x 1024 threads per SM is
+// what the HBM latency needs (ncu: the register-double-buffered 2-CTA variant stalled at 48 %).
 // Requires ld < 32 * VEC (narrow tiles) and nq4 * ld * 8 warps doubles of dynamic shared memory.
 template <typename T, int VEC, int JB>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, 4)
 reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ V,
                        int64_t total, int ld, double* __restrict__ partial, int64_t partial_stride,
                        Finalize fin) {
@@ -198,48 +198,27 @@ reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const 
   const int iters = fw < total ? (int)((total - fw + stride - 1) / stride) : 0;
   const int ngroups = (nq + JB - 1) / JB;
 
-  T v[VEC], q[JB][VEC];
-  auto issue = [&](int g, int it, T (&vv)[VEC], T (&qq)[JB][VEC]) {
-    const int64_t f = f0 + (int64_t)it * stride;
-    const int j0 = g * JB;
-    if (f < total) {
-      load_chunk<T, VEC>(V, f, vv);
-#pragma unroll
-      for (int j = 0; j < JB; ++j)
-        if (j0 + j < nq) load_chunk_stream<T, VEC>(Q + (int64_t)(j0 + j) * q_stride, f, qq[j]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) vv[i] = T(0);
-    }
-  };
-  if (iters > 0) issue(0, 0, v, q);
   for (int g = 0; g < ngroups && iters > 0; ++g) {
     const int j0 = g * JB;
+    const int nj = (nq - j0) < JB ? (nq - j0) : JB;
     double acc[JB][VEC];
 #pragma unroll
     for (int j = 0; j < JB; ++j)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
-    for (int it = 0; it < iters; ++it) {
-      T vn[VEC], qn[JB][VEC];
-      const bool last_it = it + 1 == iters;
-      const bool more = !last_it || g + 1 < ngroups;
-      if (more) issue(last_it ? g + 1 : g, last_it ? 0 : it + 1, vn, qn);
-      const bool live = f0 + (int64_t)it * stride < total;
+    const T* Qg = Q + (int64_t)j0 * q_stride;
+    for (int64_t f = f0; f < total; f += stride) {
+      T v[VEC], q[JB][VEC];
+      load_chunk<T, VEC>(V, f, v);
 #pragma unroll
       for (int j = 0; j < JB; ++j)
-        if (live && j0 + j < nq) {
+        if (j < nj) load_chunk_stream<T, VEC>(Qg + (int64_t)j * q_stride, f, q[j]);
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j < nj) {
 #pragma unroll
           for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[j][i] * (double)v[i];
         }
-      if (more) {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) v[i] = vn[i];
-#pragma unroll
-        for (int j = 0; j < JB; ++j)
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) q[j][i] = qn[j][i];
-      }
     }
     // fold the group: lanes whose chunks cover the same columns are ld / VEC lanes apart
     // (all lanes when ld <= VEC); fixed xor tree => deterministic
