@@ -175,92 +175,89 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
 }
 
 // All nq basis vectors in ONE launch (narrow tiles: the per-CTA partial rows of all nq sums fit
-// the workspace).  Groups of JB vectors are accumulated in registers; V is re-read per group but
-// stays L2-resident because the basis -- read exactly once -- is loaded with evict-first hints.
-// A finished group is folded with warp shuffles into a per-warp shared-memory row, so there is
-// no CTA-wide barrier between groups: the 32 warps of an SM (4 CTAs) drift apart and cover
-// each other's group boundaries; 80 bytes of loads in flight per thread x 1024 threads per SM is
-// what the HBM latency needs (ncu: the register-double-buffered 2-CTA variant stalled at 48 %).
-// Requires ld < 32 * VEC (narrow tiles) and nq4 * ld * 8 warps doubles of dynamic shared memory.
+// the workspace).  The work is cut in two dimensions: CTA b = (group g of JB basis vectors,
+// range r of rows), R ranges per group, so a thread accumulates JB x VEC sums over a LONG run of
+// rows and folds them once -- with one CTA per row range and all groups in sequence (the first
+// version) a thread of the 8-GPU slab folded after every 3 chunks and the warp-shuffle fold cost
+// more than the dot products (ncu launch list: 2.9 us per basis vector instead of 1.3).
+// V is re-read once per group from L2 (the basis -- read exactly once -- is loaded evict-first);
+// the last CTA adds only R partial rows per sum.  Requires ld <= 64.
 template <typename T, int VEC, int JB>
 __global__ void __launch_bounds__(kBlock, 4)
 reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T* __restrict__ V,
-                       int64_t total, int ld, double* __restrict__ partial, int64_t partial_stride,
-                       Finalize fin) {
-  extern __shared__ double wsum[];  // [nq][kBlock / 32][ld]
+                       int64_t total, int ld, int R, double* __restrict__ partial,
+                       int64_t partial_stride, Finalize fin) {
   constexpr int NW = kBlock / 32;
+  __shared__ double wsum[JB][NW][64];  // per-warp sums of this CTA's group (ld <= 64)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
-  const int64_t f0 = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC;
-  // warp-uniform trip count (lane 0 owns the smallest offset): every lane takes part in the
-  // shuffles, lanes past the end contribute zeros
-  const int64_t fw = ((int64_t)blockIdx.x * kBlock + warp * 32) * VEC;
-  const int iters = fw < total ? (int)((total - fw + stride - 1) / stride) : 0;
-  const int ngroups = (nq + JB - 1) / JB;
-
-  for (int g = 0; g < ngroups && iters > 0; ++g) {
-    const int j0 = g * JB;
-    const int nj = (nq - j0) < JB ? (nq - j0) : JB;
-    double acc[JB][VEC];
+  const int g = blockIdx.x / R, r = blockIdx.x - g * R;
+  const int j0 = g * JB;
+  const int nj = (nq - j0) < JB ? (nq - j0) : JB;
+  // rows of this range: whole sweeps of kBlock chunks, so a thread keeps its columns
+  const int64_t sweep = (int64_t)kBlock * VEC;
+  const int64_t nsweeps = (total + sweep - 1) / sweep;
+  const int64_t per = (nsweeps + R - 1) / R;
+  const int64_t f_beg = (int64_t)r * per * sweep + (int64_t)threadIdx.x * VEC;
+  int64_t f_end = (int64_t)(r + 1) * per * sweep;
+  if (f_end > total) f_end = total;
+  double acc[JB][VEC];
+#pragma unroll
+  for (int j = 0; j < JB; ++j)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
+  const T* Qg = Q + (int64_t)j0 * q_stride;
+  for (int64_t f = f_beg; f < f_end; f += sweep) {
+    T v[VEC], q[JB][VEC];
+    load_chunk<T, VEC>(V, f, v);
 #pragma unroll
     for (int j = 0; j < JB; ++j)
+      if (j < nj) load_chunk_stream<T, VEC>(Qg + (int64_t)j * q_stride, f, q[j]);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[j][i] = 0.0;
-    const T* Qg = Q + (int64_t)j0 * q_stride;
-    for (int64_t f = f0; f < total; f += stride) {
-      T v[VEC], q[JB][VEC];
-      load_chunk<T, VEC>(V, f, v);
+    for (int j = 0; j < JB; ++j)
+      if (j < nj) {
 #pragma unroll
-      for (int j = 0; j < JB; ++j)
-        if (j < nj) load_chunk_stream<T, VEC>(Qg + (int64_t)j * q_stride, f, q[j]);
+        for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[j][i] * (double)v[i];
+      }
+  }
+  // fold: first the elements of a chunk that share a column (ld < VEC), then the lanes whose
+  // chunks cover the same columns (ld / VEC lanes apart); fixed xor tree => deterministic
+  const int lanes_per_row = ld >= VEC ? ld / VEC : 1;
 #pragma unroll
-      for (int j = 0; j < JB; ++j)
-        if (j < nj) {
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[j][i] += (double)q[j][i] * (double)v[i];
-        }
+  for (int j = 0; j < JB; ++j) {
+    if constexpr (VEC == 4) {
+      if (ld == 1) acc[j][0] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+      if (ld == 2) {
+        acc[j][0] += acc[j][2];
+        acc[j][1] += acc[j][3];
+      }
+    } else if constexpr (VEC == 2) {
+      if (ld == 1) acc[j][0] += acc[j][1];
     }
-    // fold the group: lanes whose chunks cover the same columns are ld / VEC lanes apart
-    // (all lanes when ld <= VEC); fixed xor tree => deterministic
-    const int lanes_per_row = ld >= VEC ? ld / VEC : 1;
 #pragma unroll
-    for (int j = 0; j < JB; ++j) {
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
+    for (int i = 0; i < VEC; ++i) {
+      if (i < ld) {
         double s = acc[j][i];
         for (int off = 16; off >= lanes_per_row; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         acc[j][i] = s;
       }
-      if constexpr (VEC == 4) {  // the elements of a chunk wrap around ld < VEC columns
-        if (ld == 1) acc[j][0] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
-        if (ld == 2) {
-          acc[j][0] += acc[j][2];
-          acc[j][1] += acc[j][3];
-        }
-      } else if constexpr (VEC == 2) {
-        if (ld == 1) acc[j][0] += acc[j][1];
-      }
-      if (j0 + j < nq && lane < lanes_per_row) {
-        double* dst = wsum + ((int64_t)(j0 + j) * NW + warp) * ld;
-        const int c0 = (threadIdx.x * VEC) & (ld - 1);
+    }
+    if (lane < lanes_per_row) {
+      const int c0 = (threadIdx.x * VEC) & (ld - 1);
 #pragma unroll
-        for (int i = 0; i < VEC; ++i)
-          if (i < ld) dst[(c0 + i) & (ld - 1)] = acc[j][i];
-      }
+      for (int i = 0; i < VEC; ++i)
+        if (i < ld) wsum[j][warp][(c0 + i) & (ld - 1)] = acc[j][i];
     }
   }
   __syncthreads();
-  // per-CTA partial row: the warps' sums in warp order
-  for (int idx = threadIdx.x; idx < nq * ld; idx += kBlock) {
-    const int a = idx / ld, c = idx - a * ld;
+  // this CTA's partial row r of the group's sums: the warps' sums in warp order
+  for (int idx = threadIdx.x; idx < nj * ld; idx += kBlock) {
+    const int j = idx / ld, c = idx - j * ld;
     double s = 0.0;
-    for (int w = 0; w < NW; ++w) {  // warps past the end of the block never wrote their row
-      const int64_t fww = ((int64_t)blockIdx.x * kBlock + w * 32) * VEC;
-      if (fww < total) s += wsum[((int64_t)a * NW + w) * ld + c];
-    }
-    partial[(int64_t)a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += wsum[j][w][c];
+    partial[(int64_t)(j0 + j) * partial_stride + (int64_t)r * ld + c] = s;
   }
-  finalize_if_last<T>(ld, partial, partial_stride, nq, fin);
+  finalize_if_last<T>(ld, partial, partial_stride, nq, fin, R);
 }
 
 template <typename T, int VEC, bool NORM>
@@ -522,16 +519,18 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
   const bool mf_wide = wide_ok(dtype, total, Q, V) && q_stride % (dtype == MF_F64 ? 2 : 4) == 0;
   const int64_t pstride = (int64_t)kMaxPartialCtas * ld;
   constexpr int JB = 4;
-  if (nq > JB && partial_rows >= (nq + JB - 1) / JB * JB) {
+  if (nq > JB && ld <= 64 && partial_rows >= (nq + JB - 1) / JB * JB) {
     // one launch for all nq sums
     Finalize fin{counter, 0, h_out, nullptr, dbl_out, peer};
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_all_kernel<T, VEC, JB>;
-      const size_t smem = (size_t)nq * (kBlock / 32) * ld * sizeof(double);
-      const int grid = resident_grid((const void*)kern, kBlock, smem,
-                                     (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC));
-      kern<<<grid, kBlock, smem, st>>>((const T*)Q, q_stride, (int)nq, (const T*)V, total, (int)ld,
-                                       partial, pstride, fin);
+      const int ngroups = (int)((nq + JB - 1) / JB);
+      const int64_t nsweeps = (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC);
+      int R = resident_grid((const void*)kern, kBlock, 0, nsweeps * ngroups) / ngroups;
+      if (R < 1) R = 1;
+      if (R > nsweeps) R = (int)(nsweeps > 0 ? nsweeps : 1);
+      kern<<<ngroups * R, kBlock, 0, st>>>((const T*)Q, q_stride, (int)nq, (const T*)V, total,
+                                           (int)ld, R, partial, pstride, fin);
     });
     return check_launch("reorth_dots_all");
   }

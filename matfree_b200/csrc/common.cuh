@@ -245,7 +245,7 @@ __device__ __forceinline__ void finalize_write(const Finalize& fin, int64_t i, d
 template <typename T>
 __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ partial,
                                                  int64_t partial_stride, int nacc_live,
-                                                 const Finalize& fin) {
+                                                 const Finalize& fin, int nrows = 0) {
   if (fin.counter == nullptr) return;
   __shared__ bool is_last;
   __threadfence();
@@ -257,7 +257,7 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int grid = gridDim.x;
+  const int grid = nrows > 0 ? nrows : (int)gridDim.x;  // partial rows per accumulator
   const int npairs = nacc_live * ld;
   const int L = lanes_per_pair(npairs);
   const int lane = threadIdx.x & (L - 1);

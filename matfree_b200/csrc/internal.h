@@ -58,9 +58,8 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
 // that costs at most 8 MB (narrow tiles), otherwise 4 (groups of four basis vectors per launch).
 inline int64_t reorth_partial_rows(int64_t ld, int64_t k) {
   const int64_t k4 = (k + 3) / 4 * 4;
-  // narrow tiles only: k4 * ld <= 512 keeps the partial rows under 6 MB and the per-warp sums of
-  // reorth_dots_all_kernel (k4 * ld * 8 warps doubles) at 32 KB of shared memory
-  return (k4 > 4 && k4 * ld <= 512) ? k4 : 4;
+  // narrow tiles only (ld <= 64): k4 * ld <= 768 keeps the partial rows under 8 MB
+  return (k4 > 4 && k4 * ld <= 768 && ld <= 64) ? k4 : 4;
 }
 // value[i] = sums[i] (mode 0) or sqrt(sums[i]) (mode 1); inv[i] = 1 / value[i]
 int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* value, void* inv,

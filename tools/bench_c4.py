@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--depth", type=int, default=100)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--planes", type=int, default=0,
+                    help="grid planes along the sharded axis (default: --grid); e.g. 32 on one GPU "
+                         "reproduces the per-GPU problem of the 8-GPU run")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -42,8 +45,8 @@ def main():
         os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=dev)
     g = a.grid
-    shape = (g, g, g)
-    n = g ** 3
+    shape = (a.planes or g, g, g)
+    n = shape[0] * g * g
     plane = g * g
     k = a.depth
     r0, r1 = _rowshard.slab_range(n, world, rank, align=plane)
@@ -104,13 +107,14 @@ def main():
         T = np.diag(diag.double().cpu().numpy()) + np.diag(off.double().cpu().numpy(), 1) + np.diag(off.double().cpu().numpy(), -1)
         theta = np.linalg.eigvalsh(T)
         lam_1d = 2.0 - 2.0 * np.cos(np.arange(1, g + 1) * np.pi / (g + 1))
-        lo, hi = 3 * lam_1d.min() + 1.0, 3 * lam_1d.max() + 1.0
+        lam_p = 2.0 - 2.0 * np.cos(np.arange(1, shape[0] + 1) * np.pi / (shape[0] + 1))
+        lo, hi = 2 * lam_1d.min() + lam_p.min() + 1.0, 2 * lam_1d.max() + lam_p.max() + 1.0
         total_ms = sum(v_[0] for v_ in per_class.values()) or 1.0
         kernels = {c_: {"ms_total_per_decomposition": v_[0] / a.steps, "launches": int(v_[1] // a.steps),
                         "share": v_[0] / total_ms}
                    for c_, v_ in sorted(per_class.items(), key=lambda kv: -kv[1][0])}
         line = {
-            "workload": f"C4: tridiag_sym(reortho=full), depth {k}, 3-D 7-pt Laplacian {g}^3 (n={n}) + 1.0*I, fp32, "
+            "workload": f"C4: tridiag_sym(reortho=full), depth {k}, 3-D 7-pt Laplacian {shape[0]}x{g}x{g} (n={n}) + 1.0*I, fp32, "
                         f"row-sharded x{world} (slabs of {nloc // plane} planes, halo {op.plan.halo_rows} rows)",
             "n_gpus": world, "route": route, "ms_per_decomposition": ms, "steps": a.steps, "warmup": a.warmup,
             "algorithmic_bytes_per_gpu": alg, "achieved_gbs_per_gpu": alg / (ms * 1e-3) / 1e9,
