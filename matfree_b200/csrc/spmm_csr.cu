@@ -108,6 +108,7 @@ struct SpmmParams {
   int prefetch;        // L2 prefetch of the rows one window ahead
   int l1pf;            // L1 prefetch of the gathers of the row `l1pf` sweeps ahead (0 = off)
   int window;          // throttle: a chunk may start when done + window > chunk
+  int pfd;             // L2 prefetch of the CTA's own X rows `pfd` sweeps ahead (0 = off)
 };
 
 // The gathers of one row held in registers: up to SEGL non-zeros (a whole stencil row);
@@ -385,6 +386,23 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
           }
           RowRegs<T, VEC, SEGL> ra;
           issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra);
+          if (p.pfd) {
+            // Short-distance L2 prefetch of the X row this row-group owns `pfd` sweeps from now
+            // (possibly in the CTA's next chunk).  All CTAs advance through one contiguous window
+            // in step, and for a banded matrix the rows a sweep gathers are the rows other CTAs
+            // own at the same sweep: without this every first touch of an X row -- and the up to
+            // nnz/row requesters that pile onto it -- waits a full DRAM latency with only one row
+            // per warp in flight.  One prefetch per 128-byte line by the first lanes of the group.
+            const int lane_in_row = threadIdx.x % tpr;
+            const int lines = (ld * (int)sizeof(T) + 127) / 128;
+            if (lane_in_row < lines) {
+              const int lp = lr + p.pfd * rps;
+              const int64_t prow = lp < R ? r0 + lp : r0 + G * R + (lp - R);
+              if (prow < n)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(
+                    reinterpret_cast<const char*>(X + prow * ld) + lane_in_row * 128));
+            }
+          }
           if (p.l1pf) {
             const int lp = lr + p.l1pf * rps;
             if (lp < nr) prefetch_row_l1<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lp);
@@ -573,7 +591,7 @@ int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T*
   R = R / rps * rps;
   if (R < rps) R = rps;
   const int64_t nchunks = (n + R - 1) / R;
-  SpmmParams prm{(int)ld, (int)R, 0, 0, 0};
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, 0};
   {
     auto kern = spmm_csr_kernel<T, VEC, 0, 8, false, false, true>;
     const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);
@@ -644,7 +662,11 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     fin = red->fin;
     partial = red->partial;
   }
-  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0};
+  // measured on C2 (tools/bench_spmm.py, profiles/r1j_spmm_sweep.jsonl): 7.62 ms without,
+  // 7.40 / 7.18 / 7.11 ms at 1 / 2 / 3 sweeps ahead, worse from 4 on (the prefetched rows then
+  // leave the window the L2 holds)
+  static const int env_pfd = env_int("MF_SPMM_PFD", 3);
+  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd};
 #define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
   do {                                                                                         \
     auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT>;                                  \

@@ -140,3 +140,58 @@ def test_gather_shards_world_size_2_gloo(tmp_path, P):
         env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+@pytest.mark.parametrize("world,n,band", [(2, 64, 5), (3, 300, 10), (4, 257, 3), (8, 4096, 256), (3, 40, 39)])
+def test_peer_halo_plans_are_mutually_consistent(world, n, band):
+    """`HaloPlan.c_struct()` (the `mf_halo_plan_t` the peer-memory halo kernel executes): replaying
+    every rank's send list with NumPy must leave every extended block equal to the global vector
+    on exactly the rows the rank's columns reference -- i.e. each send lands where the RECEIVER's
+    plan expects it -- and `recv_peers` must be exactly the ranks that send to it."""
+    from matfree_b200 import _rowshard
+
+    ranges = [_rowshard.slab_range(n, world, r, align=1) for r in range(world)]
+    needs = [(max(0, a - band), min(n, b + band)) for a, b in ranges]
+    plans = [_rowshard.HaloPlan(r, ranges, needs) for r in range(world)]
+    x = np.arange(1, n + 1, dtype=np.float64)
+    ext = []
+    for p in plans:
+        c = p.c_struct()
+        assert c.rows_alloc % 4 == 0 and c.mid_row % 4 == 0 and c.mid_row + (p.r1 - p.r0) <= c.rows_alloc
+        e = np.zeros(c.rows_alloc)
+        e[c.mid_row:c.mid_row + (p.r1 - p.r0)] = x[p.r0:p.r1]
+        ext.append(e)
+    senders = [set() for _ in range(world)]
+    for r, p in enumerate(plans):
+        c = p.c_struct()
+        for i in range(c.num_sends):
+            s = c.sends[i]
+            assert s.dst_rows_alloc == plans[s.peer].rows_alloc
+            ext[s.peer][s.dst_row:s.dst_row + s.rows] = ext[r][s.src_row:s.src_row + s.rows]
+            senders[s.peer].add(r)
+    for r, p in enumerate(plans):
+        c = p.c_struct()
+        assert sorted(senders[r]) == [c.recv_peers[i] for i in range(c.num_recv_peers)]
+        lo, hi = p.row(p.c0), p.row(p.c1)
+        assert np.array_equal(ext[r][lo:hi], x[p.c0:p.c1]), r
+
+
+def test_sharded_entry_points_validate_without_gpu():
+    import ctypes
+
+    from matfree_b200 import _lib, _rowshard
+
+    lib = _lib.load()
+    plan = _rowshard.HaloPlan(0, [(0, 13)], [(0, 13)]).c_struct()
+    op = _lib.MfOperator(kind=_lib.MF_OP_CSR, dtype=0, n=13, m=13, nnz=1, values=8, indptr=8, indices=8,
+                         lda=0, split_planes=None)
+    assert lib.mf_lanczos_sharded_heap_bytes(ctypes.byref(plan), 4, 10, _lib.MF_REORTHO_FULL, 0, 0) == 10 * 16 * 4 * 4
+    assert lib.mf_lanczos_sharded_heap_bytes(ctypes.byref(plan), 4, 10, _lib.MF_REORTHO_NONE, 0, 0) == 2 * 16 * 4 * 4
+    assert lib.mf_lanczos_sharded_workspace_bytes(ctypes.byref(op), 4, 10, _lib.MF_REORTHO_FULL) > 0
+    assert lib.mf_lanczos_sharded_workspace_bytes(ctypes.byref(op), 3, 10, _lib.MF_REORTHO_FULL) == -1
+    dense = _lib.MfOperator(kind=_lib.MF_OP_DENSE, dtype=0, n=13, m=13, nnz=0, values=8, indptr=None,
+                            indices=None, lda=13, split_planes=None)
+    assert lib.mf_lanczos_sharded_workspace_bytes(ctypes.byref(dense), 4, 10, 0) == -1  # CSR only
+    h = ctypes.c_void_p()
+    with pytest.raises(ValueError, match="world must be"):
+        _lib.check(lib.mf_comm_create(9, 0, 0, ctypes.byref(h)))
