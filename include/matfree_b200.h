@@ -305,6 +305,18 @@ int32_t mf_funm_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int
                         int64_t k, int32_t fn, double fn_param, void* out, void* workspace,
                         int64_t workspace_bytes, void* stream);
 
+/* Hutchinson integrands that return one value PER ROW (matfree/stochtrace.py:836-849 diagonal,
+ * :868-883 trace_and_diagonal, :886-898 rownorms_squared), accumulated over the probes of a tile:
+ *   t[r][c] = A[r][c] * B[r][c]     diagonal: A = probe block, B = operator applied to it;
+ *                                   squared row norms: A = B = operator applied to the probes
+ *   rowsum[r] (+)= sum_{c < num_probes} t[r][c];   rowsumsq[r] (+)= sum_c t[r][c]^2   (fp64)
+ * `accumulate` = 0 overwrites (first tile), 1 adds (later tiles).  mean = rowsum / P and
+ * sem = sqrt(rowsumsq / P - mean^2) / sqrt(P) are then what estimator_monte_carlo[_mean_and_sem]
+ * returns (stochtrace.py:47-50,83-87).  rowsumsq may be NULL. */
+int32_t mf_hutch_rows(const void* A, const void* B, int32_t dtype, int64_t n, int64_t ld,
+                      int64_t num_probes, int32_t accumulate, double* rowsum, double* rowsumsq,
+                      void* stream);
+
 /* ------------------------------------------------------------------ multi-GPU (row sharding)
  * One process per GPU.  A communicator owns one device region per rank -- a control block plus
  * a "heap" the caller places extended Lanczos blocks in -- that every rank maps into its own

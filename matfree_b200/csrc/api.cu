@@ -999,6 +999,18 @@ int32_t mf_sums_finalize(const double* sums, int64_t count, int32_t take_sqrt, v
                               (cudaStream_t)stream);
 }
 
+int32_t mf_hutch_rows(const void* A, const void* B, int32_t dtype, int64_t n, int64_t ld,
+                      int64_t num_probes, int32_t accumulate, double* rowsum, double* rowsumsq,
+                      void* stream) {
+  if (!A || !B || !rowsum || n < 0 || !valid_ld(ld) || num_probes < 0 || num_probes > ld ||
+      (dtype != MF_F32 && dtype != MF_F64)) {
+    set_error("hutch_rows: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_hutch_rows(A, B, dtype, n, ld, num_probes, accumulate != 0, rowsum, rowsumsq,
+                           (cudaStream_t)stream);
+}
+
 int32_t mf_full_offdiag(void* offdiag_row, const void* h_row, int32_t dtype, int64_t ld,
                         void* stream) {
   if (!offdiag_row || !h_row || ld <= 0) {

@@ -384,10 +384,32 @@ __global__ void sums_finalize_kernel(const double* __restrict__ sums, int64_t co
   if (inv) inv[i] = T(1) / v;
 }
 
-inline int vec_for(int32_t dtype, int64_t ld) {
-  const int nv = dtype == MF_F64 ? 2 : 4;
-  return ld >= nv ? nv : 1;
+// Hutchinson row statistics over the probes of a tile (matfree/stochtrace.py:836-849,868-898):
+// t[r][c] = A[r][c] * B[r][c]   (diagonal: A = probes, B = A v;  row norms: A = B = A v)
+// rowsum[r] (+)= sum_{c < np} t,  rowsumsq[r] (+)= sum_{c < np} t^2      (fp64)
+// One warp per row: coalesced over the probes, fixed xor tree => deterministic, no atomics.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+hutch_rows_kernel(const T* __restrict__ A, const T* __restrict__ B, int64_t n, int ld, int np,
+                  int accumulate, double* __restrict__ rowsum, double* __restrict__ rowsumsq) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (kBlock / 32);
+  for (int64_t r = (int64_t)blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); r < n; r += warps) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int c = lane; c < np; c += 32) {
+      const double t = (double)A[r * ld + c] * (double)B[r * ld + c];
+      s1 += t;
+      s2 += t * t;
+    }
+    s1 = group_sum(s1, 32);
+    s2 = group_sum(s2, 32);
+    if (lane == 0) {
+      rowsum[r] = accumulate ? rowsum[r] + s1 : s1;
+      if (rowsumsq) rowsumsq[r] = accumulate ? rowsumsq[r] + s2 : s2;
+    }
+  }
 }
+
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 // all of the (possibly null) pointers 16-byte aligned and the element count a whole number of
@@ -640,6 +662,26 @@ int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* 
     sums_finalize_kernel<double><<<blocks, threads, 0, st>>>(sums, count, mode, (double*)value,
                                                              (double*)inv);
   return check_launch("sums_finalize");
+}
+
+int32_t launch_hutch_rows(const void* A, const void* B, int32_t dtype, int64_t n, int64_t ld,
+                          int64_t num_probes, bool accumulate, double* rowsum, double* rowsumsq,
+                          cudaStream_t st) {
+  MF_KSCOPE(MF_KC_OTHER, st);
+  if (n <= 0) return MF_OK;
+  const int64_t want = (n + kBlock / 32 - 1) / (kBlock / 32);
+  if (dtype == MF_F32) {
+    auto kern = hutch_rows_kernel<float>;
+    const int grid = resident_grid((const void*)kern, kBlock, 0, want);
+    kern<<<grid, kBlock, 0, st>>>((const float*)A, (const float*)B, n, (int)ld, (int)num_probes,
+                                  accumulate ? 1 : 0, rowsum, rowsumsq);
+  } else {
+    auto kern = hutch_rows_kernel<double>;
+    const int grid = resident_grid((const void*)kern, kBlock, 0, want);
+    kern<<<grid, kBlock, 0, st>>>((const double*)A, (const double*)B, n, (int)ld, (int)num_probes,
+                                  accumulate ? 1 : 0, rowsum, rowsumsq);
+  }
+  return check_launch("hutch_rows");
 }
 
 int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dtype, int64_t ld,

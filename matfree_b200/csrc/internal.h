@@ -75,6 +75,11 @@ int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scal
                              cudaStream_t st);
 int32_t launch_transpose(const void* src, void* dst, int32_t dtype, int64_t n,
                          int64_t num_probes, int64_t ld, bool to_blocked, cudaStream_t st);
+// rowsum[r] (+)= sum_c A[r][c] B[r][c], rowsumsq[r] (+)= sum_c (A B)^2 over the first num_probes
+// columns (Hutchinson diagonal / row norms, stochtrace.py:836-849,868-898)
+int32_t launch_hutch_rows(const void* A, const void* B, int32_t dtype, int64_t n, int64_t ld,
+                          int64_t num_probes, bool accumulate, double* rowsum, double* rowsumsq,
+                          cudaStream_t st);
 // tiny helpers on [ld] scalar rows
 int32_t launch_full_offdiag(void* betas_prev_row, const void* h_row, int32_t dtype, int64_t ld,
                             cudaStream_t st);

@@ -5,7 +5,9 @@
   (`stochtrace.py:927-937,957-977`): the returned ``sample(key)`` gives the
   ``(num, n)`` device array `jax.random.rademacher` / `normal` would produce for
   that key (bit-exact Rademacher; Threefry-2x32, partitionable counters).
-* `monte_carlo_trace()` (`stochtrace.py:853-865`).
+* `monte_carlo_trace()` (`stochtrace.py:853-865`), `monte_carlo_diagonal()`,
+  `monte_carlo_trace_and_diagonal()`, `monte_carlo_rownorms_squared()`,
+  `monte_carlo_frobeniusnorm_squared()` (`stochtrace.py:836-914`).
 * `estimator_monte_carlo(integrand, sampler)` and `_mean_and_sem`
   (`stochtrace.py:7-52,55-89`).
 
@@ -86,7 +88,11 @@ def _make_sampler(kind: int, args_like, num: int):
                                     int(key[1]), kind, 0, None, _device.stream()))
         return out
 
-    sample._mf_sampler = {"kind": kind, "n": n, "num": num, "dtype": dtype}
+    shape = None  # a single array-like keeps its shape in per-row outputs (ravel_pytree's unflatten)
+    if len(args_like) == 1 and not isinstance(args_like[0], (dict, list, tuple)):
+        shp = tuple(getattr(args_like[0], "shape", np.shape(args_like[0])))
+        shape = shp if len(shp) > 1 else None
+    sample._mf_sampler = {"kind": kind, "n": n, "num": num, "dtype": dtype, "shape": shape}
     return sample
 
 
@@ -114,6 +120,149 @@ def monte_carlo_trace():
     return integrand
 
 
+def _unflatten_like(flat, like):
+    """Inverse of the reference's `ravel_pytree` for the simple pytrees samplers accept."""
+    if like is None:
+        return flat
+    return flat.reshape(tuple(like))
+
+
+def monte_carlo_diagonal():
+    """Integrand ``v * (A v)`` (`stochtrace.py:836-849`): its mean estimates ``diag(A)``."""
+
+    def integrand(matvec, v, *parameters):
+        v = _device.as_device(v)
+        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
+        return (v.reshape(-1) * Qv).reshape(v.shape)
+
+    integrand._mf_integrand = {"kind": "diagonal"}
+    return integrand
+
+
+def monte_carlo_trace_and_diagonal():
+    """Integrand ``{"trace": v^T A v, "diagonal": v * (A v)}`` (`stochtrace.py:868-883`)."""
+
+    def integrand(matvec, v, *parameters):
+        import torch
+
+        v = _device.as_device(v)
+        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
+        return {"trace": torch.dot(v.reshape(-1), Qv), "diagonal": (v.reshape(-1) * Qv).reshape(v.shape)}
+
+    integrand._mf_integrand = {"kind": "trace_and_diagonal"}
+    return integrand
+
+
+def monte_carlo_rownorms_squared():
+    """Integrand ``(A v)^2`` elementwise (`stochtrace.py:886-898`): its mean estimates the squared
+    row norms of ``A``."""
+
+    def integrand(matvec, v, *parameters):
+        v = _device.as_device(v)
+        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
+        return (Qv * Qv).reshape(v.shape)
+
+    integrand._mf_integrand = {"kind": "rownorms_squared"}
+    return integrand
+
+
+def monte_carlo_frobeniusnorm_squared():
+    """Integrand ``|A v|^2`` (`stochtrace.py:901-914`): its mean estimates ``|A|_F^2``."""
+
+    def integrand(matvec, v, *parameters):
+        import torch
+
+        v = _device.as_device(v)
+        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
+        return torch.dot(Qv, Qv)
+
+    integrand._mf_integrand = {"kind": "frobeniusnorm_squared"}
+    return integrand
+
+
+_BLOCK_KINDS = ("diagonal", "trace_and_diagonal", "rownorms_squared", "frobeniusnorm_squared")
+
+
+def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None):
+    """The Hutchinson integrands that are not a single dot product, probe-blocked: per tile one
+    `mf_probe_gen` (blocked layout, bit-identical to the reference's sample array), one block
+    product `mf_matmat` and one pass that folds the tile into per-row fp64 sums
+    (`mf_hutch_rows`) and/or per-probe column sums (`mf_block_dot`).  Returns
+    ``(mean, sem)`` with the integrand's output structure, or None if not applicable."""
+    ispec = getattr(integrand, "_mf_integrand", None)
+    sspec = getattr(sampler, "_mf_sampler", None)
+    if (ispec is None or ispec["kind"] not in _BLOCK_KINDS or sspec is None
+            or not isinstance(matvec, ops.Operator) or parameters):
+        return None
+    import torch
+
+    lib = _lib.load()
+    op = matvec
+    kind = ispec["kind"]
+    n, P, dt = sspec["n"], sspec["num"], op.dtype
+    if n != op.n:
+        raise ValueError(f"sampler draws vectors of length {n}, operator dimension is {op.n}")
+    if sspec["dtype"] != dt:
+        raise TypeError(f"sampler dtype {sspec['dtype']} does not match operator dtype {dt}")
+    dev = _device.device()
+    mfdt = _device.mf_dtype(dt)
+    p0, p1, group, world = 0, P, None, 1
+    if _PROBE_GROUP["enabled"]:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            group = _PROBE_GROUP["group"]
+            world = dist.get_world_size(group)
+            p0, p1 = _sharding.shard_range(P, world, dist.get_rank(group))
+    nloc = p1 - p0
+    ld = int(tile) if tile else _device.ld_for(max(nloc, 1))
+    want_rows = kind != "frobeniusnorm_squared"
+    want_cols = kind in ("trace_and_diagonal", "frobeniusnorm_squared")
+    V = torch.empty((n, ld), dtype=dt, device=dev)
+    rows = torch.zeros((2, n), dtype=torch.float64, device=dev) if want_rows else None
+    colvals = []
+    bws = _device.workspace(lib.mf_blockvec_workspace_bytes(ld, 4))
+    first = True
+    for t0 in range(p0, p1, ld):
+        npb = min(ld, p1 - t0)
+        _lib.check(lib.mf_probe_gen(V.data_ptr(), mfdt, _lib.MF_LAYOUT_BLOCKED, n, ld, t0, npb,
+                                    int(key[0]), int(key[1]), sspec["kind"], 0, None, _device.stream()))
+        W = op.matmat_blocked(V)
+        if want_rows:
+            A = W if kind == "rownorms_squared" else V
+            _lib.check(lib.mf_hutch_rows(A.data_ptr(), W.data_ptr(), mfdt, n, ld, npb, int(not first),
+                                         rows[0].data_ptr(), rows[1].data_ptr(), _device.stream()))
+        if want_cols:
+            A = W if kind == "frobeniusnorm_squared" else V
+            sums = torch.empty((ld,), dtype=torch.float64, device=dev)
+            _lib.check(lib.mf_block_dot(A.data_ptr(), W.data_ptr(), mfdt, n, ld, sums.data_ptr(),
+                                        bws.data_ptr(), bws.numel(), _device.stream()))
+            colvals.append(sums[:npb].to(dt))
+        first = False
+    out_mean, out_sem = {}, {}
+    if want_rows:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(rows, group=group)
+        mean = rows[0] / P
+        var = torch.clamp(rows[1] / P - mean * mean, min=0.0)
+        like = sspec.get("shape")
+        out_mean["rows"] = _unflatten_like(mean.to(dt), like)
+        out_sem["rows"] = _unflatten_like((torch.sqrt(var) / np.sqrt(P)).to(dt), like)
+    if want_cols:
+        vals = torch.cat(colvals) if colvals else torch.empty((0,), dtype=dt, device=dev)
+        if world > 1:
+            vals = _sharding.gather_shards(vals, P, group)
+        out_mean["cols"], out_sem["cols"] = _reduce(vals)
+    if kind == "trace_and_diagonal":
+        return ({"trace": out_mean["cols"], "diagonal": out_mean["rows"]},
+                {"trace": out_sem["cols"], "diagonal": out_sem["rows"]})
+    if kind == "frobeniusnorm_squared":
+        return out_mean["cols"], out_sem["cols"]
+    return out_mean["rows"], out_sem["rows"]
+
+
 # ----------------------------------------------------------------------------
 
 
@@ -123,6 +272,8 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
     sspec = getattr(sampler, "_mf_sampler", None)
     if ispec is None or sspec is None or not isinstance(matvec, ops.Operator) or parameters:
         return None
+    if ispec["kind"] in _BLOCK_KINDS:
+        return None  # handled by _hutchinson_block
     import torch
 
     lib = _lib.load()
@@ -214,11 +365,21 @@ def _reduce(values):
     return stats[0].to(values.dtype), stats[2].to(values.dtype)
 
 
+def _tree_map(fn, tree):
+    if isinstance(tree, dict):
+        return {k: _tree_map(fn, v) for k, v in tree.items()}
+    return fn(tree)
+
+
 def _generic_values(integrand, sampler, matvecs, key, parameters):
+    """Sample-by-sample evaluation of a user integrand (any callable, dict outputs allowed):
+    the reference's `vmap` (`stochtrace.py:49`) as a loop; stacked along a leading sample axis."""
     import torch
 
     samples = sampler(key)
     vals = [integrand(matvecs, s, *parameters) for s in samples]
+    if vals and isinstance(vals[0], dict):
+        return {k: torch.stack([_device.as_device(v[k]) for v in vals]) for k in vals[0]}
     return torch.stack([_device.as_device(v) for v in vals])
 
 
@@ -229,8 +390,11 @@ def estimator_monte_carlo(integrand, /, sampler):
         vals = _fused_values(integrand, sampler, matvecs, key, parameters)
         if vals is not None:
             return _reduce(vals)[0]
+        blk = _hutchinson_block(integrand, sampler, matvecs, key, parameters)
+        if blk is not None:
+            return blk[0]
         Qs = _generic_values(integrand, sampler, matvecs, key, parameters)
-        return Qs.mean(dim=0)
+        return _tree_map(lambda q: q.mean(dim=0), Qs)
 
     estimate.per_probe = lambda matvecs, key, *parameters, **kw: _fused_values(
         integrand, sampler, matvecs, key, parameters, **kw)
@@ -246,7 +410,11 @@ def estimator_monte_carlo_mean_and_sem(integrand, /, sampler):
         vals = _fused_values(integrand, sampler, matvecs, key, parameters)
         if vals is not None:
             return _reduce(vals)
+        blk = _hutchinson_block(integrand, sampler, matvecs, key, parameters)
+        if blk is not None:
+            return blk
         Qs = _generic_values(integrand, sampler, matvecs, key, parameters)
-        return Qs.mean(dim=0), Qs.std(dim=0, unbiased=False) / np.sqrt(Qs.shape[0])
+        return (_tree_map(lambda q: q.mean(dim=0), Qs),
+                _tree_map(lambda q: q.std(dim=0, unbiased=False) / np.sqrt(q.shape[0]), Qs))
 
     return estimate

@@ -245,13 +245,65 @@ def monte_carlo_trace():
     return integrand
 
 
+def monte_carlo_diagonal():
+    """`matfree/stochtrace.py:836-849` (real dtypes: conj is the identity)."""
+
+    def integrand(matvec, v):
+        return v * matvec(v)
+
+    return integrand
+
+
+def monte_carlo_trace_and_diagonal():
+    """`matfree/stochtrace.py:868-883`."""
+
+    def integrand(matvec, v):
+        qv = matvec(v)
+        return {"trace": np.inner(v, qv), "diagonal": v * qv}
+
+    return integrand
+
+
+def monte_carlo_rownorms_squared():
+    """`matfree/stochtrace.py:886-898`."""
+
+    def integrand(matvec, v):
+        qv = matvec(v)
+        return qv * qv
+
+    return integrand
+
+
+def monte_carlo_frobeniusnorm_squared():
+    """`matfree/stochtrace.py:901-914`."""
+
+    def integrand(matvec, v):
+        x = matvec(v)
+        return np.inner(x, x)
+
+    return integrand
+
+
+def _stack(vals):
+    """The sample axis `vmap` adds (`stochtrace.py:49`), for arrays and one-level dicts."""
+    if isinstance(vals[0], dict):
+        return {k: np.stack([v[k] for v in vals]) for k in vals[0]}
+    return np.stack(vals)
+
+
+def _tree_map(fn, tree):
+    if isinstance(tree, dict):
+        return {k: fn(v) for k, v in tree.items()}
+    return fn(tree)
+
+
 def estimator_monte_carlo(integrand, /, sampler):
     """`matfree/stochtrace.py:7-52`."""
 
     def estimate(matvec, key):
         samples = sampler(key)
-        qs = np.stack([integrand(matvec, s) for s in samples])
-        return np.mean(qs, axis=0)
+        qs = _stack([integrand(matvec, s) for s in samples])
+        return _tree_map(lambda q: np.mean(q, axis=0), qs)
 
     return estimate
 
@@ -261,8 +313,9 @@ def estimator_monte_carlo_mean_and_sem(integrand, /, sampler):
 
     def estimate(matvec, key):
         samples = sampler(key)
-        qs = np.stack([integrand(matvec, s) for s in samples])
-        return np.mean(qs, axis=0), np.std(qs, axis=0) / np.sqrt(qs.shape[0])
+        qs = _stack([integrand(matvec, s) for s in samples])
+        return (_tree_map(lambda q: np.mean(q, axis=0), qs),
+                _tree_map(lambda q: np.std(q, axis=0) / np.sqrt(q.shape[0]), qs))
 
     return estimate
 

@@ -247,3 +247,27 @@ def test_batched_matches_single(reortho, dtype):
     single = np.array([integrand(lambda x: A @ x, v) for v in V])
     tol = 2e-4 if dtype == np.float32 else 1e-10
     assert np.allclose(q, single, rtol=tol)
+
+
+# tests/test_stochtrace/test_monte_carlo/test_{diagonal,trace_and_diagonal,rownorms_squared,
+# frobeniusnorm_squared}.py: the estimates approach the dense ground truth (rtol/atol 0.05 there)
+def test_hutchinson_row_integrands_against_dense_truth():
+    n, num = 6, 20_000
+    A = prng.normal(prng.prng_key(4), (n, n), np.float64)
+    mv = lambda v: A @ v  # noqa: E731
+    sampler = ref.sampler_normal(n, num=num, dtype=np.float64)
+    key = prng.prng_key(1)
+    diag = ref.estimator_monte_carlo(ref.monte_carlo_diagonal(), sampler)(mv, key)
+    assert np.allclose(diag, np.diag(A), rtol=0.05, atol=0.05)
+    both, sem = ref.estimator_monte_carlo_mean_and_sem(ref.monte_carlo_trace_and_diagonal(), sampler)(mv, key)
+    assert np.allclose(both["diagonal"], diag) and np.allclose(both["trace"], np.trace(A), rtol=0.05, atol=0.1)
+    assert sem["diagonal"].shape == (n,) and sem["trace"].shape == ()
+    rows = ref.estimator_monte_carlo(ref.monte_carlo_rownorms_squared(), sampler)(mv, key)
+    assert np.allclose(rows, np.sum(A * A, axis=1), rtol=0.05)
+    fro = ref.estimator_monte_carlo(ref.monte_carlo_frobeniusnorm_squared(), sampler)(mv, key)
+    assert np.allclose(fro, np.sum(A * A), rtol=0.05)
+    # Rademacher probes and a diagonal operator: every sample is exact (v_i^2 = 1)
+    D = np.diag(np.arange(1.0, n + 1))
+    signs = ref.sampler_signs(n, num=7, dtype=np.float64)
+    got = ref.estimator_monte_carlo(ref.monte_carlo_diagonal(), signs)(lambda v: D @ v, key)
+    assert np.array_equal(got, np.arange(1.0, n + 1))
