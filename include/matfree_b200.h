@@ -283,6 +283,28 @@ int32_t mf_slq_estimate_gram(const void* A, const void* A_planes, int64_t m, int
                              void* quad_out, void* workspace, int64_t workspace_bytes,
                              void* stream);
 
+/* Golub-Kahan bidiagonalisation support (decomp.bidiag, matfree/decomp.py:608-750, and
+ * funm.monte_carlo_funm_product[_logdet | _schatten_norm], matfree/funm.py:246-319).
+ *   mf_matmat_rect: W = A X (trans = 0: X [n][ld] -> W [m][ld]) or W = A^T X (trans = 1:
+ *     X [m][ld] -> W [n][ld]) for a dense row-major A [m][lda >= n] -- the matvec and its `vjp`
+ *     (decomp.py:703,712) on a probe block; fp32 with A_planes (mf_operator_split of a GRAM
+ *     operator over the same A) runs on tcgen05 (3xTF32), fp64 on the FP64 tensor cores.
+ *   mf_bidiag_quad: as mf_tridiag_quad, for an upper-bidiagonal B given by its diagonal
+ *     `alphas` [k][ld] and superdiagonal `betas` [k][ld] (row i = B[i][i+1], row k-1 unused):
+ *     init_len^2 * e1^T f(B^T B) e1 -- the reference takes the SVD of B and squares the singular
+ *     values (funm.py:305-319); here T = B^T B is formed in fp64 inside the kernel.
+ * The recurrence itself is driven with the building blocks above (mf_lanczos_update,
+ * mf_reorth_dots / _update, mf_block_scale, mf_sums_finalize). */
+int64_t mf_matmat_rect_workspace_bytes(int64_t m, int64_t n, int64_t lda, int32_t trans,
+                                       int32_t dtype, int32_t have_planes, int64_t ld);
+int32_t mf_matmat_rect(const void* A, const void* A_planes, int64_t m, int64_t n, int64_t lda,
+                       int32_t trans, int32_t dtype, const void* X, void* W, int64_t ld,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+int32_t mf_bidiag_quad(const void* alphas, const void* betas, const void* init_len,
+                       int32_t dtype, int64_t ld, int64_t num_probes, int64_t k, int32_t fn,
+                       double fn_param, void* quad, double* nodes, double* weights,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
 /* funm.funm_lanczos_sym (matfree/funm.py:114-147) given a stored basis:
  * out[n][ld] = init_len * sum_j Q[j] * y[j],  y = f(T) e1 per probe
  * (coeffs [k][ld], dtype).  `mf_tridiag_funm_e1` computes y. */

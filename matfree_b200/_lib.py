@@ -119,6 +119,13 @@ SIGNATURES = {
                                      c_int32, c_double, c_void_p, c_void_p, c_int64, c_void_p]),
     "mf_basis_combine": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64,
                                    c_int64, c_void_p, c_void_p]),
+    "mf_matmat_rect_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                                 c_int64]),
+    "mf_matmat_rect": (c_int32, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32,
+                                 c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "mf_bidiag_quad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64,
+                                 c_int32, c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p]),
     "mf_hutch_rows": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int32,
                                 c_void_p, c_void_p, c_void_p]),
     "mf_comm_create": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_void_p)]),

@@ -843,6 +843,58 @@ int32_t mf_tridiag_quad(const void* alphas, const void* betas, const void* init_
                              (cudaStream_t)stream);
 }
 
+int32_t mf_bidiag_quad(const void* alphas, const void* betas, const void* init_len,
+                       int32_t dtype, int64_t ld, int64_t num_probes, int64_t k, int32_t fn,
+                       double fn_param, void* quad, double* nodes, double* weights,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+  if (k <= 0 || ld <= 0 || num_probes > ld || alphas == nullptr || betas == nullptr) {
+    set_error("bidiag_quad: bad arguments (k=%lld ld=%lld)", (long long)k, (long long)ld);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if (workspace == nullptr || workspace_bytes < 3 * k * ld * 8) {
+    set_error("bidiag_quad: workspace too small");
+    return MF_ERR_WORKSPACE;
+  }
+  return launch_tridiag_quad(alphas, betas, init_len, dtype, ld, num_probes, k, fn, fn_param,
+                             quad, nodes, weights, nullptr, (double*)workspace,
+                             (cudaStream_t)stream, 1);
+}
+
+// One product with a rectangular dense operator or its transpose (Golub-Kahan needs both).
+int64_t mf_matmat_rect_workspace_bytes(int64_t m, int64_t n, int64_t lda, int32_t trans,
+                                       int32_t dtype, int32_t have_planes, int64_t ld) {
+  const int64_t M = trans ? n : m, K = trans ? m : n;
+  if (have_planes && g_gemm_tc.load(std::memory_order_relaxed) && tc_gemm_supported(lda, M, K, ld, dtype))
+    return 2 * K * ld * 4 + 256;
+  return 256;
+}
+
+int32_t mf_matmat_rect(const void* A, const void* A_planes, int64_t m, int64_t n, int64_t lda,
+                       int32_t trans, int32_t dtype, const void* X, void* W, int64_t ld,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
+  if (!A || !X || !W || m <= 0 || n <= 0 || lda < n || !valid_ld(ld) ||
+      (dtype != MF_F32 && dtype != MF_F64)) {
+    set_error("matmat_rect: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = trans ? n : m, K = trans ? m : n;
+  if (A_planes != nullptr && g_gemm_tc.load(std::memory_order_relaxed) &&
+      tc_gemm_supported(lda, M, K, ld, dtype)) {
+    const int64_t need = 2 * K * ld * 4;
+    void* xs = (void*)align_up((int64_t)(uintptr_t)workspace, 256);
+    if (workspace == nullptr || (char*)xs + need > (char*)workspace + workspace_bytes) {
+      set_error("matmat_rect: workspace for the TF32 planes of X is missing");
+      return MF_ERR_WORKSPACE;
+    }
+    MF_TRY(launch_split_tf32(X, xs, K * ld, st));
+    return launch_gemm_tcgen05(A_planes, lda, trans != 0, M, K, xs, 1, nullptr, W, nullptr, ld,
+                               gemm_variant(), st);
+  }
+  const auto gemm = g_gemm_tc.load(std::memory_order_relaxed) ? launch_gemm_blocked : launch_gemm_simt;
+  return gemm(A, lda, trans != 0, M, K, X, nullptr, W, ld, dtype, st);
+}
+
 int32_t mf_tridiag_funm_e1(const void* alphas, const void* betas, int32_t dtype, int64_t ld,
                            int64_t num_probes, int64_t k, int32_t fn, double fn_param,
                            void* coeffs, void* workspace, int64_t workspace_bytes,

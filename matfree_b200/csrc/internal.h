@@ -143,7 +143,8 @@ int32_t launch_peer_barrier(const mf_comm* c, cudaStream_t st);
 int32_t launch_tridiag_quad(const void* alphas, const void* betas, const void* init_len,
                             int32_t dtype, int64_t ld, int64_t num_probes, int64_t k,
                             int32_t fn, double fn_param, void* quad, double* nodes,
-                            double* weights, void* coeffs, double* work, cudaStream_t st);
+                            double* weights, void* coeffs, double* work, cudaStream_t st,
+                            int product = 0);
 int32_t launch_mc_reduce(const void* values, int32_t dtype, int64_t num, double* stats,
                          cudaStream_t st);
 

@@ -37,7 +37,8 @@ __global__ void tridiag_ql_kernel(const T* __restrict__ alphas, const T* __restr
                                   const T* __restrict__ init_len, int ld, int num_probes, int k,
                                   int fn, double fn_param, T* __restrict__ quad,
                                   double* __restrict__ nodes, double* __restrict__ weights,
-                                  T* __restrict__ coeffs, double* __restrict__ work) {
+                                  T* __restrict__ coeffs, double* __restrict__ work,
+                                  int product) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= num_probes) return;
   double* d = work + p;
@@ -48,8 +49,19 @@ __global__ void tridiag_ql_kernel(const T* __restrict__ alphas, const T* __restr
 #define Z0(i) z[(int64_t)(i) * ld]
 #define ZF(r, j) z[((int64_t)(r) * k + (j)) * ld]
   for (int i = 0; i < k; ++i) {
-    D(i) = (double)alphas[(int64_t)i * ld + p];
-    E(i) = (i < k - 1) ? (double)betas[(int64_t)i * ld + p] : 0.0;
+    if (product) {
+      // (alphas, betas) are the diagonal / superdiagonal of an upper-bidiagonal B (Golub-Kahan,
+      // matfree/decomp.py:608-750); the quadrature runs on T = B^T B, formed here in fp64:
+      // T[i][i] = a_i^2 + e_{i-1}^2, T[i][i+1] = a_i e_i  (matfree/funm.py:305-319 takes the
+      // SVD of B and squares the singular values -- the same spectrum)
+      const double a = (double)alphas[(int64_t)i * ld + p];
+      const double em = i > 0 ? (double)betas[(int64_t)(i - 1) * ld + p] : 0.0;
+      D(i) = a * a + em * em;
+      E(i) = (i < k - 1) ? a * (double)betas[(int64_t)i * ld + p] : 0.0;
+    } else {
+      D(i) = (double)alphas[(int64_t)i * ld + p];
+      E(i) = (i < k - 1) ? (double)betas[(int64_t)i * ld + p] : 0.0;
+    }
     if (FULL) {
       for (int r = 0; r < k; ++r) ZF(r, i) = (r == i) ? 1.0 : 0.0;
     } else {
@@ -195,7 +207,8 @@ __global__ void mc_reduce_kernel(const T* __restrict__ v, int64_t num, double* _
 int32_t launch_tridiag_quad(const void* alphas, const void* betas, const void* init_len,
                             int32_t dtype, int64_t ld, int64_t num_probes, int64_t k,
                             int32_t fn, double fn_param, void* quad, double* nodes,
-                            double* weights, void* coeffs, double* work, cudaStream_t st) {
+                            double* weights, void* coeffs, double* work, cudaStream_t st,
+                            int product) {
   MF_KSCOPE(MF_KC_TRIDIAG_QUAD, st);
   if (num_probes <= 0) return MF_OK;
   const int threads = 32;
@@ -204,7 +217,7 @@ int32_t launch_tridiag_quad(const void* alphas, const void* betas, const void* i
 #define MF_QL(T, FULL)                                                                        \
   tridiag_ql_kernel<T, FULL><<<blocks, threads, 0, st>>>(                                     \
       (const T*)alphas, (const T*)betas, (const T*)init_len, (int)ld, (int)num_probes, (int)k, \
-      fn, fn_param, (T*)quad, nodes, weights, (T*)coeffs, work)
+      fn, fn_param, (T*)quad, nodes, weights, (T*)coeffs, work, product)
   if (dtype == MF_F32) {
     if (full) MF_QL(float, true); else MF_QL(float, false);
   } else {

@@ -142,3 +142,117 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
     decompose._mf_spec = {"kind": "tridiag_sym", "num_matvecs": k, "reortho": reortho,
                           "materialize": materialize}
     return decompose
+
+
+def bidiag_blocked(op, V0b, k: int, reortho: str):
+    """Golub-Kahan bidiagonalisation of a block of start vectors ``V0b[n][ld]``
+    (`matfree/decomp.py:645-735`, the operation order of `step`).
+
+    Returns ``(alphas [k][ld], betas [k][ld], init_len [ld], Us [k][m][ld], Vs [k][n][ld],
+    vk [n][ld])``: `alphas` is the diagonal of the upper-bidiagonal ``B``, row ``i < k-1`` of
+    `betas` its superdiagonal entry ``B[i][i+1]`` and row ``k-1`` the final ``beta`` (the
+    reference keeps these as ``betas[1:]`` and ``beta``); `vk` is the normalised last vector.
+    All arithmetic on vectors is the library's: two GEMMs per step (`mf_matmat_rect`), the fused
+    update+norm kernel, and the CGS dots / update pair applied twice for ``reortho="full"``."""
+    import torch
+
+    from matfree_b200 import _rowshard
+
+    n, ld = V0b.shape
+    m = op.m
+    dt, dev = V0b.dtype, V0b.device
+    be = _rowshard.CudaBackend(ld, max_nq=max(k, 1))
+    kk = max(k, 1)
+    Us = torch.zeros((kk, m, ld), dtype=dt, device=dev)
+    Vs = torch.zeros((kk, n, ld), dtype=dt, device=dev)
+    alphas = torch.zeros((kk, ld), dtype=dt, device=dev)
+    betas = torch.zeros((kk, ld), dtype=dt, device=dev)
+    init_len = torch.empty((ld,), dtype=dt, device=dev)
+    one = torch.empty((ld,), dtype=dt, device=dev)
+    h = torch.empty((kk, ld), dtype=dt, device=dev)
+    sums = torch.zeros((kk, ld), dtype=torch.float64, device=dev)
+    sq = torch.zeros((ld,), dtype=torch.float64, device=dev)
+    full = reortho == "full"
+
+    def cgs_twice(Q, nq, W):
+        """W -= Q^T (Q W), twice (decomp.py:706-709,715-718); the squared norm of the result."""
+        for rep in range(2):
+            be.reorth_dots(Q, nq, W, sums[:nq])
+            be.finalize(sums[:nq], False, value=h[:nq])
+            be.reorth_update(Q, nq, h, W, sq if rep == 1 else None)
+
+    be.block_dot(V0b, V0b, sq)
+    be.finalize(sq, True, value=init_len)
+    vk = torch.empty((n, ld), dtype=dt, device=dev)
+    be.scale(V0b, init_len, vk, True)                # decomp.py:660
+    be.block_dot(vk, vk, sq)                         # `init` normalises once more (:697)
+    be.finalize(sq, True, value=one)
+    be.scale(vk, one, Vs[0] if k > 0 else vk, True)
+    for i in range(k):
+        vi = Vs[i]                                   # :699 (vk was written straight into Vs[i])
+        W = op.apply_blocked(vi, trans=False)        # :703  A vk
+        if i > 0:
+            be.lanczos_update(W, Us[i - 1], betas[i - 1], None, None, W, sq)   # :704
+            if full:
+                cgs_twice(Us, i, W)                  # :705-709 (rows >= i of Us are zero)
+        else:
+            be.block_dot(W, W, sq)
+        be.finalize(sq, True, value=alphas[i])       # :711
+        be.scale(W, alphas[i], Us[i], True)
+        Z = op.apply_blocked(Us[i], trans=True)      # :714  A^T uk
+        be.lanczos_update(Z, vi, alphas[i], None, None, Z, sq)                 # :715
+        if full:
+            cgs_twice(Vs, i + 1, Z)                  # :716-720
+        be.finalize(sq, True, value=betas[i])        # :722
+        if i + 1 < k:
+            be.scale(Z, betas[i], Vs[i + 1], True)
+        else:
+            be.scale(Z, betas[i], vk, True)
+    return alphas[:k], betas[:k], init_len, Us[:k], Vs[:k], vk
+
+
+def _todense_bidiag(d, e):
+    import torch
+
+    k = d.shape[0]
+    B = torch.zeros((k, k), dtype=d.dtype, device=d.device)
+    idx = torch.arange(k, device=d.device)
+    B[idx, idx] = d
+    if k > 1:
+        B[idx[:-1], idx[1:]] = e
+    return B
+
+
+def bidiag(num_matvecs: int, /, materialize: bool = True, reortho: str = "full"):
+    """Construct an implementation of bidiagonalisation via the Golub-Kahan algorithm
+    (`matfree/decomp.py:608-750`): ``A ~ U B V^T`` for an arbitrary real rectangular matrix.
+
+    The matvec must be a registered rectangular operator (`ops.rect(A)`: the vector-matrix
+    product the reference gets from `jax.vjp` needs the operator's buffers)."""
+    if reortho not in ("full", "none"):
+        raise ValueError(f"reortho={reortho} unsupported. Choose eiter {'full', 'none'}.")
+    k = int(num_matvecs)
+
+    def estimate(Av, v0, *parameters):
+        import torch
+
+        if parameters:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        op = ops.require_operator(Av, "bidiag")
+        if not isinstance(op, ops.RectOperator):
+            raise TypeError("bidiag: matvec must be ops.rect(A)")
+        v = _device.as_device(v0, op.dtype).reshape(-1)
+        if v.shape[0] != op.n:
+            raise ValueError(f"vector has length {v.shape[0]}, operator has {op.n} columns")
+        if k > min(op.m, op.n) or k < 0:
+            raise ValueError(_error_num_matvecs(k, maxval=min(op.m, op.n), minval=0))  # decomp.py:655-658
+        alphas, betas, init_len, Us, Vs, vk = bidiag_blocked(op, v.reshape(-1, 1).contiguous(), k, reortho)
+        d = alphas[:, 0]
+        e = betas[: max(k - 1, 0), 0]
+        beta = betas[k - 1, 0] if k > 0 else torch.zeros((), dtype=op.dtype, device=v.device)
+        J = _todense_bidiag(d, e) if materialize else (d, e)
+        return _DecompResult(Q_tall=(Us[:, :, 0], Vs[:, :, 0]), J_small=J, residual=beta * vk[:, 0],
+                             init_length_inv=1.0 / init_len[0])
+
+    estimate._mf_spec = {"kind": "bidiag", "num_matvecs": k, "reortho": reortho, "materialize": materialize}
+    return estimate

@@ -327,3 +327,90 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
     estimate.batched = batched
     estimate.blocked = blocked
     return estimate
+
+
+# ---------------------------------------------------------------- products A^T A (bidiag)
+
+
+def dense_funm_product_svd(matfun):
+    """Dense matrix function of ``B^T B`` via the SVD of ``B`` (`funm.py:305-319`)."""
+
+    def dense_funm(matrix, /):
+        import torch
+
+        M = _device.as_device(matrix)
+        _, S, Vt = torch.linalg.svd(M, full_matrices=False)
+        fx = _apply_matfun(matfun, S**2)
+        return Vt.T @ (fx[:, None] * Vt)
+
+    dense_funm._mf_matfun = matfun
+    return dense_funm
+
+
+def product_quadrature_blocked(alphas, betas, init_len, num_probes, matfun):
+    """``init_len^2 * e1^T f(B^T B) e1`` for every probe of a tile (`mf_bidiag_quad`)."""
+    import torch
+
+    lib = _lib.load()
+    k, ld = alphas.shape
+    dt, dev = alphas.dtype, alphas.device
+    ws = _device.workspace(lib.mf_tridiag_quad_workspace_bytes(ld, k))
+    known = _known_fn(matfun) if (not callable(matfun) or _is_hashable(matfun)) else None
+    if known is not None:
+        quad = torch.empty((ld,), dtype=dt, device=dev)
+        _lib.check(lib.mf_bidiag_quad(alphas.data_ptr(), betas.data_ptr(), init_len.data_ptr(),
+                                      _device.mf_dtype(dt), ld, num_probes, k, known[0], known[1],
+                                      quad.data_ptr(), None, None, ws.data_ptr(), ws.numel(),
+                                      _device.stream()))
+        return quad[:num_probes]
+    nodes = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    weights = torch.empty((k, ld), dtype=torch.float64, device=dev)
+    _lib.check(lib.mf_bidiag_quad(alphas.data_ptr(), betas.data_ptr(), init_len.data_ptr(),
+                                  _device.mf_dtype(dt), ld, num_probes, k, _lib.MF_FN_NONE, 0.0, None,
+                                  nodes.data_ptr(), weights.data_ptr(), ws.data_ptr(), ws.numel(),
+                                  _device.stream()))
+    fx = _apply_matfun(matfun, nodes[:, :num_probes].to(dt)).to(torch.float64)
+    q = (fx * weights[:, :num_probes]).sum(dim=0) * init_len[:num_probes].to(torch.float64) ** 2
+    return q.to(dt)
+
+
+def monte_carlo_funm_product(dense_funm, bidiag, /):
+    """Integrand for the trace of a function of ``A^T A`` (`funm.py:275-302`)."""
+    spec = getattr(bidiag, "_mf_spec", None)
+    matfun = getattr(dense_funm, "_mf_matfun", None)
+    fusable = spec is not None and spec.get("kind") == "bidiag" and matfun is not None
+
+    def quadform(matvec, v0, *parameters):
+        import torch
+
+        if not fusable:
+            v = _device.as_device(v0).reshape(-1)
+            length = torch.linalg.vector_norm(v)
+            _, B, *_ = bidiag(matvec, v / length, *parameters)
+            return length**2 * dense_funm(B)[0, 0]
+        if parameters:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        op = ops.require_operator(matvec, "monte_carlo_funm_product")
+        if not isinstance(op, ops.RectOperator):
+            raise TypeError("monte_carlo_funm_product: matvec must be ops.rect(A)")
+        v = _device.as_device(v0, op.dtype).reshape(-1)
+        k = spec["num_matvecs"]
+        if k > min(op.m, op.n) or k < 0:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=min(op.m, op.n), minval=0))
+        alphas, betas, init_len, *_ = decomp.bidiag_blocked(op, v.reshape(-1, 1).contiguous(), k, spec["reortho"])
+        return product_quadrature_blocked(alphas, betas, init_len, 1, matfun)[0]
+
+    quadform._mf_integrand = None if not fusable else {
+        "kind": "product", "num_matvecs": spec["num_matvecs"], "reortho": spec["reortho"], "matfun": matfun}
+    return quadform
+
+
+def monte_carlo_funm_product_logdet(bidiag, /):
+    """Integrand for ``logdet(A^T A)`` (`funm.py:246-255`)."""
+    return monte_carlo_funm_product(dense_funm_product_svd(np.log), bidiag)
+
+
+def monte_carlo_funm_product_schatten_norm(power, bidiag, /):
+    """Integrand for the p-th power of the Schatten-p norm (`funm.py:258-272`):
+    ``f(x) = x^(p/2)`` applied to the eigenvalues of ``A^T A``."""
+    return monte_carlo_funm_product(dense_funm_product_svd(("pow", power / 2)), bidiag)

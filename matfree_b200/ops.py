@@ -162,6 +162,59 @@ class GramOperator(Operator):
                                split_planes=None if self._planes is None else self._planes.data_ptr())
 
 
+class RectOperator(GramOperator):
+    """``v -> A v`` for a rectangular dense ``A (m, n)`` -- the (non-symmetric) matvec the
+    Golub-Kahan bidiagonalisation takes (`matfree/decomp.py:608-750`); the reference obtains
+    ``u -> A^T u`` from it with `jax.vjp` (`decomp.py:703,712`), here both products are one GEMM
+    each on the operator's buffers (`mf_matmat_rect`).  Shares the storage (and, for fp32, the
+    TF32 planes) of the Gram operator over the same matrix."""
+
+    def __call__(self, v, *params):
+        if params:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        v = _device.as_device(v, self.dtype)
+        if v.ndim != 1 or v.shape[0] != self.n:
+            raise ValueError(f"expected a flat vector of length {self.n}, got shape {tuple(v.shape)}")
+        return self.apply_blocked(v.reshape(self.n, 1), trans=False).reshape(self.m)
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    def apply_blocked(self, X, *, trans: bool):
+        """``A @ X`` (``X[n][ld] -> [m][ld]``) or ``A^T @ X`` (``X[m][ld] -> [n][ld]``)."""
+        import torch
+
+        lib = _lib.load()
+        rows_in, rows_out = (self.m, self.n) if trans else (self.n, self.m)
+        k, ld = X.shape
+        assert k == rows_in and X.is_contiguous() and X.dtype == self.dtype
+        W = torch.empty((rows_out, ld), dtype=self.dtype, device=X.device)
+        mfdt = _device.mf_dtype(self.dtype)
+        have = self._planes is not None
+        ws = _device.workspace(lib.mf_matmat_rect_workspace_bytes(self.m, self.n, self.n, int(trans), mfdt,
+                                                                  int(have), ld))
+        _lib.check(lib.mf_matmat_rect(self.A.data_ptr(), self._planes.data_ptr() if have else None,
+                                      self.m, self.n, self.n, int(trans), mfdt, X.data_ptr(),
+                                      W.data_ptr(), ld, ws.data_ptr(), ws.numel(), _device.stream()))
+        return W
+
+    def matmat_blocked(self, X):
+        return self.apply_blocked(X, trans=False)
+
+    def rmatmat_blocked(self, U):
+        return self.apply_blocked(U, trans=True)
+
+    def matmat(self, V):
+        raise TypeError("ops.rect is not square: use apply_blocked")
+
+
+def rect(A) -> RectOperator:
+    """Rectangular dense operator ``v -> A @ v`` (for `decomp.bidiag` and the
+    `funm.monte_carlo_funm_product*` integrands)."""
+    return RectOperator(A)
+
+
 def dense(A) -> DenseOperator:
     """Symmetric dense operator ``v -> A @ v``."""
     return DenseOperator(A)

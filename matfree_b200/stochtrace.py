@@ -183,6 +183,57 @@ def monte_carlo_frobeniusnorm_squared():
 _BLOCK_KINDS = ("diagonal", "trace_and_diagonal", "rownorms_squared", "frobeniusnorm_squared")
 
 
+def _product_values(integrand, sampler, matvec, key, parameters, *, tile=None):
+    """Per-probe values of `funm.monte_carlo_funm_product*` with all probes of a tile advancing
+    together: `mf_probe_gen` (blocked) -> Golub-Kahan on the block (`decomp.bidiag_blocked`) ->
+    `mf_bidiag_quad`.  None if not applicable."""
+    ispec = getattr(integrand, "_mf_integrand", None)
+    sspec = getattr(sampler, "_mf_sampler", None)
+    if (ispec is None or ispec["kind"] != "product" or sspec is None
+            or not isinstance(matvec, ops.RectOperator) or parameters):
+        return None
+    import torch
+
+    from matfree_b200 import decomp
+
+    lib = _lib.load()
+    op = matvec
+    n, P, dt = sspec["n"], sspec["num"], op.dtype
+    if n != op.n:
+        raise ValueError(f"sampler draws vectors of length {n}, operator has {op.n} columns")
+    if sspec["dtype"] != dt:
+        raise TypeError(f"sampler dtype {sspec['dtype']} does not match operator dtype {dt}")
+    k = ispec["num_matvecs"]
+    if k > min(op.m, op.n) or k < 0:
+        raise ValueError(decomp._error_num_matvecs(k, maxval=min(op.m, op.n), minval=0))
+    dev = _device.device()
+    mfdt = _device.mf_dtype(dt)
+    p0, p1, group, world = 0, P, None, 1
+    if _PROBE_GROUP["enabled"]:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            group = _PROBE_GROUP["group"]
+            world = dist.get_world_size(group)
+            p0, p1 = _sharding.shard_range(P, world, dist.get_rank(group))
+    nloc = p1 - p0
+    ld = int(tile) if tile else _device.ld_for(max(nloc, 1), cap=64)
+    V = torch.empty((n, ld), dtype=dt, device=dev)
+    parts = []
+    for t0 in range(p0, p1, ld):
+        npb = min(ld, p1 - t0)
+        _lib.check(lib.mf_probe_gen(V.data_ptr(), mfdt, _lib.MF_LAYOUT_BLOCKED, n, ld, t0, npb,
+                                    int(key[0]), int(key[1]), sspec["kind"], 0, None, _device.stream()))
+        if npb < ld:
+            V[:, npb:] = 1.0  # padding columns: any non-zero vector keeps the recurrence finite
+        alphas, betas, init_len, *_ = decomp.bidiag_blocked(op, V, k, ispec["reortho"])
+        parts.append(_funm.product_quadrature_blocked(alphas, betas, init_len, npb, ispec["matfun"]))
+    vals = torch.cat(parts) if parts else torch.empty((0,), dtype=dt, device=dev)
+    if world > 1:
+        vals = _sharding.gather_shards(vals, P, group)
+    return vals
+
+
 def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None):
     """The Hutchinson integrands that are not a single dot product, probe-blocked: per tile one
     `mf_probe_gen` (blocked layout, bit-identical to the reference's sample array), one block
@@ -274,6 +325,8 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
         return None
     if ispec["kind"] in _BLOCK_KINDS:
         return None  # handled by _hutchinson_block
+    if ispec["kind"] == "product":
+        return _product_values(integrand, sampler, matvec, key, parameters, tile=tile)
     import torch
 
     lib = _lib.load()

@@ -406,6 +406,89 @@ def slq_batched(matmat, V, k, *, reortho="none", matfun=np.log):
 
 
 # --------------------------------------------------------------------------
+# Golub-Kahan bidiagonalisation and functions of A^T A
+# --------------------------------------------------------------------------
+
+
+def bidiag(num_matvecs, /, materialize=True, reortho="full"):
+    """`matfree/decomp.py:608-750`, same operation order; `A` is a dense (nrows, ncols) array
+    (the reference gets the vector-matrix product from `jax.vjp` of the matvec)."""
+
+    def estimate(A, v0):
+        A = np.asarray(A)
+        dt = np.asarray(v0).dtype
+        nrows, ncols = A.shape
+        k = num_matvecs
+        if k > min(nrows, ncols) or k < 0:
+            raise ValueError(_error_num_matvecs(k, maxval=min(nrows, ncols), minval=0))
+        length = np.linalg.norm(v0).astype(dt)
+        v0n = v0 / length                               # :660
+        alphas = np.zeros((k,), dt)
+        betas = np.zeros((k,), dt)
+        Us = np.zeros((k, nrows), dt)
+        Vs = np.zeros((k, ncols), dt)
+        vk = v0n / np.linalg.norm(v0n).astype(dt)       # :697
+        beta = dt.type(0)
+        for i in range(k):
+            Vs[i] = vk
+            betas[i] = beta
+            uk = A @ vk - beta * Us[i - 1]              # :703-704
+            if reortho == "full":
+                uk = uk - Us.T @ (Us @ uk)
+                uk = uk - Us.T @ (Us @ uk)
+            alpha = np.linalg.norm(uk).astype(dt)
+            uk = uk / alpha
+            Us[i] = uk
+            alphas[i] = alpha
+            vk = A.T @ uk - alpha * vk                  # :712-713
+            if reortho == "full":
+                vk = vk - Vs.T @ (Vs @ vk)
+                vk = vk - Vs.T @ (Vs @ vk)
+            beta = np.linalg.norm(vk).astype(dt)
+            vk = vk / beta
+        if materialize:
+            J = np.diag(alphas) + np.diag(betas[1:], 1)
+        else:
+            J = (alphas, betas[1:])
+        return (Us, Vs), J, beta * vk, 1 / length
+
+    return estimate
+
+
+def dense_funm_product_svd(matfun):
+    """`matfree/funm.py:305-319`."""
+
+    def dense_funm(matrix):
+        _, S, Vt = np.linalg.svd(matrix, full_matrices=False)
+        eigvals, eigvecs = S**2, Vt.T
+        return eigvecs @ (matfun(eigvals)[:, None] * eigvecs.T)
+
+    return dense_funm
+
+
+def monte_carlo_funm_product(dense_funm, bidiag_alg, /):
+    """`matfree/funm.py:275-302`; the `matvec` argument is the dense matrix itself."""
+
+    def quadform(A, v0):
+        length = np.linalg.norm(v0).astype(v0.dtype)
+        _, B, *_ = bidiag_alg(A, v0 / length)
+        fA = dense_funm(B)
+        return length**2 * fA[0, 0]
+
+    return quadform
+
+
+def monte_carlo_funm_product_logdet(bidiag_alg, /):
+    """`matfree/funm.py:246-255`."""
+    return monte_carlo_funm_product(dense_funm_product_svd(np.log), bidiag_alg)
+
+
+def monte_carlo_funm_product_schatten_norm(power, bidiag_alg, /):
+    """`matfree/funm.py:258-272`."""
+    return monte_carlo_funm_product(dense_funm_product_svd(lambda x: x ** (power / 2)), bidiag_alg)
+
+
+# --------------------------------------------------------------------------
 # matfree/test_util.py restated (fixtures for the parity tests)
 # --------------------------------------------------------------------------
 

@@ -271,3 +271,40 @@ def test_hutchinson_row_integrands_against_dense_truth():
     signs = ref.sampler_signs(n, num=7, dtype=np.float64)
     got = ref.estimator_monte_carlo(ref.monte_carlo_diagonal(), signs)(lambda v: D @ v, key)
     assert np.array_equal(got, np.arange(1.0, n + 1))
+
+
+# tests/test_decomp/test_bidiag.py:18-46 and :49-78: U, V orthonormal, A V^T = U^T B,
+# A^T U^T = V^T B^T + res e_k^T, 1/|v0|
+@pytest.mark.parametrize("nrows,ncols,k", [(50, 49, 6), (15, 13, 12), (13, 15, 12), (15, 15, 12)])
+def test_bidiag_decomposition_is_satisfied(nrows, ncols, k):
+    if (nrows, ncols) == (50, 49):
+        d = np.arange(49) + 10.0
+        d[4:] = 0.001
+        A = ref.asymmetric_matrix_from_singular_values(d, nrows=nrows, ncols=ncols)
+    else:
+        a = np.arange(0, max(ncols, nrows))
+        A = (1.0 / (1.0 + a[:, None] + a[None, :]))[:nrows, :ncols]
+    v0 = prng.normal(prng.prng_key(1), (ncols,), np.float64)
+    (U, V), B, res, ln = ref.bidiag(k, materialize=True)(A, v0)
+    ref.assert_columns_orthonormal(U.T)
+    ref.assert_columns_orthonormal(V.T)
+    em = np.eye(k)[:, -1]
+    ref.assert_allclose(A @ V.T - U.T @ B, 0.0)
+    ref.assert_allclose(A.T @ U.T - V.T @ B.T - np.outer(res, em), 0.0)
+    ref.assert_allclose(1.0 / np.linalg.norm(v0), ln)
+
+
+# tests/test_funm/test_monte_carlo_funm_product_logdet.py:44-70: exact for full-order bidiag
+def test_logdet_product_exact_for_full_num_matvecs():
+    n = 50
+    A = ref.asymmetric_matrix_from_singular_values(np.sqrt(np.arange(1.0, 1.0 + n)), nrows=n, ncols=n)
+    integrand = ref.monte_carlo_funm_product_logdet(ref.bidiag(n - 1))
+    x = prng.normal(prng.prng_key(1), (n,), np.float64) + 1
+    received = integrand(A, x)
+    w, Q = np.linalg.eigh(A.T @ A)
+    expected = x @ (Q @ np.diag(np.log(w)) @ Q.T) @ x
+    assert np.allclose(received, expected, atol=1e-3, rtol=1e-3)
+    # Schatten norm (test_monte_carlo_funm_product_schatten_norm.py): |A|_p^p = sum sigma^p
+    sch = ref.monte_carlo_funm_product_schatten_norm(3, ref.bidiag(n - 1))(A, x)
+    expected = x @ (Q @ np.diag(w ** 1.5) @ Q.T) @ x
+    assert np.allclose(sch, expected, rtol=1e-6)
