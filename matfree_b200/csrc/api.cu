@@ -390,9 +390,14 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
       return MF_ERR_CUDA;
     }
     if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
-    MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, st));  // :464
-    MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st, nullptr,
-                              b.partial_rows));  // :468
+    if (cgs_fused_supported(Q, 0, i + 1, b.V, dt, n, ld, b.partial_rows)) {
+      // :464 and the dots of :468 in one sweep over the basis
+      MF_TRY(launch_reorth_update_dots(Q, i + 1, b.h, b.V, n, ld, b.partial, b.counter, b.h2, st));
+    } else {
+      MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, nullptr, st));  // :464
+      MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st, nullptr,
+                                b.partial_rows));  // :468
+    }
     const Reduce red_n{b.partial, Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr}};
     MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, &red_n, st));  // :468,471
     length = row(betas, i, ld, dt);
@@ -455,9 +460,14 @@ int32_t lanczos_full_sharded(const Shard& sh, const mf_operator_t* op, const voi
       return MF_ERR_CUDA;
     }
     if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
-    MF_TRY(launch_reorth_update(Qmid, i + 1, b.h, b.V, dt, n, ld, nullptr, st, q_stride));  // :464
-    MF_TRY(launch_reorth_dots(Qmid, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st, nullptr,
-                              b.partial_rows, q_stride, sh.peer));  // :468
+    if (cgs_fused_supported(Qmid, q_stride, i + 1, b.V, dt, n, ld, b.partial_rows)) {
+      MF_TRY(launch_reorth_update_dots(Qmid, i + 1, b.h, b.V, n, ld, b.partial, b.counter, b.h2,
+                                       st, q_stride, sh.peer));  // :464 + dots of :468
+    } else {
+      MF_TRY(launch_reorth_update(Qmid, i + 1, b.h, b.V, dt, n, ld, nullptr, st, q_stride));  // :464
+      MF_TRY(launch_reorth_dots(Qmid, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h2, st,
+                                nullptr, b.partial_rows, q_stride, sh.peer));  // :468
+    }
     const Reduce red_n{b.partial,
                        Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr, sh.peer}};
     MF_TRY(launch_reorth_update(Qmid, i + 1, b.h2, b.V, dt, n, ld, &red_n, st, q_stride));  // :468,471

@@ -8,6 +8,8 @@
 // thread always owns the same probe columns; per-column sums are accumulated in
 // fp64 registers, reduced deterministically inside the CTA and written as one
 // partial row per CTA; `finalize` adds the partial rows in a fixed order.
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace mf {
@@ -310,6 +312,125 @@ reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T*
   if (NORM) cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
 }
 
+// ---------------------------------------------------------------- fused CGS pass (narrow tiles)
+// Second half of the first Gram-Schmidt pass and first half of the second one in ONE sweep over
+// the basis (matfree/decomp.py:464 and :468):   V <- V - sum_j h_j Q_j ;  h'_j = Q_j . V  (new V).
+// The two need the basis in different shapes -- the update wants, per row, all j; the dots want,
+// per j, all rows -- so the tile Q[0..nq)[R rows] is staged ONCE in shared memory (cp.async,
+// double-buffered, one CTA of R threads per SM, ~100 KB per stage) and read twice from there:
+//   phase A: thread t owns row t of the tile: s = sum_j h_j Qs[j][t]; V' = V - s  -> global + smem
+//   phase B: warp w owns the vectors j = w, w + 8, ... and keeps their fp64 sums in registers for
+//            the whole kernel; lane l covers rows l, l + 32, ... of the tile.
+// One sweep over Q instead of two: CGS twice costs 3 sweeps of the basis per Arnoldi step, not 4.
+constexpr int kCgsRows = 256;  // rows (flat elements) per tile = threads per CTA
+constexpr int kCgsMaxNq = 104;  // (nq + 1) * kCgsRows * 4 B per stage, two stages <= 227 KB
+constexpr int kCgsJW = (kCgsMaxNq + 7) / 8;
+
+__device__ __forceinline__ void cgs_cp16(void* smem, const void* gmem, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+}
+
+__global__ void __launch_bounds__(kCgsRows, 1)
+cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
+                       const float* __restrict__ h, float* __restrict__ V, int64_t total, int ld,
+                       double* __restrict__ partial, int64_t partial_stride, Finalize fin) {
+  constexpr int R = kCgsRows, NW = R / 32;
+  extern __shared__ __align__(16) float cgs_smem[];
+  const int stage_floats = (nq + 1) * R;  // nq basis segments + the segment of V
+  const int nq4 = (nq + 3) & ~3;
+  float* vs = cgs_smem + 2 * stage_floats;   // [R] updated V of the current tile
+  float* hs = vs + R;                         // [ld][nq4]: coefficients, transposed and zero-padded
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < nq4 * ld; i += R) {
+    const int c = i / nq4, j = i - c * nq4;
+    hs[i] = j < nq ? h[j * ld + c] : 0.f;
+  }
+
+  const int64_t ntiles = (total + R - 1) / R;
+  auto issue = [&](int buf, int64_t tile) {
+    float* st = cgs_smem + buf * stage_floats;
+    const int64_t base = tile * R;
+    const int chunks = (nq + 1) * (R / 4);
+    for (int c = tid; c < chunks; c += R) {
+      const int j = c / (R / 4), ch = (c - j * (R / 4)) * 4;
+      const int64_t f = base + ch;
+      const float* src = j < nq ? Q + (int64_t)j * q_stride : V;
+      int64_t left = (total - f) * 4;
+      const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+      cgs_cp16(st + j * R + ch, bytes ? (const void*)(src + f) : (const void*)src, bytes);
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  double acc[kCgsJW];
+#pragma unroll
+  for (int jj = 0; jj < kCgsJW; ++jj) acc[jj] = 0.0;
+
+  int64_t tile = blockIdx.x;
+  if (tile < ntiles) issue(0, tile);
+  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    const int buf = it & 1;
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) {
+      issue(buf ^ 1, next);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    const float* Qs = cgs_smem + buf * stage_floats;
+    // phase A: row `tid` of the tile; four coefficients per shared-memory load
+    const int64_t f = tile * R + tid;
+    const float4* hc = reinterpret_cast<const float4*>(hs + (int)(f & (ld - 1)) * nq4);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int j = 0; j < nq4; j += 4) {  // Qs rows nq..nq4-1 are the V segment / the next stage: x 0
+      const float4 hv = hc[j >> 2];
+      s0 += hv.x * Qs[(j + 0) * R + tid];
+      if (j + 1 < nq) s1 += hv.y * Qs[(j + 1) * R + tid];
+      if (j + 2 < nq) s2 += hv.z * Qs[(j + 2) * R + tid];
+      if (j + 3 < nq) s3 += hv.w * Qs[(j + 3) * R + tid];
+    }
+    float v = 0.f;
+    if (f < total) {
+      v = Qs[nq * R + tid] - ((s0 + s1) + (s2 + s3));
+      V[f] = v;
+    }
+    vs[tid] = v;
+    __syncthreads();
+    // phase B: this warp's vectors against the whole tile.  Lane l covers rows 4l..4l+3 and
+    // 128+4l..128+4l+3 (two 16-byte loads per vector); the 8 products of a vector are summed in
+    // fp32 and added to the fp64 accumulator once per tile.
+    const float4 va = reinterpret_cast<const float4*>(vs)[lane];
+    const float4 vb = reinterpret_cast<const float4*>(vs)[32 + lane];
+#pragma unroll
+    for (int jj = 0; jj < kCgsJW; ++jj) {
+      const int jv = warp + jj * NW;
+      if (jv < nq) {
+        const float4 qa = reinterpret_cast<const float4*>(Qs + jv * R)[lane];
+        const float4 qb = reinterpret_cast<const float4*>(Qs + jv * R)[32 + lane];
+        float p0 = qa.x * va.x, p1 = qa.y * va.y, p2 = qa.z * va.z, p3 = qa.w * va.w;
+        p0 += qb.x * vb.x;
+        p1 += qb.y * vb.y;
+        p2 += qb.z * vb.z;
+        p3 += qb.w * vb.w;
+        acc[jj] += (double)((p0 + p1) + (p2 + p3));
+      }
+    }
+    __syncthreads();  // the stage is refilled by the next iteration's issue
+  }
+  // fold all lanes of the warp (ld == 1: every row belongs to the one column); fixed xor tree
+#pragma unroll
+  for (int jj = 0; jj < kCgsJW; ++jj) {
+    const int jv = warp + jj * NW;
+    double sacc = acc[jj];
+    for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+    if (jv < nq && lane == 0)
+      partial[(int64_t)jv * partial_stride + (int64_t)blockIdx.x] = sacc;
+  }
+  finalize_if_last<float>(ld, partial, partial_stride, nq, fin);
+}
+
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
 basis_combine_kernel(const T* __restrict__ Q, int64_t q_stride, int k, const T* __restrict__ coef,
@@ -608,6 +729,49 @@ int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, 
   }
 #undef MF_RU
   return check_launch("reorth_update");
+}
+
+bool cgs_fused_supported(const void* Q, int64_t q_stride, int64_t nq, const void* V, int32_t dtype,
+                         int64_t n, int64_t ld, int64_t partial_rows) {
+  // Opt-in (MF_CGS_FUSED=1): measured on C4 (profiles/r1q_*, r1r_cgs_full.txt) the fused sweep
+  // runs at 3.2 TB/s -- with one 256-thread CTA per SM its two shared-memory phases are
+  // latency-bound (short-scoreboard / wait stalls, 0.29 IPC) and take as long as the two sweeps
+  // they replace (112 ms vs 52 + 57 ms per decomposition), so the two-kernel route stays default.
+  const bool on = getenv("MF_CGS_FUSED") != nullptr;
+  // ld == 1 (a single start vector: BASELINE config 4) -- wider tiles keep the two-kernel route
+  if (!on || dtype != MF_F32 || ld != 1 || nq < 1 || nq > kCgsMaxNq) return false;
+  if (partial_rows < nq) return false;  // one partial row per basis vector
+  if (q_stride <= 0) q_stride = n * ld;
+  if (q_stride % 4 != 0 || !al16(Q) || !al16(V)) return false;
+  return n * ld >= 4 * kCgsRows;  // tiny problems: the plain kernels are launch-bound anyway
+}
+
+int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void* V, int64_t n,
+                                  int64_t ld, double* partial, unsigned int* counter, void* h_out,
+                                  cudaStream_t st, int64_t q_stride, const PeerCtx* peer) {
+  MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
+  const int64_t total = n * ld;
+  if (q_stride <= 0) q_stride = total;
+  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + kCgsRows + (nq + 3) / 4 * 4 * ld) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + kCgsRows + kCgsMaxNq) * 4;
+    if (cudaFuncSetAttribute(cgs_update_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)max_smem) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("cgs_update_dots: shared-memory opt-in failed");
+      return MF_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t ntiles = (total + kCgsRows - 1) / kCgsRows;
+  int grid = num_sms();
+  if (grid > ntiles) grid = (int)ntiles;
+  Finalize fin{counter, 0, h_out, nullptr, nullptr, peer};
+  cgs_update_dots_kernel<<<grid, kCgsRows, smem, st>>>((const float*)Q, q_stride, (int)nq,
+                                                       (const float*)h, (float*)V, total, (int)ld,
+                                                       partial, (int64_t)kMaxPartialCtas * ld, fin);
+  return check_launch("cgs_update_dots");
 }
 
 int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scale,

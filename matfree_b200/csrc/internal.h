@@ -69,6 +69,15 @@ int32_t launch_sums_finalize(const double* sums, int64_t count, int mode, void* 
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
                              int64_t n, int64_t ld, const Reduce* red, cudaStream_t st,
                              int64_t q_stride = 0);
+// Fused CGS pass for narrow fp32 tiles: V <- V - sum_j Q[j] h[j], then h_out[j] = Q[j] . V of
+// the NEW V, in one sweep over the basis (decomp.py:464 + :468).  cgs_fused_supported says
+// whether the shape qualifies (fp32, ld == 1, nq <= 104, one partial row per basis vector).
+bool cgs_fused_supported(const void* Q, int64_t q_stride, int64_t nq, const void* V, int32_t dtype,
+                         int64_t n, int64_t ld, int64_t partial_rows);
+int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void* V, int64_t n,
+                                  int64_t ld, double* partial, unsigned int* counter, void* h_out,
+                                  cudaStream_t st, int64_t q_stride = 0,
+                                  const PeerCtx* peer = nullptr);
 // out[r][c] = scale[c] * sum_j Q[j][r][c] * coeff[j][c]
 int32_t launch_basis_combine(const void* Q, const void* coeffs, const void* scale,
                              int32_t dtype, int64_t n, int64_t ld, int64_t k, void* out,

@@ -1,0 +1,69 @@
+"""Fused CGS pass (`cgs_update_dots_kernel`: V -= Q h and h' = Q^T V in one sweep over the basis,
+narrow fp32 tiles) against the two-kernel route and the oracle.
+
+Reference: the two re-orthogonalisation lines of `_hessenberg_forward_step`,
+matfree/decomp.py:462-468."""
+
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import prng as oprng  # noqa: E402
+from oracle import ref  # noqa: E402
+
+
+def mfb():
+    import matfree_b200
+
+    return matfree_b200
+
+
+# (shape, ld, k, fused expected): the fused kernel takes single start vectors (ld = 1) whose
+# length is a multiple of 4 (16-byte cp.async chunks), at most 104 basis vectors
+@pytest.mark.parametrize("shape,ld,k,fused", [((40, 40), 1, 30, True), ((64, 64), 1, 100, True),
+                                              ((36, 57), 1, 104, True), ((61, 68), 1, 40, True),
+                                              ((37, 41), 1, 24, False), ((50, 30), 8, 20, False)])
+def test_fused_cgs_matches_two_kernel_route_and_oracle(shape, ld, k, fused):
+    import scipy.sparse as sp
+
+    from matfree_b200 import workloads
+
+    m = mfb()
+    n = shape[0] * shape[1]
+    ip, ix, d = workloads.laplacian_csr(shape, shift=1.0)
+    op = m.ops.csr(ip, ix, d)
+    V = torch.as_tensor(oprng.normal(oprng.prng_key(4), (n, ld), np.float32)).cuda()
+    lib_launches = __import__("matfree_b200._lib", fromlist=["load"]).load().mf_launch_count
+    os.environ.pop("MF_CGS_FUSED", None)
+    l0 = lib_launches()
+    a2, b2, len2, Q2, r2 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
+    torch.cuda.synchronize()
+    plain_launches = lib_launches() - l0
+    os.environ["MF_CGS_FUSED"] = "1"   # the fused sweep is opt-in (see blockvec.cu)
+    try:
+        l0 = lib_launches()
+        a1, b1, len1, Q1, r1 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
+        torch.cuda.synchronize()
+        fused_launches = lib_launches() - l0
+    finally:
+        del os.environ["MF_CGS_FUSED"]
+    assert (fused_launches < plain_launches) == fused, (fused_launches, plain_launches)
+    tol = 3e-5
+    assert np.allclose(a1.cpu(), a2.cpu(), rtol=tol, atol=tol)
+    assert np.allclose(b1.cpu(), b2.cpu(), rtol=tol, atol=tol)
+    assert np.allclose(Q1.cpu(), Q2.cpu(), atol=2e-4)
+    # the basis is orthonormal per column of the tile (decomp.py:462-468 is what guarantees it)
+    Qc = Q1.cpu().numpy().astype(np.float64)
+    for c in range(min(ld, 3)):
+        G = Qc[:, :, c] @ Qc[:, :, c].T
+        assert np.abs(G - np.eye(k)).max() < 5e-5, (c, np.abs(G - np.eye(k)).max())
+    # oracle on the first column
+    A = sp.csr_matrix((d.numpy(), ix.numpy(), ip.numpy()), shape=(n, n))
+    od, oe, _ = ref.lanczos_full_batched(lambda X: (A @ X.T).T, V[:, :1].T.cpu().numpy(), k)
+    kk = min(k, 20)  # later coefficients amplify rounding differences (H3 in SURVEY.md)
+    assert np.allclose(a1[:kk, 0].cpu().numpy(), od[0][:kk], rtol=2e-4, atol=2e-4)
