@@ -488,6 +488,28 @@ def monte_carlo_funm_product_schatten_norm(power, bidiag_alg, /):
     return monte_carlo_funm_product(dense_funm_product_svd(lambda x: x ** (power / 2)), bidiag_alg)
 
 
+def eigh_partial(tridiag_alg):
+    """`matfree/eig.py:69-104`: Ritz values / vectors from a tridiagonalisation."""
+
+    def eigh(Av, v0):
+        Q, H, *_ = tridiag_alg(Av, v0)
+        vals, vecs = np.linalg.eigh(H)
+        return vals, vecs.T @ Q
+
+    return eigh
+
+
+def svd_partial(bidiag_alg):
+    """`matfree/eig.py:22-66`."""
+
+    def svd(A, v0):
+        (u, v), B, *_ = bidiag_alg(A, v0)
+        U, S, Vt = np.linalg.svd(B, full_matrices=False)
+        return U.T @ u, S, Vt @ v
+
+    return svd
+
+
 # --------------------------------------------------------------------------
 # matfree/test_util.py restated (fixtures for the parity tests)
 # --------------------------------------------------------------------------
