@@ -144,3 +144,104 @@ def test_c5_scaled_powerlaw_expm_action():
     ofun = ref.funm_lanczos_sym(ref.dense_funm_sym_eigh(lambda x: np.exp(-t * x)), ref.tridiag_sym(k, reortho="none"))
     L32 = L.astype(np.float32)
     assert np.allclose(one, ofun(lambda x: L32 @ x, V[3]), rtol=1e-4, atol=2e-5)
+
+
+def test_c2_full_size_subset_parity_and_properties():
+    """BASELINE config 2 at its FULL size (2-D 5-point Laplacian 4096^2 = 16.7M rows, depth 30):
+    the reference cannot even allocate this, so parity is asserted per probe on a
+    probe SUBSET against the oracle's C port (counter-based PRNG: probe p is the same numbers
+    whatever the batch), plus size-independent properties: Rademacher |v| = sqrt(n) exactly,
+    tile invariance (probes 256..259 evaluated alone == inside a 512-probe run), the estimate
+    within 4 sem of the closed-form log-determinant, Hutchinson trace within 4 sem of n(4+sigma)."""
+    import torch
+
+    from matfree_b200 import workloads
+    from oracle import port
+
+    m = mfb()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~75 GB of free device memory")
+    shape = (4096, 4096)
+    n = shape[0] * shape[1]
+    k = 30
+    ip, ix, d = workloads.laplacian_csr(shape, shift=1.0, device="cuda")
+    op = m.ops.csr(ip, ix, d)
+    key = m.prng.prng_key(1)
+    integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+    P = 512
+    sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1), (n,)), num=P)
+    plain = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+    quad, alphas, betas, lens = plain.per_probe(op, key, return_coeffs=True)
+    quad = quad.cpu().numpy()
+    assert np.all(lens.cpu().numpy()[:, :256] == np.float32(4096.0))
+    # (1) per-probe parity on a subset, against the OpenMP C restatement of the reference
+    ipc, ixc, dc = ip.cpu().numpy(), ix.cpu().numpy(), d.cpu().numpy()
+    for p0, num in ((0, 2), (300, 2)):
+        oq, oal, obe = port.csr_logdet_quadforms(ipc, ixc, dc, oprng.prng_key(1), p0, num, k, return_coeffs=True)
+        assert np.max(np.abs(quad[p0:p0 + num] - oq) / np.abs(oq)) <= 1e-5, (p0, quad[p0:p0 + num], oq)
+        # Ritz values (not raw alphas, SURVEY.md H3) within 1e-5
+        for j in range(num):
+            t, c = divmod(p0 + j, 256)
+            a = alphas[t, :, c].double().cpu().numpy()
+            b = betas[t, : k - 1, c].double().cpu().numpy()
+            theta = np.linalg.eigvalsh(np.diag(a) + np.diag(b, 1) + np.diag(b, -1))
+            otheta = np.linalg.eigvalsh(np.diag(oal[j].astype(np.float64)) + np.diag(obe[j, : k - 1].astype(np.float64), 1)
+                                        + np.diag(obe[j, : k - 1].astype(np.float64), -1))
+            assert np.max(np.abs(theta - otheta) / np.abs(otheta)) <= 1e-5
+    # (2) tile invariance: probes 0..127 through 128-wide tiles give the same bits as inside the
+    # 256-wide tiles of the run above
+    sub = m.stochtrace.estimator_monte_carlo(
+        integrand, m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1), (n,)), num=128))
+    q128 = sub.per_probe(op, key, tile=128).cpu().numpy()
+    assert np.array_equal(q128, quad[:128])
+    # (3) the estimate against the closed form
+    mean, sem = quad.astype(np.float64).mean(), quad.astype(np.float64).std() / np.sqrt(P)
+    want = workloads.laplacian_logdet(shape, 1.0)
+    assert abs(mean - want) <= 4 * sem + 1e-5 * abs(want), (mean, want, sem)
+    # (4) Hutchinson trace (exact value n * (4 + sigma))
+    tr = m.stochtrace.estimator_monte_carlo_mean_and_sem(m.stochtrace.monte_carlo_trace(), sampler)
+    tmean, tsem = tr(op, key)
+    assert abs(float(tmean) - 5.0 * n) <= 4 * float(tsem) + 1e-5 * n
+
+
+def test_c4_full_size_properties_one_gpu():
+    """BASELINE config 4 at its FULL size on one GPU (3-D 7-point Laplacian 256^3, depth 100, full
+    re-orthogonalisation, start vector = Rademacher probe 0 of PRNGKey(1); the 8-GPU row-sharded
+    run is covered by tests/test_gpu_multi.py at reduced size and by tools/bench_c4.py):
+    size-independent properties of `decomp.py:426-477` -- the three-term identity
+    A q_i = b_{i-1} q_{i-1} + a_i q_i + b_i q_{i+1} on sampled columns, orthonormality of sampled
+    basis vectors (what CGS twice buys), Ritz values inside the closed-form spectrum with the
+    extreme ones converged, 1/|v0| = 1/sqrt(n) exactly."""
+    import torch
+
+    from matfree_b200 import workloads
+
+    m = mfb()
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~20 GB of free device memory")
+    g, k = 256, 100
+    n = g ** 3
+    ip, ix, d = workloads.laplacian_csr((g, g, g), shift=1.0, device="cuda")
+    op = m.ops.csr(ip, ix, d)
+    del ix
+    v = m.prng.rademacher(m.prng.prng_key(1), shape=(n,), dtype=np.float32)
+    Q, (diag, off), res, c = m.decomp.tridiag_sym(k, reortho="full", materialize=False)(op, v)
+    assert Q.shape == (k, n) and float(c) == 1.0 / 4096.0
+    a = diag.double().cpu().numpy()
+    b = off.double().cpu().numpy()
+    theta = np.linalg.eigvalsh(np.diag(a) + np.diag(b, 1) + np.diag(b, -1))
+    lam = 2.0 - 2.0 * np.cos(np.arange(1, g + 1) * np.pi / (g + 1))
+    lo, hi = 3 * lam.min() + 1.0, 3 * lam.max() + 1.0
+    assert theta.min() >= lo - 1e-4 and theta.max() <= hi + 1e-4
+    assert theta.min() - lo < 0.01 and hi - theta.max() < 0.01       # extreme Ritz values converge first
+    for i in (0, 37, 98):
+        Aq = op(Q[i]).double()
+        want = a[i] * Q[i].double() + b[i] * Q[i + 1].double()
+        if i > 0:
+            want += b[i - 1] * Q[i - 1].double()
+        assert float((Aq - want).norm()) <= 2e-5 * 13.0, i           # |A| <= 13
+    idx = [0, 1, 50, 98, 99]
+    G = (Q[idx].double() @ Q[idx].double().T).cpu().numpy()
+    assert np.abs(G - np.eye(len(idx))).max() < 1e-5
