@@ -195,6 +195,18 @@ int32_t mf_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int64_t 
                    int32_t reortho, void* alphas, void* betas, void* init_len, void* Q,
                    void* residual, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* decomp.hessenberg (matfree/decomp.py:351-477): Arnoldi factorisation A Q^T ~ Q^T H of an
+ * ARBITRARY square operator on a block of start vectors -- the loop of mf_lanczos(reortho=FULL)
+ * keeping the whole upper-Hessenberg matrix instead of its symmetrised tridiagonal part.
+ *   H   out: [k][k][ld], H[r][i][c] (column i = first-pass coefficients Q^T A q_i, the norm of
+ *            the orthogonalised vector below the diagonal), zero elsewhere
+ *   reortho: MF_REORTHO_NONE = one Gram-Schmidt pass, MF_REORTHO_FULL = two (decomp.py:467-468)
+ *   Q   out: [k][n][ld] basis;  residual out (optional): the un-normalised last vector */
+int64_t mf_hessenberg_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k);
+int32_t mf_hessenberg(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
+                      int32_t reortho, void* H, void* init_len, void* Q, void* residual,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Building blocks of a ROW-SHARDED decomposition (operators too large for one GPU, or
  * BASELINE config 4): the same kernels mf_lanczos chains, one call each, with every
  * reduction stopping at THIS device's fp64 partial sums so the driver can all-reduce

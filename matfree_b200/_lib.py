@@ -76,6 +76,9 @@ SIGNATURES = {
     "mf_lanczos_workspace_bytes": (c_int64, [_OP, c_int64, c_int64, c_int32, c_int32]),
     "mf_lanczos": (c_int32, [_OP, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mf_hessenberg_workspace_bytes": (c_int64, [_OP, c_int64, c_int64]),
+    "mf_hessenberg": (c_int32, [_OP, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "mf_blockvec_workspace_bytes": (c_int64, [c_int64, c_int64]),
     "mf_block_dot": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p,
                                c_int64, c_void_p]),

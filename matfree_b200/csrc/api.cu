@@ -365,9 +365,18 @@ int32_t lanczos_none(const mf_operator_t* op, void* V0, bool v0_owned, bool have
 
 // Arnoldi with classical Gram-Schmidt applied twice (matfree/decomp.py:426-477)
 // and T = (H + H^T)/2 (decomp.py:133-135), on a probe block.
+// Hess (optional): the public Arnoldi factorisation (decomp.hessenberg, decomp.py:351-477) on
+// the same loop: H[r][i][ld] receives column i = the first-pass coefficients h (+ the norm below
+// the diagonal); second_pass = false is the reference's reortho="none" (one CGS pass).
+struct HessOut {
+  void* H;           // [k][k][ld], zeroed by the caller
+  bool second_pass;
+};
+
 int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int64_t ld,
                      int64_t k, void* alphas, void* betas, void* init_len, void* Q,
-                     void* residual, const LanczosBufs& b, cudaStream_t st) {
+                     void* residual, const LanczosBufs& b, cudaStream_t st,
+                     const HessOut* hess = nullptr) {
   const int32_t dt = op->dtype;
   const int64_t n = op->n;
   const int64_t es = (int64_t)dtype_size(dt);
@@ -389,7 +398,30 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
       set_error("alpha copy failed");
       return MF_ERR_CUDA;
     }
-    if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
+    if (hess != nullptr) {
+      // H[0..i][i] = h (decomp.py:463,474-475)
+      if (cudaMemcpy2DAsync((char*)hess->H + i * ld * es, (size_t)(k * ld * es), b.h,
+                            (size_t)(ld * es), (size_t)(ld * es), (size_t)(i + 1),
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+        set_error("hessenberg: copy of column %lld failed", (long long)i);
+        return MF_ERR_CUDA;
+      }
+      if (!hess->second_pass) {
+        const Reduce red_1{b.partial,
+                           Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr}};
+        MF_TRY(launch_reorth_update(Q, i + 1, b.h, b.V, dt, n, ld, &red_1, st));  // :464,471
+        length = row(betas, i, ld, dt);
+        if (i + 1 < k &&
+            cudaMemcpyAsync((char*)hess->H + ((i + 1) * k + i) * ld * es, length, ld * es,
+                            cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+          set_error("hessenberg: copy of the subdiagonal failed");
+          return MF_ERR_CUDA;
+        }
+        continue;
+      }
+    } else if (i > 0) {
+      MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
+    }
     if (cgs_fused_supported(Q, 0, i + 1, b.V, dt, n, ld, b.partial_rows)) {
       // :464 and the dots of :468 in one sweep over the basis
       MF_TRY(launch_reorth_update_dots(Q, i + 1, b.h, b.V, n, ld, b.partial, b.counter, b.h2, st));
@@ -401,6 +433,12 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     const Reduce red_n{b.partial, Finalize{b.counter, 1, row(betas, i, ld, dt), nullptr, nullptr}};
     MF_TRY(launch_reorth_update(Q, i + 1, b.h2, b.V, dt, n, ld, &red_n, st));  // :468,471
     length = row(betas, i, ld, dt);
+    if (hess != nullptr && i + 1 < k &&
+        cudaMemcpyAsync((char*)hess->H + ((i + 1) * k + i) * ld * es, length, ld * es,
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("hessenberg: copy of the subdiagonal failed");
+      return MF_ERR_CUDA;
+    }
   }
   if (residual != nullptr) {
     const void* src = k > 0 ? b.V : V0;
@@ -829,6 +867,44 @@ int32_t mf_lanczos_sharded(const mf_comm_t* comm, const mf_operator_t* op,
     return lanczos_none_sharded(sh, op, V0, ld, k, want_Q != 0, alphas, betas, init_len, residual,
                                 b, st);
   return lanczos_full_sharded(sh, op, V0, ld, k, alphas, betas, init_len, residual, b, st);
+}
+
+int32_t mf_hessenberg(const mf_operator_t* op, const void* V0, int64_t ld, int64_t k,
+                      int32_t reortho, void* H, void* init_len, void* Q, void* residual,
+                      void* workspace, int64_t workspace_bytes, void* stream) {
+  MF_TRY(check_lanczos_args(op, ld, k, reortho));
+  if (V0 == nullptr || init_len == nullptr || (k > 0 && (H == nullptr || Q == nullptr))) {
+    set_error("hessenberg: V0, init_len, H and Q must be non-null");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  Arena a(workspace, workspace_bytes, false);
+  LanczosBufs b;
+  MF_TRY(carve_lanczos(a, op, ld, k, MF_REORTHO_FULL, &b));
+  // scratch rows for the norms (the symmetric driver's alphas / betas): after the Lanczos buffers
+  const int64_t es = (int64_t)dtype_size(op->dtype);
+  void* al = a.take((k + 1) * ld * es);
+  void* be = a.take((k + 1) * ld * es);
+  if (a.used > a.size) {
+    set_error("workspace too small: need %lld bytes, have %lld", (long long)a.used,
+              (long long)a.size);
+    return MF_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  MF_TRY(zero_counter(b, st));
+  if (k > 0 && cudaMemsetAsync(H, 0, (size_t)(k * k * ld * es), st) != cudaSuccess) {
+    set_error("hessenberg: memset failed");
+    return MF_ERR_CUDA;
+  }
+  const HessOut hess{H, reortho == MF_REORTHO_FULL};
+  return lanczos_full(op, V0, false, ld, k, al, be, init_len, Q, residual, b, st, &hess);
+}
+
+int64_t mf_hessenberg_workspace_bytes(const mf_operator_t* op, int64_t ld, int64_t k) {
+  if (check_lanczos_args(op, ld, k, MF_REORTHO_FULL) != MF_OK) return -1;
+  Arena a(nullptr, 0, true);
+  LanczosBufs b;
+  carve_lanczos(a, op, ld, k, MF_REORTHO_FULL, &b);
+  return a.used + 2 * (k + 1) * ld * (int64_t)dtype_size(op->dtype) + 1024;
 }
 
 int64_t mf_tridiag_quad_workspace_bytes(int64_t ld, int64_t k) {

@@ -256,3 +256,43 @@ def bidiag(num_matvecs: int, /, materialize: bool = True, reortho: str = "full")
 
     estimate._mf_spec = {"kind": "bidiag", "num_matvecs": k, "reortho": reortho, "materialize": materialize}
     return estimate
+
+
+def hessenberg(num_matvecs, /, *, reortho: str, custom_vjp: bool = True, reortho_vjp: str = "match"):
+    """Construct a Hessenberg factorisation via the Arnoldi iteration (`matfree/decomp.py:351-477`):
+    ``A Q^T ~ Q^T H`` for an arbitrary square operator.  `custom_vjp` / `reortho_vjp` are accepted
+    for signature compatibility (gradients are out of scope)."""
+    del custom_vjp, reortho_vjp
+    if reortho not in ("none", "full"):
+        raise TypeError(f"Unexpected input for {reortho}: either of {['none', 'full']} expected.")  # :375-378
+    k = int(num_matvecs)
+
+    def estimate(matvec, v, *params):
+        import torch
+
+        if params:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        op = ops.require_operator(matvec, "hessenberg")
+        lib = _lib.load()
+        vec = _device.as_device(v, op.dtype).reshape(-1)
+        n = vec.shape[0]
+        if k < 0 or k > n:
+            raise ValueError(_error_num_matvecs(k, maxval=n, minval=0))
+        if n != op.n:
+            raise ValueError(f"vector has length {n}, operator dimension is {op.n}")
+        dt, dev = op.dtype, vec.device
+        st = op._struct()
+        ws = _device.workspace(lib.mf_hessenberg_workspace_bytes(ctypes.byref(st), 1, k))
+        H = torch.zeros((k, k, 1), dtype=dt, device=dev)
+        Q = torch.zeros((max(k, 1), n, 1), dtype=dt, device=dev)
+        init_len = torch.empty((1,), dtype=dt, device=dev)
+        residual = torch.empty((n, 1), dtype=dt, device=dev)
+        rflag = _lib.MF_REORTHO_FULL if reortho == "full" else _lib.MF_REORTHO_NONE
+        _lib.check(lib.mf_hessenberg(ctypes.byref(st), vec.data_ptr(), 1, k, rflag, H.data_ptr(),
+                                     init_len.data_ptr(), Q.data_ptr(), residual.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _device.stream()))
+        return _DecompResult(Q_tall=Q[:k, :, 0], J_small=H[:, :, 0], residual=residual[:, 0],
+                             init_length_inv=1.0 / init_len[0])
+
+    estimate._mf_spec = {"kind": "hessenberg", "num_matvecs": k, "reortho": reortho}
+    return estimate

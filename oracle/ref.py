@@ -107,7 +107,7 @@ def _tridiag_reortho_none(num_matvecs, *, materialize):
 # --------------------------------------------------------------------------
 
 
-def _hessenberg_forward(matvec, num_matvecs, v):
+def _hessenberg_forward(matvec, num_matvecs, v, reortho="full"):
     """`matfree/decomp.py:426-477`."""
     if num_matvecs < 0 or num_matvecs > len(v):
         raise ValueError(_error_num_matvecs(num_matvecs, maxval=len(v), minval=0))
@@ -124,7 +124,8 @@ def _hessenberg_forward(matvec, num_matvecs, v):
         v = matvec(v)  # :460
         h = Q.T @ v  # :463
         v = v - Q @ h  # :464
-        v = v - Q @ (Q.T @ v)  # :467-468 (h NOT updated)
+        if reortho != "none":
+            v = v - Q @ (Q.T @ v)  # :467-468 (h NOT updated)
         length = np.sqrt(np.inner(v, v)).astype(dt)  # :471
         if i + 1 < k:  # :474 (out-of-bounds write is dropped by JAX)
             h[i + 1] = length
@@ -486,6 +487,18 @@ def monte_carlo_funm_product_logdet(bidiag_alg, /):
 def monte_carlo_funm_product_schatten_norm(power, bidiag_alg, /):
     """`matfree/funm.py:258-272`."""
     return monte_carlo_funm_product(dense_funm_product_svd(lambda x: x ** (power / 2)), bidiag_alg)
+
+
+def hessenberg(num_matvecs, /, *, reortho):
+    """`matfree/decomp.py:351-477` (forward pass): returns ``(Q (k, n), H, residual, 1/|v|)``."""
+    if reortho not in ("none", "full"):
+        raise TypeError(f"Unexpected input for {reortho}: either of {['none', 'full']} expected.")
+
+    def estimate(matvec, v):
+        Q, H, r, c = _hessenberg_forward(matvec, num_matvecs, np.asarray(v), reortho=reortho)
+        return Q.T, H, r, c
+
+    return estimate
 
 
 def eigh_partial(tridiag_alg):

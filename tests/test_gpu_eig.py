@@ -64,3 +64,39 @@ def test_svd_partial_equal_to_linalg_svd(dtype):
     tol = 2e-4 if dtype == np.float32 else 1e-9
     assert np.allclose(np.sort(s), np.sort(d), rtol=tol)
     assert np.abs(ut.T @ np.diag(s) @ vt - A).max() < tol * 10 * d.max()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("n,k", [(12, 7), (300, 24), (64, 64)])
+def test_hessenberg_decomposition_nonsymmetric(dtype, reortho, n, k):
+    """decomp.hessenberg on a NON-symmetric dense operator: A Q^T = Q^T H + r e_k^T, orthonormal Q,
+    upper-Hessenberg H, and the same H as the oracle (tests/test_decomp/test_hessenberg.py)."""
+    m = mfb()
+    A = (oprng.normal(oprng.prng_key(1), (n, n), dtype) / np.sqrt(n)).astype(dtype)
+    v = oprng.normal(oprng.prng_key(2), (n,), dtype)
+    Q, H, r, c = m.decomp.hessenberg(k, reortho=reortho)(m.ops.dense(A), v)
+    Q, H, r = (x.cpu().numpy().astype(np.float64) for x in (Q, H, r))
+    assert Q.shape == (k, n) and H.shape == (k, k)
+    tol = 2e-5 if dtype == np.float32 else 1e-11
+    if reortho == "full" or k < 30:
+        assert np.abs(Q @ Q.T - np.eye(k)).max() < 20 * tol
+    assert np.abs(np.tril(H, -2)).max() == 0.0
+    ek = np.eye(k)[:, -1]
+    Ad = A.astype(np.float64)
+    assert np.abs(Ad @ Q.T - Q.T @ H - np.outer(r, ek)).max() < 20 * tol
+    assert np.allclose(float(c), 1 / np.linalg.norm(v.astype(np.float64)), rtol=1e-6)
+    if k <= 24:
+        oQ, oH, orr, oc = ref.hessenberg(k, reortho=reortho)(lambda x: Ad @ x, v.astype(np.float64))
+        assert np.abs(H - oH).max() < 200 * tol
+
+
+def test_eigh_partial_accepts_hessenberg():
+    """tests/test_eig/test_eigh_partial.py:8-22 passes `decomp.hessenberg` to `eigh_partial`."""
+    m = mfb()
+    nrows = 10
+    A = ref.hermitian_matrix_from_eigenvalues(np.arange(1.0, 1.0 + nrows), oprng.prng_key(1), dtype=np.float64)
+    vals, vecs = m.eig.eigh_partial(m.decomp.hessenberg(nrows, reortho="full"))(m.ops.dense(A), np.ones(nrows))
+    assert np.allclose(vals.cpu().numpy(), np.arange(1.0, 1.0 + nrows), rtol=1e-8)
+    with pytest.raises(TypeError, match="Unexpected input"):
+        m.decomp.hessenberg(3, reortho="partial")

@@ -308,3 +308,18 @@ def test_logdet_product_exact_for_full_num_matvecs():
     sch = ref.monte_carlo_funm_product_schatten_norm(3, ref.bidiag(n - 1))(A, x)
     expected = x @ (Q @ np.diag(w ** 1.5) @ Q.T) @ x
     assert np.allclose(sch, expected, rtol=1e-6)
+
+
+# tests/test_decomp/test_hessenberg.py: A Q^T = Q^T H + r e_k^T, Q orthonormal, H upper Hessenberg
+@pytest.mark.parametrize("reortho", ["full", "none"])
+def test_hessenberg_decomposition_is_satisfied(reortho):
+    n, k = 12, 7
+    A = prng.normal(prng.prng_key(1), (n, n), np.float64)  # NOT symmetric
+    v = prng.normal(prng.prng_key(2), (n,), np.float64)
+    Q, H, r, c = ref.hessenberg(k, reortho=reortho)(lambda x: A @ x, v)
+    assert Q.shape == (k, n) and H.shape == (k, k)
+    assert np.allclose(Q @ Q.T, np.eye(k), atol=1e-10)
+    assert np.allclose(np.tril(H, -2), 0.0)
+    ek = np.eye(k)[:, -1]
+    assert np.allclose(A @ Q.T, Q.T @ H + np.outer(r, ek), atol=1e-9)
+    assert np.allclose(c, 1 / np.linalg.norm(v))
