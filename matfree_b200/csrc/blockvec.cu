@@ -322,37 +322,37 @@ reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T*
 //   phase B: warp w owns the vectors j = w, w + 8, ... and keeps their fp64 sums in registers for
 //            the whole kernel; lane l covers rows l, l + 32, ... of the tile.
 // One sweep over Q instead of two: CGS twice costs 3 sweeps of the basis per Arnoldi step, not 4.
-constexpr int kCgsRows = 256;  // rows (flat elements) per tile = threads per CTA
-constexpr int kCgsMaxNq = 104;  // (nq + 1) * kCgsRows * 4 B per stage, two stages <= 227 KB
-constexpr int kCgsJW = (kCgsMaxNq + 7) / 8;
+constexpr int kCgsRows = 256;     // rows (flat elements) per tile
+constexpr int kCgsThreads = 512;  // 16 warps (8 left the two shared-memory phases latency-bound; 32 are no faster)
+constexpr int kCgsMaxNq = 104;    // (nq + 1) * kCgsRows * 4 B per stage, two stages <= 227 KB
+constexpr int kCgsJW = (kCgsMaxNq + kCgsThreads / 32 - 1) / (kCgsThreads / 32);
 
 __device__ __forceinline__ void cgs_cp16(void* smem, const void* gmem, int bytes) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
 }
 
-__global__ void __launch_bounds__(kCgsRows, 1)
+__global__ void __launch_bounds__(kCgsThreads, 1)
 cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
                        const float* __restrict__ h, float* __restrict__ V, int64_t total, int ld,
                        double* __restrict__ partial, int64_t partial_stride, Finalize fin) {
-  constexpr int R = kCgsRows, NW = R / 32;
+  constexpr int R = kCgsRows, NT = kCgsThreads, NW = NT / 32;
   extern __shared__ __align__(16) float cgs_smem[];
   const int stage_floats = (nq + 1) * R;  // nq basis segments + the segment of V
-  const int nq4 = (nq + 3) & ~3;
+  constexpr int G = NT / R;                   // threads per row in phase A
+  const int nqg = (nq + 4 * G - 1) / (4 * G) * (4 * G);  // G parts of whole float4 groups
   float* vs = cgs_smem + 2 * stage_floats;   // [R] updated V of the current tile
-  float* hs = vs + R;                         // [ld][nq4]: coefficients, transposed and zero-padded
+  float* sp = vs + R;                         // [G - 1][R] partial sums of the other parts of the j range
+  float* hs = sp + (G - 1) * R;               // [nqg]: coefficients, zero-padded (ld == 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < nq4 * ld; i += R) {
-    const int c = i / nq4, j = i - c * nq4;
-    hs[i] = j < nq ? h[j * ld + c] : 0.f;
-  }
+  for (int i = tid; i < nqg; i += NT) hs[i] = i < nq ? h[i] : 0.f;
 
   const int64_t ntiles = (total + R - 1) / R;
   auto issue = [&](int buf, int64_t tile) {
     float* st = cgs_smem + buf * stage_floats;
     const int64_t base = tile * R;
     const int chunks = (nq + 1) * (R / 4);
-    for (int c = tid; c < chunks; c += R) {
+    for (int c = tid; c < chunks; c += NT) {
       const int j = c / (R / 4), ch = (c - j * (R / 4)) * 4;
       const int64_t f = base + ch;
       const float* src = j < nq ? Q + (int64_t)j * q_stride : V;
@@ -380,23 +380,36 @@ cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
     }
     __syncthreads();
     const float* Qs = cgs_smem + buf * stage_floats;
-    // phase A: row `tid` of the tile; four coefficients per shared-memory load
-    const int64_t f = tile * R + tid;
-    const float4* hc = reinterpret_cast<const float4*>(hs + (int)(f & (ld - 1)) * nq4);
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    for (int j = 0; j < nq4; j += 4) {  // Qs rows nq..nq4-1 are the V segment / the next stage: x 0
-      const float4 hv = hc[j >> 2];
-      s0 += hv.x * Qs[(j + 0) * R + tid];
-      if (j + 1 < nq) s1 += hv.y * Qs[(j + 1) * R + tid];
-      if (j + 2 < nq) s2 += hv.z * Qs[(j + 2) * R + tid];
-      if (j + 3 < nq) s3 += hv.w * Qs[(j + 3) * R + tid];
+    // phase A: G threads per row, each over one part of the basis vectors (four coefficients
+    // per shared-memory load); parts 1..G-1 park their sums in sp
+    {
+      const int rowA = tid & (R - 1), half = tid / R;
+      const int jbeg = half * (nqg / G), jend = jbeg + nqg / G;
+      const float4* hc = reinterpret_cast<const float4*>(hs);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int j = jbeg; j < jend; j += 4) {
+        const float4 hv = hc[j >> 2];
+        if (j + 0 < nq) s0 += hv.x * Qs[(j + 0) * R + rowA];
+        if (j + 1 < nq) s1 += hv.y * Qs[(j + 1) * R + rowA];
+        if (j + 2 < nq) s2 += hv.z * Qs[(j + 2) * R + rowA];
+        if (j + 3 < nq) s3 += hv.w * Qs[(j + 3) * R + rowA];
+      }
+      const float sA = (s0 + s1) + (s2 + s3);
+      if (half > 0) sp[(half - 1) * R + rowA] = sA;
+      __syncthreads();
+      if (half == 0) {
+        const int64_t f = tile * R + rowA;
+        float v = 0.f;
+        if (f < total) {
+          float sall = sA;
+#pragma unroll
+          for (int g = 1; g < G; ++g) sall += sp[(g - 1) * R + rowA];
+          v = Qs[nq * R + rowA] - sall;
+          V[f] = v;
+        }
+        vs[rowA] = v;
+      }
     }
-    float v = 0.f;
-    if (f < total) {
-      v = Qs[nq * R + tid] - ((s0 + s1) + (s2 + s3));
-      V[f] = v;
-    }
-    vs[tid] = v;
     __syncthreads();
     // phase B: this warp's vectors against the whole tile.  Lane l covers rows 4l..4l+3 and
     // 128+4l..128+4l+3 (two 16-byte loads per vector); the 8 products of a vector are summed in
@@ -733,11 +746,12 @@ int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, 
 
 bool cgs_fused_supported(const void* Q, int64_t q_stride, int64_t nq, const void* V, int32_t dtype,
                          int64_t n, int64_t ld, int64_t partial_rows) {
-  // Opt-in (MF_CGS_FUSED=1): measured on C4 (profiles/r1q_*, r1r_cgs_full.txt) the fused sweep
-  // runs at 3.2 TB/s -- with one 256-thread CTA per SM its two shared-memory phases are
-  // latency-bound (short-scoreboard / wait stalls, 0.29 IPC) and take as long as the two sweeps
-  // they replace (112 ms vs 52 + 57 ms per decomposition), so the two-kernel route stays default.
-  const bool on = getenv("MF_CGS_FUSED") != nullptr;
+  // Measured on C4 (profiles/r1q_*, r1r_cgs_full.txt, r1v_*): with 8 warps per SM the two
+  // shared-memory phases were latency-bound and the fused sweep was no faster than the two sweeps
+  // it replaces; with 16 warps it takes 94 ms instead of 52 + 56 ms per decomposition (3.7 TB/s --
+  // still short of the 6.5 TB/s of the plain update kernel), i.e. -6 % on the whole of C4.
+  // MF_CGS_FUSED_OFF=1 restores the two-kernel route (A/B runs, tests).
+  const bool on = getenv("MF_CGS_FUSED_OFF") == nullptr;
   // ld == 1 (a single start vector: BASELINE config 4) -- wider tiles keep the two-kernel route
   if (!on || dtype != MF_F32 || ld != 1 || nq < 1 || nq > kCgsMaxNq) return false;
   if (partial_rows < nq) return false;  // one partial row per basis vector
@@ -752,10 +766,10 @@ int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
   if (q_stride <= 0) q_stride = total;
-  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + kCgsRows + (nq + 3) / 4 * 4 * ld) * sizeof(float);
+  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + (kCgsThreads / kCgsRows) * kCgsRows + nq + 16) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + kCgsRows + kCgsMaxNq) * 4;
+    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + (kCgsThreads / kCgsRows) * kCgsRows + kCgsMaxNq + 16) * 4;
     if (cudaFuncSetAttribute(cgs_update_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)max_smem) != cudaSuccess) {
       cudaGetLastError();
@@ -768,7 +782,7 @@ int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void
   int grid = num_sms();
   if (grid > ntiles) grid = (int)ntiles;
   Finalize fin{counter, 0, h_out, nullptr, nullptr, peer};
-  cgs_update_dots_kernel<<<grid, kCgsRows, smem, st>>>((const float*)Q, q_stride, (int)nq,
+  cgs_update_dots_kernel<<<grid, kCgsThreads, smem, st>>>((const float*)Q, q_stride, (int)nq,
                                                        (const float*)h, (float*)V, total, (int)ld,
                                                        partial, (int64_t)kMaxPartialCtas * ld, fin);
   return check_launch("cgs_update_dots");

@@ -39,19 +39,19 @@ def test_fused_cgs_matches_two_kernel_route_and_oracle(shape, ld, k, fused):
     op = m.ops.csr(ip, ix, d)
     V = torch.as_tensor(oprng.normal(oprng.prng_key(4), (n, ld), np.float32)).cuda()
     lib_launches = __import__("matfree_b200._lib", fromlist=["load"]).load().mf_launch_count
-    os.environ.pop("MF_CGS_FUSED", None)
+    os.environ.pop("MF_CGS_FUSED_OFF", None)
     l0 = lib_launches()
-    a2, b2, len2, Q2, r2 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
+    a1, b1, len1, Q1, r1 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
     torch.cuda.synchronize()
-    plain_launches = lib_launches() - l0
-    os.environ["MF_CGS_FUSED"] = "1"   # the fused sweep is opt-in (see blockvec.cu)
+    fused_launches = lib_launches() - l0
+    os.environ["MF_CGS_FUSED_OFF"] = "1"   # the two-kernel route
     try:
         l0 = lib_launches()
-        a1, b1, len1, Q1, r1 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
+        a2, b2, len2, Q2, r2 = m.decomp.lanczos_blocked(op, V, k, "full", want_Q=True, want_residual=True)
         torch.cuda.synchronize()
-        fused_launches = lib_launches() - l0
+        plain_launches = lib_launches() - l0
     finally:
-        del os.environ["MF_CGS_FUSED"]
+        del os.environ["MF_CGS_FUSED_OFF"]
     assert (fused_launches < plain_launches) == fused, (fused_launches, plain_launches)
     tol = 3e-5
     assert np.allclose(a1.cpu(), a2.cpu(), rtol=tol, atol=tol)

@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+( timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/r1w_tests.log 2>&1
+tail -4 gpurun_out/r1w_tests.log
