@@ -323,3 +323,25 @@ def test_hessenberg_decomposition_is_satisfied(reortho):
     ek = np.eye(k)[:, -1]
     assert np.allclose(A @ Q.T, Q.T @ H + np.outer(r, ek), atol=1e-9)
     assert np.allclose(c, 1 / np.linalg.norm(v))
+
+
+def test_oracle_reproduces_committed_slq_golden():
+    """tests/golden/slq_golden.json (made by tests/golden/make_slq_golden.py) pins the oracle
+    against drift: regenerating it must give the committed numbers."""
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_slq_golden", os.path.join(here, "golden", "make_slq_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fresh = mod.build()
+    with open(os.path.join(here, "golden", "slq_golden.json")) as f:
+        gold = json.load(f)
+    for name, tol in (("f32", 2e-6), ("f64", 1e-12)):
+        for key, want in gold["cases"][name].items():
+            got = fresh["cases"][name][key]
+            if isinstance(want, list) and want and isinstance(want[0], float):
+                want, got = np.asarray(want), np.asarray(got)
+                assert np.max(np.abs(got - want)) <= tol * (np.abs(want).max() + 1e-30), (name, key)
+            else:
+                assert got == want, (name, key)
