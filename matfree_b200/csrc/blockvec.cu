@@ -345,20 +345,30 @@ cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
   float* sp = vs + R;                         // [G - 1][R] partial sums of the other parts of the j range
   float* hs = sp + (G - 1) * R;               // [nqg]: coefficients, zero-padded (ld == 1)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < nqg; i += NT) hs[i] = i < nq ? h[i] : 0.f;
+  // All of shared memory starts as zeros: phase A reads up to 4 G - 1 segments past the last
+  // basis vector with a zero coefficient, and 0 * (stale bits that happen to be NaN) is NaN.
+  {
+    const int all = 2 * stage_floats + R + (G - 1) * R + nqg + 4 * G * R;  // + read-ahead padding
+    for (int i = tid; i < all; i += NT) cgs_smem[i] = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < nq; i += NT) hs[i] = h[i];
 
   const int64_t ntiles = (total + R - 1) / R;
+  // A warp copies whole 1 KB segments (segment j = warp, warp + NW, ...: lane l moves the 16-byte
+  // chunks l and l + 32), so the inner loop has no divisions and one pointer per segment.
   auto issue = [&](int buf, int64_t tile) {
     float* st = cgs_smem + buf * stage_floats;
     const int64_t base = tile * R;
-    const int chunks = (nq + 1) * (R / 4);
-    for (int c = tid; c < chunks; c += NT) {
-      const int j = c / (R / 4), ch = (c - j * (R / 4)) * 4;
-      const int64_t f = base + ch;
-      const float* src = j < nq ? Q + (int64_t)j * q_stride : V;
-      int64_t left = (total - f) * 4;
-      const int bytes = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
-      cgs_cp16(st + j * R + ch, bytes ? (const void*)(src + f) : (const void*)src, bytes);
+    const int64_t left0 = (total - base - lane * 4) * 4;         // bytes left from chunk `lane`
+    const int64_t left1 = left0 - 32 * 16;                       // ... from chunk `lane + 32`
+    const int b0 = left0 >= 16 ? 16 : (left0 > 0 ? (int)left0 : 0);
+    const int b1 = left1 >= 16 ? 16 : (left1 > 0 ? (int)left1 : 0);
+    for (int j = warp; j <= nq; j += NW) {
+      const float* src = (j < nq ? Q + (int64_t)j * q_stride : V) + base + lane * 4;
+      float* dst = st + j * R + lane * 4;
+      cgs_cp16(dst, b0 ? (const void*)src : (const void*)V, b0);
+      cgs_cp16(dst + 128, b1 ? (const void*)(src + 128) : (const void*)V, b1);
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -388,11 +398,13 @@ cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
       const float4* hc = reinterpret_cast<const float4*>(hs);
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       for (int j = jbeg; j < jend; j += 4) {
+        // segments nq .. nqg-1 (the V segment and what follows it in shared memory) meet zero
+        // coefficients; they are finite (user data or the zeros written above)
         const float4 hv = hc[j >> 2];
-        if (j + 0 < nq) s0 += hv.x * Qs[(j + 0) * R + rowA];
-        if (j + 1 < nq) s1 += hv.y * Qs[(j + 1) * R + rowA];
-        if (j + 2 < nq) s2 += hv.z * Qs[(j + 2) * R + rowA];
-        if (j + 3 < nq) s3 += hv.w * Qs[(j + 3) * R + rowA];
+        s0 += hv.x * Qs[(j + 0) * R + rowA];
+        s1 += hv.y * Qs[(j + 1) * R + rowA];
+        s2 += hv.z * Qs[(j + 2) * R + rowA];
+        s3 += hv.w * Qs[(j + 3) * R + rowA];
       }
       const float sA = (s0 + s1) + (s2 + s3);
       if (half > 0) sp[(half - 1) * R + rowA] = sA;
@@ -766,10 +778,13 @@ int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
   if (q_stride <= 0) q_stride = total;
-  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + (kCgsThreads / kCgsRows) * kCgsRows + nq + 16) * sizeof(float);
+  // stages + vs + sp + hs (nq rounded up to 4 G) + 4 G segments of zero padding that phase A may
+  // read past the last stage with zero coefficients
+  constexpr int kG = kCgsThreads / kCgsRows;
+  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + kG * kCgsRows + (nq + 4 * kG) + 4 * kG * kCgsRows) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + (kCgsThreads / kCgsRows) * kCgsRows + kCgsMaxNq + 16) * 4;
+    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + kG * kCgsRows + (kCgsMaxNq + 4 * kG) + 4 * kG * kCgsRows) * 4;
     if (cudaFuncSetAttribute(cgs_update_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)max_smem) != cudaSuccess) {
       cudaGetLastError();
