@@ -11,7 +11,9 @@
  *   - all pointers are DEVICE pointers unless the name starts with `h_`;
  *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as
  *     void*); nothing here synchronises the device or the stream, allocates or
- *     frees device memory, or keeps a pointer after returning;
+ *     frees device memory, or keeps a pointer after returning -- with the
+ *     documented exceptions of the profiling aid mf_timing_collect and of the
+ *     set-up / tear-down calls of the multi-GPU communicator (mf_comm_*);
  *   - scratch memory is caller-provided (`workspace`, sized by the matching
  *     `*_workspace_bytes` function);
  *   - return value: 0 on success, a negative MF_ERR_* code otherwise;
