@@ -25,7 +25,7 @@
 //   * per row all gathers (a whole 5- or 7-point stencil row) are issued
 //     back to back into registers before the first FMA, one IMAD.WIDE + one
 //     LDG.128 per non-zero (tile width is a template constant).
-// Variants that were measured and rejected (tools/gpu_run*.sh, profiles/README.md):
+// Variants that were measured and rejected (tools/runs/gpu_run*.sh, profiles/README.md):
 // dynamic chunk tickets (same speed, not reproducible), a cp.async ring in shared
 // memory as the landing zone (2x the instructions, fewer warps: slower), register
 // software pipelining across rows (spills), L1/L2 software prefetch (no gain).

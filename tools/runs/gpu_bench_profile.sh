@@ -1,6 +1,6 @@
 #!/bin/bash
 # Standard single-GPU pass: parity tests, smoke, bench (both arms), ncu launch list + full capture of the HBM kernels.
-# usage: tools/gpu_bench_profile.sh <tag>
+# usage: tools/runs/gpu_bench_profile.sh <tag>
 TAG=${1:-run}
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest_gpu.log 2>&1

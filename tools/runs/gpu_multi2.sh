@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU pass: NCCL parity tests (probe sharding + row sharding), C4 row-sharded, C2 probe-sharded
-# usage: tools/gpu_multi2.sh <ngpus>
+# usage: tools/runs/gpu_multi2.sh <ngpus>
 N=${1:-2}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -15 > gpurun_out/m${N}_tests.log

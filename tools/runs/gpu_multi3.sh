@@ -1,6 +1,6 @@
 #!/bin/bash
 # multi-GPU pass for the peer-memory path: NCCL/peer parity tests, C4 row-sharded (peer route and NCCL route)
-# usage: tools/gpu_multi3.sh <ngpus> [tag]
+# usage: tools/runs/gpu_multi3.sh <ngpus> [tag]
 N=${1:-2}
 TAG=${2:-r1e}
 mkdir -p gpurun_out

@@ -1,7 +1,7 @@
 #!/bin/bash
 # multi-GPU pass: parity tests (probe sharding, row sharding via peer memory and NCCL), C4 peer route (fused CGS on/off),
 # C4 NCCL route, C2 probe-sharded bench
-# usage: tools/gpu_multi4.sh <ngpus> [tag]
+# usage: tools/runs/gpu_multi4.sh <ngpus> [tag]
 N=${1:-8}
 TAG=${2:-r1x}
 mkdir -p gpurun_out
