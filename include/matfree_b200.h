@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 3
+#define MF_ABI_VERSION 4
 
 /* status codes */
 #define MF_OK 0
@@ -140,6 +140,14 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
                      int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
                      int32_t sampler, int32_t prng_flags, double* sqnorm_out,
                      void* stream);
+
+/* The same stream for ONE RANK's rows of a row-sharded sample array (blocked layout only):
+ * out[rows][ld] holds components row0 .. row0+rows-1 of probes p0 .. p0+num_probes-1 of length
+ * n_total, i.e. counter = p * n_total + row0 + r -- bit-identical to the corresponding rows of
+ * the single-device array, so a row-sharded estimate does not depend on the number of ranks. */
+int32_t mf_probe_gen_rows(void* out, int32_t dtype, int64_t n_total, int64_t row0, int64_t rows,
+                          int64_t ld, int64_t p0, int64_t num_probes, uint32_t key0,
+                          uint32_t key1, int32_t sampler, int32_t prng_flags, void* stream);
 
 /* One-time preprocessing of an fp32 dense / Gram operator for the tensor-core
  * path: the two TF32 planes of its matrix, hi = rna_tf32(A), lo = rna_tf32(A - hi),

@@ -8,7 +8,7 @@ runs in hand-written sm_100a CUDA kernels inside `libmatfree_b200.so`
 CUDA device is missing, calls raise.
 """
 
-from matfree_b200 import decomp, eig, funm, ops, stochtrace  # noqa: F401
+from matfree_b200 import config, decomp, eig, funm, ops, stochtrace  # noqa: F401
 from matfree_b200.backend import prng  # noqa: F401
 
-__all__ = ["decomp", "eig", "funm", "ops", "stochtrace", "prng"]
+__all__ = ["config", "decomp", "eig", "funm", "ops", "stochtrace", "prng"]

@@ -60,6 +60,8 @@ SIGNATURES = {
     "mf_timing_collect": (c_int32, [c_void_p, c_void_p]),
     "mf_probe_gen": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_int64, c_int64,
                                c_uint32, c_uint32, c_int32, c_int32, c_void_p, c_void_p]),
+    "mf_probe_gen_rows": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                    c_int64, c_uint32, c_uint32, c_int32, c_int32, c_void_p]),
     "mf_gemm_config": (c_int32, [c_int32, c_int32]),
     "mf_operator_split_bytes": (c_int64, [_OP]),
     "mf_operator_split": (c_int32, [_OP, c_void_p, c_void_p]),

@@ -463,7 +463,7 @@ def lanczos_sharded_native(op, V0, k, reortho, *, want_Q, want_residual):
     Q = None
     if keep_Q and k > 0:
         m0 = op.plan.row(op.r0)
-        Q = ext[:k, m0:m0 + nloc].contiguous()  # the heap is reused by the next call
+        Q = ext[:k, m0:m0 + nloc].clone()  # a copy: the heap is reused by the next call
     return alphas[:k], betas[:k], init_len, Q, residual
 
 

@@ -46,7 +46,7 @@ def split(key, num: int = 2):
 def _generate(key, shape, dtype, sampler):
     import torch
 
-    from matfree_b200 import _lib, _device
+    from matfree_b200 import _lib, _device, config
 
     lib = _lib.load()
     tdt = _device.torch_dtype(dtype)
@@ -55,8 +55,8 @@ def _generate(key, shape, dtype, sampler):
     out = torch.empty(max(total, 1), dtype=tdt, device=_device.device())
     # one "probe" of length total: counter = flat index
     _lib.check(lib.mf_probe_gen(out.data_ptr(), _device.mf_dtype(tdt), _lib.MF_LAYOUT_PROBE_MAJOR,
-                                total, total, 0, 1, int(key[0]), int(key[1]), sampler, 0, None,
-                                _device.stream()))
+                                total, total, 0, 1, int(key[0]), int(key[1]), sampler,
+                                config.prng_flags(tdt), None, _device.stream()))
     return out[:total].reshape(shape)
 
 

@@ -629,6 +629,22 @@ int32_t mf_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_
                           prng_flags, nullptr, (cudaStream_t)stream);
 }
 
+int32_t mf_probe_gen_rows(void* out, int32_t dtype, int64_t n_total, int64_t row0, int64_t rows,
+                          int64_t ld, int64_t p0, int64_t num_probes, uint32_t key0,
+                          uint32_t key1, int32_t sampler, int32_t prng_flags, void* stream) {
+  if (out == nullptr || rows < 0 || row0 < 0 || row0 + rows > n_total || num_probes < 0 || p0 < 0) {
+    set_error("probe_gen_rows: bad arguments");
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  if ((dtype != MF_F32 && dtype != MF_F64) ||
+      (sampler != MF_SAMPLER_SIGNS && sampler != MF_SAMPLER_NORMAL)) {
+    set_error("probe_gen_rows: dtype %d / sampler %d unsupported", dtype, sampler);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  return launch_probe_gen(out, dtype, MF_LAYOUT_BLOCKED, rows, ld, p0, num_probes, key0, key1,
+                          sampler, prng_flags, nullptr, (cudaStream_t)stream, row0, n_total);
+}
+
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores) {
   if (variant < 0 || variant > 2) {
     set_error("gemm_config: variant must be 0, 1 or 2");

@@ -721,16 +721,26 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
 int32_t launch_reorth_update(const void* Q, int64_t nq, const void* h, void* V, int32_t dtype,
                              int64_t n, int64_t ld, const Reduce* red, cudaStream_t st,
                              int64_t q_stride) {
+  if (q_stride <= 0) q_stride = n * ld;
+  const int64_t max_nq = (160 * 1024) / (ld * (int64_t)dtype_size(dtype));
+  if (nq > max_nq) {
+    // The coefficients of all nq basis vectors do not fit the shared-memory staging (e.g. depth
+    // > 160 at ld = 256 in fp32): subtract the basis in groups, V -= sum_{j in group} Q[j] h[j];
+    // the fused norm rides on the last group.
+    const int64_t es = (int64_t)dtype_size(dtype);
+    for (int64_t j0 = 0; j0 < nq; j0 += max_nq) {
+      const int64_t nj = (nq - j0) < max_nq ? (nq - j0) : max_nq;
+      MF_TRY(launch_reorth_update((const char*)Q + j0 * q_stride * es, nj,
+                                  (const char*)h + j0 * ld * es, V, dtype, n, ld,
+                                  j0 + nj == nq ? red : nullptr, st, q_stride));
+    }
+    return MF_OK;
+  }
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
   if (q_stride <= 0) q_stride = total;
   const bool mf_wide = wide_ok(dtype, total, Q, V) && q_stride % (dtype == MF_F64 ? 2 : 4) == 0;
   const size_t smem = (size_t)nq * ld * dtype_size(dtype);
-  if (smem > 160 * 1024) {
-    set_error("reorth_update: %lld basis vectors x %lld probes exceed the shared-memory budget; "
-              "use a narrower tile", (long long)nq, (long long)ld);
-    return MF_ERR_UNSUPPORTED;
-  }
   Finalize fin{};
   double* partial = nullptr;
   if (red) {

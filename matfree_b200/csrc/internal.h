@@ -23,10 +23,12 @@ inline int64_t partial_bytes(int64_t ld, int nacc = 1) {
 
 // ---- probe_gen.cu
 // red (optional): column sums of squares -> red->fin (mode 1: |probe|, 1/|probe|)
+// row0 / n_total (blocked layout): the block holds rows [row0, row0 + n) of probes of length
+// n_total (a rank's slab of a row-sharded sample array); n_total = 0 means n_total = n.
 int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
                          int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
                          int32_t sampler, int32_t prng_flags, const Reduce* red,
-                         cudaStream_t st);
+                         cudaStream_t st, int64_t row0 = 0, int64_t n_total = 0);
 
 // ---- blockvec.cu : all operate on blocked vectors X[n][ld]
 // sum_r (X[r][c] * sx[c]) * Y[r][c] -> red.fin         (sx may be null)

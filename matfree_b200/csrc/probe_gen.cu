@@ -91,9 +91,9 @@ __device__ __forceinline__ T sample_one(uint32_t k0, uint32_t k1, uint64_t ctr, 
 // flat elements per sweep, so its columns never change.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
-probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int ld, int64_t p0, int num_probes,
-                         uint32_t k0, uint32_t k1, int sampler, int flags, uint32_t one,
-                         double* __restrict__ partial, Finalize fin) {
+probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int64_t row0, int64_t n_total, int ld,
+                         int64_t p0, int num_probes, uint32_t k0, uint32_t k1, int sampler,
+                         int flags, uint32_t one, double* __restrict__ partial, Finalize fin) {
   const int64_t total = n * (int64_t)ld;
   const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
   double acc[1][VEC];
@@ -109,7 +109,7 @@ probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int ld, int64_t p0, int
       const int64_t rr = (VEC > 1 && ld < VEC) ? (f + i) / ld : r;
       T x = T(0);
       if (c < num_probes) {
-        const uint64_t ctr = (uint64_t)(p0 + c) * (uint64_t)n + (uint64_t)rr;
+        const uint64_t ctr = (uint64_t)(p0 + c) * (uint64_t)n_total + (uint64_t)(row0 + rr);
         x = sample_one<T>(k0, k1, ctr, sampler, flags, one);
       }
       v[i] = x;
@@ -132,9 +132,9 @@ probe_gen_blocked_kernel(T* __restrict__ out, int64_t n, int ld, int64_t p0, int
 // is the number of rows generated (every entry is +-1), counted per thread.
 template <typename T, int VEC, bool X64>
 __global__ void __launch_bounds__(kBlock)
-probe_gen_signs_kernel(T* __restrict__ out, int64_t n, int ld, int ld_shift, int64_t p0,
-                       int num_probes, uint32_t k0, uint32_t k1, uint32_t one,
-                       double* __restrict__ partial, Finalize fin) {
+probe_gen_signs_kernel(T* __restrict__ out, int64_t n, int64_t row0, int64_t n_total, int ld,
+                       int ld_shift, int64_t p0, int num_probes, uint32_t k0, uint32_t k1,
+                       uint32_t one, double* __restrict__ partial, Finalize fin) {
   const int64_t total = n * (int64_t)ld;
   const int64_t stride = (int64_t)gridDim.x * kBlock * VEC;
   const int e0 = threadIdx.x * VEC;
@@ -144,7 +144,7 @@ probe_gen_signs_kernel(T* __restrict__ out, int64_t n, int ld, int ld_shift, int
   for (int i = 0; i < VEC; ++i) {
     const int c = (e0 + i) & (ld - 1);
     live[i] = c < num_probes;
-    cbase[i] = (uint64_t)(p0 + c) * (uint64_t)n;
+    cbase[i] = (uint64_t)(p0 + c) * (uint64_t)n_total + (uint64_t)row0;
   }
   int64_t iters = 0;
   for (int64_t f = ((int64_t)blockIdx.x * kBlock + threadIdx.x) * VEC; f < total; f += stride) {
@@ -195,9 +195,10 @@ probe_gen_pn_kernel(T* __restrict__ out, int64_t n, int64_t ld, int64_t p0, int6
 int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, int64_t ld,
                          int64_t p0, int64_t num_probes, uint32_t key0, uint32_t key1,
                          int32_t sampler, int32_t prng_flags, const Reduce* red,
-                         cudaStream_t st) {
+                         cudaStream_t st, int64_t row0, int64_t n_total) {
   MF_KSCOPE(MF_KC_PROBE_GEN, st);
   if (n <= 0 || num_probes <= 0) return MF_OK;
+  if (n_total <= 0) n_total = n;  // the block holds all rows of the sample array
   if (layout == MF_LAYOUT_BLOCKED) {
     if (!valid_ld(ld) || num_probes > ld) {
       set_error("probe_gen: blocked layout needs ld a power of two <= 256 and num_probes <= ld");
@@ -212,8 +213,8 @@ int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, in
     auto kern = probe_gen_blocked_kernel<T, VEC>;                                              \
     const int grid = resident_grid((const void*)kern, kBlock, 0,                               \
                                    (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC)); \
-    kern<<<grid, kBlock, 0, st>>>((T*)out, n, (int)ld, p0, (int)num_probes, key0, key1, sampler, \
-                                  prng_flags, 1u, partial, fin);                                   \
+    kern<<<grid, kBlock, 0, st>>>((T*)out, n, row0, n_total, (int)ld, p0, (int)num_probes, key0,   \
+                                  key1, sampler, prng_flags, 1u, partial, fin);                    \
   } while (0)
 #define MF_PGS(T, VEC, X64)                                                                    \
   do {                                                                                         \
@@ -222,8 +223,8 @@ int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, in
                                    (total + (int64_t)kBlock * VEC - 1) / ((int64_t)kBlock * VEC)); \
     int ld_shift = 0;                                                                          \
     while ((1ll << ld_shift) < ld) ++ld_shift;                                                 \
-    kern<<<grid, kBlock, 0, st>>>((T*)out, n, (int)ld, ld_shift, p0, (int)num_probes, key0,    \
-                                  key1, 1u, partial, fin);                                     \
+    kern<<<grid, kBlock, 0, st>>>((T*)out, n, row0, n_total, (int)ld, ld_shift, p0,            \
+                                  (int)num_probes, key0, key1, 1u, partial, fin);              \
   } while (0)
     const bool x64 = (prng_flags & MF_PRNG_X64_BITS) != 0;
     if (sampler == MF_SAMPLER_SIGNS && dtype == MF_F32 && ld >= 4) {
@@ -240,6 +241,10 @@ int32_t launch_probe_gen(void* out, int32_t dtype, int32_t layout, int64_t n, in
     return check_launch("probe_gen_blocked");
   }
   if (layout == MF_LAYOUT_PROBE_MAJOR) {
+    if (row0 != 0 || n_total != n) {
+      set_error("probe_gen: row slabs are generated in the blocked layout only");
+      return MF_ERR_UNSUPPORTED;
+    }
     if (ld < n) {
       set_error("probe_gen: probe-major layout needs ld >= n");
       return MF_ERR_INVALID_ARGUMENT;

@@ -8,8 +8,10 @@ three-term Lanczos recurrence (`decomp.py:220-292`).  The returned
 ``decompose(matvec, vec, *params)`` gives the reference's four-field result
 ``(Q_tall (k, n), J_small, residual (n,), init_length_inv)``.
 
-`matvec` must be a registered operator (`matfree_b200.ops`); the arithmetic
-runs in `mf_lanczos` (`include/matfree_b200.h`).
+`matvec` is a registered operator (`matfree_b200.ops`: the whole recurrence runs in
+`mf_lanczos`, `include/matfree_b200.h`) or any callable ``matvec(vec, *params)`` of CUDA tensors
+with `vec` any pytree (`decomp.py:156-182`): the callable supplies the product, the library the
+rest of the recurrence (`matfree_b200/_generic.py`).
 """
 
 from __future__ import annotations
@@ -58,8 +60,15 @@ def lanczos_blocked(op: ops.Operator, V0b, k: int, reortho: str, *, want_Q: bool
     """
     import torch
 
-    from matfree_b200 import _rowshard
+    from matfree_b200 import _generic, _rowshard
 
+    if isinstance(op, _generic.CallableOperator):
+        # a user callable supplies the product; the rest of the recurrence is the library's
+        if reortho == "full":
+            a, b, length, Q, res, _ = _generic.arnoldi(op, V0b.contiguous(), k)
+        else:
+            a, b, length, Q, res = _generic.lanczos_none(op, V0b.contiguous(), k, want_Q=want_Q)
+        return a, b, length, Q, (res if want_residual else None)
     if isinstance(op, _rowshard.RowShardedCsr):
         # rows (and vectors) are partitioned over the ranks of op.group: V0b is this rank's slab
         if reortho == "full":
@@ -107,10 +116,11 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
     def decompose(matvec, vec, *params):
         import torch
 
-        if params:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
-        op = ops.require_operator(matvec, "tridiag_sym")
-        vec_t = _device.as_device(vec, op.dtype).reshape(-1)
+        from matfree_b200 import _generic
+
+        # decomp.py:156-164: `vec` may be any pytree, `matvec(vec, *params)` any callable of
+        # device tensors; a registered operator takes the flat vector and no parameters
+        op, vec_t, unravel = _generic.wrap(matvec, vec, params)
         n = vec_t.shape[0]
         n_total = getattr(op, "n_global", n)  # row-sharded operators: vec is this rank's slab
         if k < 0 or k > n_total:
@@ -136,8 +146,13 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
         matrix = (diags, offdiags)
         if materialize:
             matrix = _todense_tridiag_sym(diags, offdiags)
-        return _DecompResult(Q_tall=Q_tall, J_small=matrix, residual=res,
-                             init_length_inv=1.0 / init_len[0])
+        inv = 1.0 / init_len[0]
+        if reortho == "full":
+            # decomp.py:132,142: the full variant is built on `hessenberg`, whose fourth output is
+            # already 1/|v|, and returns `init_length_inv=1.0 / norm` -- i.e. the LENGTH.  Kept.
+            inv = 1.0 / inv
+        return _DecompResult(Q_tall=unravel.batched(Q_tall), J_small=matrix, residual=unravel(res),
+                             init_length_inv=inv)
 
     decompose._mf_spec = {"kind": "tridiag_sym", "num_matvecs": k, "reortho": reortho,
                           "materialize": materialize}
@@ -236,12 +251,21 @@ def bidiag(num_matvecs: int, /, materialize: bool = True, reortho: str = "full")
     def estimate(Av, v0, *parameters):
         import torch
 
-        if parameters:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
-        op = ops.require_operator(Av, "bidiag")
-        if not isinstance(op, ops.RectOperator):
-            raise TypeError("bidiag: matvec must be ops.rect(A)")
-        v = _device.as_device(v0, op.dtype).reshape(-1)
+        from matfree_b200 import _generic
+
+        if isinstance(Av, ops.Operator):
+            if parameters:
+                raise TypeError("registered operators carry their own buffers; extra matvec parameters "
+                                "are only supported for callables")
+            if not isinstance(Av, ops.RectOperator):
+                raise TypeError("bidiag: a registered matvec must be ops.rect(A)")
+            op = Av
+            v = _device.as_device(v0, op.dtype).reshape(-1)
+        else:
+            # any callable of device tensors: the vector-matrix product comes from its VJP
+            # (decomp.py:703,712 use jax.vjp; here torch.func.vjp)
+            v = _device.as_device(v0).reshape(-1)
+            op = _generic.CallableRect(Av, v, parameters)
         if v.shape[0] != op.n:
             raise ValueError(f"vector has length {v.shape[0]}, operator has {op.n} columns")
         if k > min(op.m, op.n) or k < 0:
@@ -260,9 +284,13 @@ def bidiag(num_matvecs: int, /, materialize: bool = True, reortho: str = "full")
 
 def hessenberg(num_matvecs, /, *, reortho: str, custom_vjp: bool = True, reortho_vjp: str = "match"):
     """Construct a Hessenberg factorisation via the Arnoldi iteration (`matfree/decomp.py:351-477`):
-    ``A Q^T ~ Q^T H`` for an arbitrary square operator.  `custom_vjp` / `reortho_vjp` are accepted
-    for signature compatibility (gradients are out of scope)."""
-    del custom_vjp, reortho_vjp
+    ``A Q^T ~ Q^T H`` for an arbitrary square operator.
+
+    As in the reference the forward pass runs with ``reortho=reortho_vjp`` (`decomp.py:393-396`):
+    with the default "match" the second Gram-Schmidt pass is applied whatever `reortho` says
+    (`:466` only tests ``!= "none"``); `reortho` itself selects the adjoint's re-projection
+    (`matfree_b200.adjoint`)."""
+    del custom_vjp
     if reortho not in ("none", "full"):
         raise TypeError(f"Unexpected input for {reortho}: either of {['none', 'full']} expected.")  # :375-378
     k = int(num_matvecs)
@@ -270,29 +298,39 @@ def hessenberg(num_matvecs, /, *, reortho: str, custom_vjp: bool = True, reortho
     def estimate(matvec, v, *params):
         import torch
 
-        if params:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
-        op = ops.require_operator(matvec, "hessenberg")
-        lib = _lib.load()
-        vec = _device.as_device(v, op.dtype).reshape(-1)
+        from matfree_b200 import _generic, _rowshard
+
+        op, vec, unravel = _generic.wrap(matvec, v, params)  # decomp.py:380-386
+        if isinstance(op, _rowshard.RowShardedCsr):
+            raise NotImplementedError(
+                "hessenberg: row-sharded operators are supported by tridiag_sym (both reortho modes), "
+                "not by the public Arnoldi factorisation")
         n = vec.shape[0]
         if k < 0 or k > n:
             raise ValueError(_error_num_matvecs(k, maxval=n, minval=0))
         if n != op.n:
             raise ValueError(f"vector has length {n}, operator dimension is {op.n}")
         dt, dev = op.dtype, vec.device
+        second = reortho_vjp != "none"
+        if isinstance(op, _generic.CallableOperator):
+            _, _, init_len, Q, residual, H = _generic.arnoldi(op, vec.reshape(n, 1).contiguous(), k,
+                                                              second_pass=second, want_H=True)
+            Qk = Q[:, :, 0] if k > 0 else torch.zeros((0, n), dtype=dt, device=dev)
+            return _DecompResult(Q_tall=unravel.batched(Qk), J_small=H[:, :, 0],
+                                 residual=unravel(residual[:, 0]), init_length_inv=1.0 / init_len[0])
+        lib = _lib.load()
         st = op._struct()
         ws = _device.workspace(lib.mf_hessenberg_workspace_bytes(ctypes.byref(st), 1, k))
         H = torch.zeros((k, k, 1), dtype=dt, device=dev)
         Q = torch.zeros((max(k, 1), n, 1), dtype=dt, device=dev)
         init_len = torch.empty((1,), dtype=dt, device=dev)
         residual = torch.empty((n, 1), dtype=dt, device=dev)
-        rflag = _lib.MF_REORTHO_FULL if reortho == "full" else _lib.MF_REORTHO_NONE
+        rflag = _lib.MF_REORTHO_FULL if second else _lib.MF_REORTHO_NONE
         _lib.check(lib.mf_hessenberg(ctypes.byref(st), vec.data_ptr(), 1, k, rflag, H.data_ptr(),
                                      init_len.data_ptr(), Q.data_ptr(), residual.data_ptr(),
                                      ws.data_ptr(), ws.numel(), _device.stream()))
-        return _DecompResult(Q_tall=Q[:k, :, 0], J_small=H[:, :, 0], residual=residual[:, 0],
-                             init_length_inv=1.0 / init_len[0])
+        return _DecompResult(Q_tall=unravel.batched(Q[:k, :, 0]), J_small=H[:, :, 0],
+                             residual=unravel(residual[:, 0]), init_length_inv=1.0 / init_len[0])
 
     estimate._mf_spec = {"kind": "hessenberg", "num_matvecs": k, "reortho": reortho}
     return estimate

@@ -1,5 +1,6 @@
-"""Partial eigen- and singular-value decompositions -- mirrors `matfree/eig.py:22-104`
-(`svd_partial`, `eigh_partial`): thin consumers of `decomp.tridiag_sym` / `decomp.bidiag`.
+"""Partial eigen- and singular-value decompositions -- mirrors `matfree/eig.py:22-160`
+(`svd_partial`, `eigh_partial`, `eig_partial`): thin consumers of `decomp.tridiag_sym` /
+`decomp.hessenberg` / `decomp.bidiag`; vectors may be pytrees, matvecs callables with parameters.
 
 The Krylov bases stay on the device; the small ``k x k`` factor is decomposed with LAPACK through
 torch (k is the number of matvecs: tens), and the Ritz / singular vectors ``S^T Q`` are formed by
@@ -31,6 +32,28 @@ def _combine_rows(S, Q):
     return out
 
 
+def _partial_and_flatten_matvec(Av, v0, parameters):
+    """`eig.py:145-160`: bind the parameters and conjugate the matvec with ravel / unravel.  A
+    registered operator already takes flat vectors (and carries its buffers)."""
+    from matfree_b200 import ops
+    from matfree_b200.backend import tree
+
+    if isinstance(Av, ops.Operator):
+        if parameters:
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters "
+                            "are only supported for callables")
+        v0_flat, v_unravel = tree.ravel_pytree(v0, Av.dtype)
+        return Av, v0_flat, v_unravel, None
+    v0_flat, v_unravel = tree.ravel_pytree(v0)
+    holder = {}
+
+    def Av_flat(v_flat):
+        result_flat, holder["u_unravel"] = tree.ravel_pytree(Av(v_unravel(v_flat), *parameters), v_flat.dtype)
+        return result_flat
+
+    return Av_flat, v0_flat, v_unravel, holder
+
+
 def eigh_partial(tridiag_sym):
     """Partial eigendecomposition ``A ~ V diag(vals) V^T`` of a symmetric operator
     (`eig.py:69-104`): returns ``(vals (k,), vecs (k, n))``, rows of `vecs` are Ritz vectors."""
@@ -38,15 +61,36 @@ def eigh_partial(tridiag_sym):
     def eigh(Av, v0, *parameters):
         import torch
 
-        Q, H, *_ = tridiag_sym(Av, v0, *parameters)
+        Av_flat, v0_flat, v_unravel, _ = _partial_and_flatten_matvec(Av, v0, parameters)
+        Q, H, *_ = tridiag_sym(Av_flat, v0_flat)
         if isinstance(H, tuple):  # materialize=False: (diag, offdiag)
             from matfree_b200 import decomp
 
             H = decomp._todense_tridiag_sym(*H)
         vals, vecs = torch.linalg.eigh(H)
-        return vals, _combine_rows(vecs.T, Q)
+        return vals, v_unravel.batched(_combine_rows(vecs.T, Q))
 
     return eigh
+
+
+def eig_partial(hessenberg):
+    """Partial eigendecomposition of an arbitrary square operator via the Hessenberg
+    factorisation (`eig.py:107-142`): ``vals, vecs = eig(H); vecs = vecs^T Q`` -- complex in
+    general (`jax.numpy.linalg.eig`).  The ``k x k`` eigenproblem is LAPACK's (`torch.linalg.eig`),
+    the real and imaginary parts of ``vecs^T Q`` are two passes of `mf_basis_combine` over the
+    stored basis."""
+
+    def eig(Av, v0, *parameters):
+        import torch
+
+        Av_flat, v0_flat, v_unravel, _ = _partial_and_flatten_matvec(Av, v0, parameters)
+        Q, H, *_ = hessenberg(Av_flat, v0_flat)
+        vals, vecs = torch.linalg.eig(H)
+        St = vecs.T.contiguous()
+        out = torch.complex(_combine_rows(St.real.contiguous(), Q), _combine_rows(St.imag.contiguous(), Q))
+        return vals, v_unravel.batched(out)
+
+    return eig
 
 
 def svd_partial(bidiag):
@@ -56,10 +100,14 @@ def svd_partial(bidiag):
     def svd(Av, v0, *parameters):
         import torch
 
-        (u, v), B, *_ = bidiag(Av, v0, *parameters)
+        Av_flat, v0_flat, v_unravel, holder = _partial_and_flatten_matvec(Av, v0, parameters)
+        (u, v), B, *_ = bidiag(Av_flat, v0_flat)
         if isinstance(B, tuple):
             raise TypeError("svd_partial assumes that the bidiagonalisation materialises the bidiagonal matrix")
         U, S, Vt = torch.linalg.svd(B, full_matrices=False)
-        return _combine_rows(U.T, u), S, _combine_rows(Vt, v)
+        ut, vt = _combine_rows(U.T, u), _combine_rows(Vt, v)
+        if holder and "u_unravel" in holder:
+            ut = holder["u_unravel"].batched(ut)
+        return ut, S, v_unravel.batched(vt)
 
     return svd

@@ -165,10 +165,10 @@ def monte_carlo_funm_sym(dense_funm, tridiag_sym, /):
     def quadform(matvec, v0, *parameters):
         if spec is None or matfun is None:
             return _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters)
-        if parameters:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
-        op = ops.require_operator(matvec, "monte_carlo_funm_sym")
-        v = _device.as_device(v0, op.dtype).reshape(-1)
+        from matfree_b200 import _generic
+
+        # funm.py:226-235: any pytree `v0`, any callable `matvec(v0, *parameters)`
+        op, v, _ = _generic.wrap(matvec, v0, parameters)
         k = spec["num_matvecs"]
         n_total = getattr(op, "n_global", v.shape[0])
         if k < 0 or k > n_total:
@@ -187,9 +187,16 @@ def _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters):
     # funm.py:226-241 with user-supplied pieces (device tensors)
     import torch
 
-    v0 = _device.as_device(v0).reshape(-1)
-    length = torch.linalg.vector_norm(v0)
-    _, dense, *_ = tridiag_sym(matvec, v0 / length, *parameters)
+    from matfree_b200.backend import tree
+
+    v0_flat, unravel = tree.ravel_pytree(v0)
+    length = torch.linalg.vector_norm(v0_flat)
+
+    def matvec_flat(v_f, *p):
+        return tree.ravel_pytree(matvec(unravel(v_f), *p))[0]
+
+    mv = matvec if isinstance(matvec, ops.Operator) else matvec_flat
+    _, dense, *_ = tridiag_sym(mv, v0_flat / length, *parameters)
     fA = dense_funm(dense)
     return length**2 * fA[0, 0]
 
@@ -248,24 +255,26 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
     def _use_two_pass(op, known):
         from matfree_b200 import _rowshard
 
+        from matfree_b200 import _generic
+
         return (known is not None and spec["reortho"] == "none" and spec["num_matvecs"] >= 1
-                and not isinstance(op, _rowshard.RowShardedCsr))
+                and not isinstance(op, (_rowshard.RowShardedCsr, _generic.CallableOperator)))
 
     def estimate(matvec, vec, *parameters):
         import torch
 
-        if parameters:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
+        from matfree_b200 import _generic
+
         if spec is None:
             raise TypeError("funm_lanczos_sym: tridiag_sym must come from matfree_b200.decomp.tridiag_sym")
-        op = ops.require_operator(matvec, "funm_lanczos_sym")
+        # funm.py:136-145: any pytree `vec`, any callable `matvec(vec, *parameters)`
+        op, v, unravel = _generic.wrap(matvec, vec, parameters)
         lib = _lib.load()
-        v = _device.as_device(vec, op.dtype).reshape(-1)
         n = v.shape[0]
         k = _check(op, n)
         known = _known()
         if _use_two_pass(op, known):
-            return _two_pass_blocked(op, v.reshape(n, 1).contiguous(), 1, known)[:, 0]
+            return unravel(_two_pass_blocked(op, v.reshape(n, 1).contiguous(), 1, known)[:, 0])
         alphas, betas, init_len, Q, _ = decomp.lanczos_blocked(
             op, v.reshape(n, 1), k, spec["reortho"], want_Q=True, want_residual=False)
         ld = 1
@@ -278,12 +287,13 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
                                               ws.numel(), _device.stream()))
         else:
             T = decomp._todense_tridiag_sym(alphas[:, 0], betas[: k - 1, 0])
-            coeffs = dense_funm(T)[:, 0].reshape(k, 1).contiguous()
+            coeffs = _device.as_device(dense_funm(T), op.dtype)[:, 0].reshape(k, 1).contiguous()
         out = torch.empty((n, ld), dtype=op.dtype, device=v.device)
-        _lib.check(lib.mf_basis_combine(Q.data_ptr(), coeffs.data_ptr(), init_len.data_ptr(),
+        Qc = Q if Q.is_contiguous() else Q.contiguous()
+        _lib.check(lib.mf_basis_combine(Qc.data_ptr(), coeffs.data_ptr(), init_len.data_ptr(),
                                         _device.mf_dtype(op.dtype), n, ld, k, out.data_ptr(),
                                         _device.stream()))
-        return out[:, 0]
+        return unravel(out[:, 0])
 
     def batched(matvec, V, *, tile=None):
         """``f(A) V[p]`` for every row of ``V (P, n)``; returns ``(P, n)``."""
@@ -327,6 +337,91 @@ def funm_lanczos_sym(dense_funm, tridiag_sym, /):
     estimate.batched = batched
     estimate.blocked = blocked
     return estimate
+
+
+def funm_arnoldi(dense_funm, hessenberg, /):
+    """Matrix-function-vector product ``f(A) v`` via the Arnoldi iteration, for arbitrary square
+    operators (`funm.py:150-183`): ``|v| Q^T f(H) e1`` with `decomp.hessenberg`'s ``(Q, H)``.
+    The small ``k x k`` function is `dense_funm` (`dense_funm_schur`, `dense_funm_pade_exp`, ...);
+    the combination with the stored basis is `mf_basis_combine`."""
+
+    def estimate(matvec, vec, *parameters):
+        import torch
+
+        from matfree_b200 import _generic
+        from matfree_b200.backend import tree
+
+        vec_flat, unravel = tree.ravel_pytree(vec, matvec.dtype if isinstance(matvec, ops.Operator) else None)
+        length = torch.linalg.vector_norm(vec_flat)
+
+        def matvec_flat(v_f, *p):
+            return tree.ravel_pytree(matvec(unravel(v_f), *p))[0]
+
+        mv = matvec if isinstance(matvec, ops.Operator) else matvec_flat
+        basis, matrix, *_ = hessenberg(mv, vec_flat / length, *parameters)   # funm.py:177
+        dt = vec_flat.dtype
+        fH = _device.as_device(dense_funm(matrix), dt)                       # :178
+        k, n = basis.shape
+        coeffs = fH[:, 0].reshape(k, 1).contiguous()                          # f(H) e1, :179
+        out = torch.empty((n, 1), dtype=dt, device=vec_flat.device)
+        Q = basis.reshape(k, n, 1).contiguous()
+        scale = length.reshape(1).to(dt).contiguous()
+        _lib.check(_lib.load().mf_basis_combine(Q.data_ptr(), coeffs.data_ptr(), scale.data_ptr(),
+                                                _device.mf_dtype(dt), n, 1, k, out.data_ptr(),
+                                                _device.stream()))
+        return unravel(out[:, 0])                                             # :181
+
+    return estimate
+
+
+def dense_funm_schur(matfun):
+    """Dense matrix function of a (possibly non-symmetric) small matrix (`funm.py:338-347`,
+    `linalg.funm_schur` = `jax.scipy.linalg.funm`: Schur-Parlett).  The ``k x k`` factor is
+    evaluated on the host with SciPy's Schur-Parlett `funm`, like the reference's LAPACK call."""
+
+    def fun(dense_matrix):
+        import scipy.linalg
+        import torch
+
+        M = _device.as_device(dense_matrix)
+        H = M.detach().cpu().numpy().astype(np.float64)
+
+        def f(x):
+            return np.asarray(_apply_matfun_host(matfun, x))
+
+        out = scipy.linalg.funm(H, f, disp=True)
+        return torch.as_tensor(np.real(out), device=M.device).to(M.dtype)
+
+    fun._mf_matfun = matfun
+    return fun
+
+
+def _apply_matfun_host(matfun, x):
+    known = _known_fn(matfun) if not callable(matfun) or _is_hashable(matfun) else None
+    if known is not None:
+        fn, param = known
+        return {_lib.MF_FN_LOG: np.log, _lib.MF_FN_EXP: lambda t: np.exp(param * t),
+                _lib.MF_FN_INV: lambda t: 1.0 / t, _lib.MF_FN_SQRT: np.sqrt,
+                _lib.MF_FN_POW: lambda t: t ** param, _lib.MF_FN_IDENTITY: lambda t: t,
+                _lib.MF_FN_SIN: lambda t: np.sin(param * t)}[fn](x)
+    try:
+        return np.asarray(matfun(x))
+    except Exception:
+        import torch
+
+        return matfun(torch.as_tensor(x)).numpy()
+
+
+def dense_funm_pade_exp():
+    """Dense matrix exponential by a Pade approximation (`funm.py:350-359`,
+    `jax.scipy.linalg.expm`); `torch.linalg.matrix_exp` on the small ``k x k`` factor."""
+
+    def fun(dense_matrix):
+        import torch
+
+        return torch.linalg.matrix_exp(_device.as_device(dense_matrix))
+
+    return fun
 
 
 # ---------------------------------------------------------------- products A^T A (bidiag)
@@ -383,16 +478,25 @@ def monte_carlo_funm_product(dense_funm, bidiag, /):
     def quadform(matvec, v0, *parameters):
         import torch
 
-        if not fusable:
-            v = _device.as_device(v0).reshape(-1)
+        from matfree_b200.backend import tree
+
+        if not fusable or not isinstance(matvec, ops.Operator):
+            # funm.py:287-300 with user-supplied pieces: pytree in, (possibly different) pytree out
+            v, unravel = tree.ravel_pytree(v0)
             length = torch.linalg.vector_norm(v)
-            _, B, *_ = bidiag(matvec, v / length, *parameters)
+
+            def matvec_flat(v_f, *p):
+                return tree.ravel_pytree(matvec(unravel(v_f), *p))[0]
+
+            mv = matvec if isinstance(matvec, ops.Operator) else matvec_flat
+            _, B, *_ = bidiag(mv, v / length, *parameters)
             return length**2 * dense_funm(B)[0, 0]
         if parameters:
-            raise TypeError("registered operators carry their own buffers; extra matvec parameters are not supported")
-        op = ops.require_operator(matvec, "monte_carlo_funm_product")
+            raise TypeError("registered operators carry their own buffers; extra matvec parameters "
+                            "are only supported for callables")
+        op = matvec
         if not isinstance(op, ops.RectOperator):
-            raise TypeError("monte_carlo_funm_product: matvec must be ops.rect(A)")
+            raise TypeError("monte_carlo_funm_product: a registered matvec must be ops.rect(A)")
         v = _device.as_device(v0, op.dtype).reshape(-1)
         k = spec["num_matvecs"]
         if k > min(op.m, op.n) or k < 0:

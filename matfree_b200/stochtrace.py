@@ -31,7 +31,7 @@ import ctypes
 
 import numpy as np
 
-from matfree_b200 import _device, _lib, _sharding, funm as _funm, ops
+from matfree_b200 import _device, _lib, _sharding, config as _config, funm as _funm, ops
 
 _PROBE_GROUP = {"group": None, "enabled": False}
 
@@ -74,9 +74,117 @@ def _flat_like(*args_like):
     return n, (torch.float64 if is64 else torch.float32)
 
 
+def _row_sharded(matvec):
+    from matfree_b200 import _rowshard
+
+    return isinstance(matvec, _rowshard.RowShardedCsr)
+
+
+def _gen_tile(V, op, sspec, key, t0, npb):
+    """Probes ``t0 .. t0+npb-1`` of the sampler's ``(num, n)`` array into the blocked tile
+    ``V[rows][ld]``: all rows for an ordinary operator, this rank's slab of rows for a row-sharded
+    one (`mf_probe_gen_rows`: counter ``p * n_global + row`` -- the same stream, so the estimate
+    does not depend on how the rows are partitioned)."""
+    lib = _lib.load()
+    rows, ld = V.shape
+    mfdt = _device.mf_dtype(V.dtype)
+    flags = _config.prng_flags(V.dtype)
+    if _row_sharded(op):
+        _lib.check(lib.mf_probe_gen_rows(V.data_ptr(), mfdt, op.n_global, op.r0, rows, ld, t0, npb,
+                                         int(key[0]), int(key[1]), sspec["kind"], flags,
+                                         _device.stream()))
+    else:
+        _lib.check(lib.mf_probe_gen(V.data_ptr(), mfdt, _lib.MF_LAYOUT_BLOCKED, rows, ld, t0, npb,
+                                    int(key[0]), int(key[1]), sspec["kind"], flags, None,
+                                    _device.stream()))
+
+
+def _sharded_values(ispec, sspec, op, key, *, tile=None, return_coeffs=False):
+    """Per-probe SLQ / Hutchinson-trace values on a ROW-SHARDED operator (rows and vectors
+    partitioned over the ranks of ``op.group``; every rank evaluates every probe on its slab):
+    slab probe generation -> `decomp.lanczos_blocked` (the sharded driver: halo exchange, sums
+    all-reduced over peer memory or NCCL) -> `funm.quadrature_blocked`.  Collective call."""
+    import torch
+
+    from matfree_b200 import _rowshard, decomp
+
+    n, P, dt = sspec["n"], sspec["num"], op.dtype
+    if n != op.n_global:
+        raise ValueError(f"sampler draws vectors of length {n}, operator dimension is {op.n_global}")
+    if sspec["dtype"] != dt:
+        raise TypeError(f"sampler dtype {sspec['dtype']} does not match operator dtype {dt}")
+    dev = _device.device()
+    slq = ispec["kind"] != "trace"
+    if slq:
+        k = ispec["num_matvecs"]
+        if k < 0 or k > n:
+            raise ValueError(decomp._error_num_matvecs(k, maxval=n, minval=0))
+        if k < 1:
+            raise ValueError("the SLQ integrand needs num_matvecs >= 1")
+    ld = int(tile) if tile else _device.ld_for(max(P, 1))
+    if slq and ispec["reortho"] == "full":
+        ld = _cap_tile_for_basis(ld, ispec["num_matvecs"], op.plan.rows_alloc, dt)
+    V = torch.empty((op.n, ld), dtype=dt, device=dev)
+    parts, coeffs = [], []
+    be = _rowshard.CudaBackend(ld)
+    for t0 in range(0, P, ld):
+        npb = min(ld, P - t0)
+        _gen_tile(V, op, sspec, key, t0, npb)
+        if npb < ld:
+            V[:, npb:] = 1.0  # padding columns: any non-zero vector keeps the recurrence finite
+        if not slq:
+            W = op.matmat_blocked(V)
+            sums = torch.empty((ld,), dtype=torch.float64, device=dev)
+            be.block_dot(V, W, sums)
+            _rowshard._all_reduce(sums, op.group)
+            parts.append(sums[:npb].to(dt))
+            continue
+        alphas, betas, init_len, _, _ = decomp.lanczos_blocked(
+            op, V, ispec["num_matvecs"], ispec["reortho"], want_Q=False, want_residual=False)
+        parts.append(_funm.quadrature_blocked(alphas, betas, init_len, npb, ispec["matfun"]))
+        if return_coeffs:
+            coeffs.append((alphas.clone(), betas.clone(), init_len.clone()))
+    vals = torch.cat(parts) if parts else torch.empty((0,), dtype=dt, device=dev)
+    if return_coeffs:
+        if not coeffs:
+            return vals, None, None, None
+        return (vals, torch.stack([c[0] for c in coeffs]), torch.stack([c[1] for c in coeffs]),
+                torch.stack([c[2] for c in coeffs]))
+    return vals
+
+
+def _cap_tile_for_basis(ld, k, rows, dtype):
+    """Narrow the probe tile until the stored basis ``Q[k][rows][ld]`` of a full
+    re-orthogonalisation fits in (60 % of) the free device memory."""
+    import torch
+
+    es = torch.empty((), dtype=dtype).element_size()
+    free, _ = torch.cuda.mem_get_info()
+    while ld > 1 and (k + 4) * rows * ld * es > 0.6 * free:
+        ld //= 2
+    return ld
+
+
+
 def _make_sampler(kind: int, args_like, num: int):
+    from matfree_b200.backend import tree
+
     n, dtype = _flat_like(*args_like)
     num = int(num)
+    template = args_like[0] if len(args_like) == 1 else list(args_like)
+    # stochtrace.py:957-964: one (num, n) draw, then vmap(unflatten) -- shapes only, no data
+    shapes = tree.leaf_shapes(template)
+    is_flat = tree.is_leaf(template) and len(shapes[0]) <= 1
+
+    def unflatten_batched(mat):
+        if is_flat:
+            return mat
+        parts, off = [], 0
+        for shape in shapes:
+            size = int(np.prod(shape)) if shape else 1
+            parts.append(mat[:, off:off + size].reshape((mat.shape[0],) + shape))
+            off += size
+        return tree._rebuild(template, iter(parts))
 
     def sample(key):
         import torch
@@ -85,8 +193,9 @@ def _make_sampler(kind: int, args_like, num: int):
         out = torch.empty((num, n), dtype=dtype, device=_device.device())
         _lib.check(lib.mf_probe_gen(out.data_ptr(), _device.mf_dtype(dtype),
                                     _lib.MF_LAYOUT_PROBE_MAJOR, n, n, 0, num, int(key[0]),
-                                    int(key[1]), kind, 0, None, _device.stream()))
-        return out
+                                    int(key[1]), kind, _config.prng_flags(dtype), None,
+                                    _device.stream()))
+        return unflatten_batched(out)
 
     shape = None  # a single array-like keeps its shape in per-row outputs (ravel_pytree's unflatten)
     if len(args_like) == 1 and not isinstance(args_like[0], (dict, list, tuple)):
@@ -112,12 +221,23 @@ def monte_carlo_trace():
     def integrand(matvec, v, *parameters):
         import torch
 
-        v = _device.as_device(v).reshape(-1)
-        Qv = matvec(v, *parameters)
-        return torch.dot(v, _device.as_device(Qv, v.dtype).reshape(-1))
+        v_flat, Qv_flat, _ = _apply_flat(matvec, v, parameters)
+        return torch.dot(v_flat, Qv_flat)
 
     integrand._mf_integrand = {"kind": "trace"}
     return integrand
+
+
+def _apply_flat(matvec, v, parameters):
+    """``(v_flat, (A v)_flat, unravel)`` for a pytree `v` (`stochtrace.py:844-847,859-863`)."""
+    from matfree_b200.backend import tree
+
+    if isinstance(matvec, ops.Operator):
+        v_flat, unravel = tree.ravel_pytree(v, matvec.dtype)
+        return v_flat, matvec(v_flat, *parameters).reshape(-1), unravel
+    v_flat, unravel = tree.ravel_pytree(v)
+    Qv_flat, _ = tree.ravel_pytree(matvec(v, *parameters), v_flat.dtype)
+    return v_flat, Qv_flat, unravel
 
 
 def _unflatten_like(flat, like):
@@ -131,9 +251,8 @@ def monte_carlo_diagonal():
     """Integrand ``v * (A v)`` (`stochtrace.py:836-849`): its mean estimates ``diag(A)``."""
 
     def integrand(matvec, v, *parameters):
-        v = _device.as_device(v)
-        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
-        return (v.reshape(-1) * Qv).reshape(v.shape)
+        v_flat, Qv_flat, unravel = _apply_flat(matvec, v, parameters)
+        return unravel(v_flat * Qv_flat)
 
     integrand._mf_integrand = {"kind": "diagonal"}
     return integrand
@@ -145,9 +264,8 @@ def monte_carlo_trace_and_diagonal():
     def integrand(matvec, v, *parameters):
         import torch
 
-        v = _device.as_device(v)
-        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
-        return {"trace": torch.dot(v.reshape(-1), Qv), "diagonal": (v.reshape(-1) * Qv).reshape(v.shape)}
+        v_flat, Qv_flat, unravel = _apply_flat(matvec, v, parameters)
+        return {"trace": torch.dot(v_flat, Qv_flat), "diagonal": unravel(v_flat * Qv_flat)}
 
     integrand._mf_integrand = {"kind": "trace_and_diagonal"}
     return integrand
@@ -158,9 +276,8 @@ def monte_carlo_rownorms_squared():
     row norms of ``A``."""
 
     def integrand(matvec, v, *parameters):
-        v = _device.as_device(v)
-        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
-        return (Qv * Qv).reshape(v.shape)
+        _, Qv_flat, unravel = _apply_flat(matvec, v, parameters)
+        return unravel(Qv_flat * Qv_flat)
 
     integrand._mf_integrand = {"kind": "rownorms_squared"}
     return integrand
@@ -172,9 +289,8 @@ def monte_carlo_frobeniusnorm_squared():
     def integrand(matvec, v, *parameters):
         import torch
 
-        v = _device.as_device(v)
-        Qv = _device.as_device(matvec(v.reshape(-1), *parameters), v.dtype).reshape(-1)
-        return torch.dot(Qv, Qv)
+        _, Qv_flat, _ = _apply_flat(matvec, v, parameters)
+        return torch.dot(Qv_flat, Qv_flat)
 
     integrand._mf_integrand = {"kind": "frobeniusnorm_squared"}
     return integrand
@@ -223,7 +339,8 @@ def _product_values(integrand, sampler, matvec, key, parameters, *, tile=None):
     for t0 in range(p0, p1, ld):
         npb = min(ld, p1 - t0)
         _lib.check(lib.mf_probe_gen(V.data_ptr(), mfdt, _lib.MF_LAYOUT_BLOCKED, n, ld, t0, npb,
-                                    int(key[0]), int(key[1]), sspec["kind"], 0, None, _device.stream()))
+                                    int(key[0]), int(key[1]), sspec["kind"],
+                                    _config.prng_flags(dt), None, _device.stream()))
         if npb < ld:
             V[:, npb:] = 1.0  # padding columns: any non-zero vector keeps the recurrence finite
         alphas, betas, init_len, *_ = decomp.bidiag_blocked(op, V, k, ispec["reortho"])
@@ -251,14 +368,17 @@ def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None)
     op = matvec
     kind = ispec["kind"]
     n, P, dt = sspec["n"], sspec["num"], op.dtype
-    if n != op.n:
-        raise ValueError(f"sampler draws vectors of length {n}, operator dimension is {op.n}")
+    sharded = _row_sharded(op)  # rows partitioned over op.group: every rank sees every probe
+    n_total = op.n_global if sharded else op.n
+    if n != n_total:
+        raise ValueError(f"sampler draws vectors of length {n}, operator dimension is {n_total}")
+    n = op.n  # rows held by this rank
     if sspec["dtype"] != dt:
         raise TypeError(f"sampler dtype {sspec['dtype']} does not match operator dtype {dt}")
     dev = _device.device()
     mfdt = _device.mf_dtype(dt)
     p0, p1, group, world = 0, P, None, 1
-    if _PROBE_GROUP["enabled"]:
+    if _PROBE_GROUP["enabled"] and not sharded:
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized():
@@ -276,8 +396,7 @@ def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None)
     first = True
     for t0 in range(p0, p1, ld):
         npb = min(ld, p1 - t0)
-        _lib.check(lib.mf_probe_gen(V.data_ptr(), mfdt, _lib.MF_LAYOUT_BLOCKED, n, ld, t0, npb,
-                                    int(key[0]), int(key[1]), sspec["kind"], 0, None, _device.stream()))
+        _gen_tile(V, op, sspec, key, t0, npb)
         W = op.matmat_blocked(V)
         if want_rows:
             A = W if kind == "rownorms_squared" else V
@@ -288,6 +407,10 @@ def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None)
             sums = torch.empty((ld,), dtype=torch.float64, device=dev)
             _lib.check(lib.mf_block_dot(A.data_ptr(), W.data_ptr(), mfdt, n, ld, sums.data_ptr(),
                                         bws.data_ptr(), bws.numel(), _device.stream()))
+            if sharded:  # column sums run over all rows: add the other slabs' parts
+                from matfree_b200 import _rowshard
+
+                _rowshard._all_reduce(sums, op.group)
             colvals.append(sums[:npb].to(dt))
         first = False
     out_mean, out_sem = {}, {}
@@ -298,7 +421,7 @@ def _hutchinson_block(integrand, sampler, matvec, key, parameters, *, tile=None)
             dist.all_reduce(rows, group=group)
         mean = rows[0] / P
         var = torch.clamp(rows[1] / P - mean * mean, min=0.0)
-        like = sspec.get("shape")
+        like = None if sharded else sspec.get("shape")  # sharded: this rank's slab of rows
         out_mean["rows"] = _unflatten_like(mean.to(dt), like)
         out_sem["rows"] = _unflatten_like((torch.sqrt(var) / np.sqrt(P)).to(dt), like)
     if want_cols:
@@ -327,6 +450,9 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
         return None  # handled by _hutchinson_block
     if ispec["kind"] == "product":
         return _product_values(integrand, sampler, matvec, key, parameters, tile=tile)
+    if _row_sharded(matvec):
+        # the single-GPU kernels of mf_estimate know nothing about halos or slabs
+        return _sharded_values(ispec, sspec, matvec, key, tile=tile, return_coeffs=return_coeffs)
     import torch
 
     lib = _lib.load()
@@ -369,6 +495,8 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
             raise ValueError(decomp._error_num_matvecs(k, maxval=op.n, minval=0))
 
     ld = int(tile) if tile else _device.ld_for(max(nloc, 1))
+    if not tile and rflag == _lib.MF_REORTHO_FULL and integ == _lib.MF_INTEGRAND_SLQ:
+        ld = _cap_tile_for_basis(ld, k, op.n, dt)
     ntiles = max(1, -(-nloc // ld))
     st = op._struct()
     ws_bytes = lib.mf_estimate_workspace_bytes(ctypes.byref(st), ld, k, rflag, integ)
@@ -383,7 +511,8 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
         betas = torch.empty((ntiles, k, ld), dtype=dt, device=dev)
         lens = torch.empty((ntiles, ld), dtype=dt, device=dev)
     if nloc > 0:
-        _lib.check(lib.mf_estimate(ctypes.byref(st), integ, sspec["kind"], 0, int(key[0]),
+        _lib.check(lib.mf_estimate(ctypes.byref(st), integ, sspec["kind"],
+                                   _config.prng_flags(dt), int(key[0]),
                                    int(key[1]), p0, nloc, ld, k, rflag,
                                    _lib.MF_FN_NONE if host_fn is not None else fn, param,
                                    quad.data_ptr(),
@@ -418,22 +547,27 @@ def _reduce(values):
     return stats[0].to(values.dtype), stats[2].to(values.dtype)
 
 
-def _tree_map(fn, tree):
-    if isinstance(tree, dict):
-        return {k: _tree_map(fn, v) for k, v in tree.items()}
-    return fn(tree)
+def _tree_map(fn, pytree):
+    from matfree_b200.backend import tree
+
+    return tree.tree_map(fn, pytree)
 
 
 def _generic_values(integrand, sampler, matvecs, key, parameters):
-    """Sample-by-sample evaluation of a user integrand (any callable, dict outputs allowed):
-    the reference's `vmap` (`stochtrace.py:49`) as a loop; stacked along a leading sample axis."""
+    """Sample-by-sample evaluation of a user integrand (any callable, pytree samples and
+    outputs allowed): the reference's `vmap` (`stochtrace.py:49`) as a loop; stacked along a
+    leading sample axis."""
     import torch
 
+    from matfree_b200.backend import tree
+
     samples = sampler(key)
-    vals = [integrand(matvecs, s, *parameters) for s in samples]
-    if vals and isinstance(vals[0], dict):
-        return {k: torch.stack([_device.as_device(v[k]) for v in vals]) for k in vals[0]}
-    return torch.stack([_device.as_device(v) for v in vals])
+    leaves = tree.tree_leaves(samples)
+    num = int(leaves[0].shape[0]) if leaves else 0
+    vals = [integrand(matvecs, tree.tree_map(lambda x: x[p], samples), *parameters) for p in range(num)]
+    per_sample = [[_device.as_device(x) for x in tree.tree_leaves(v)] for v in vals]
+    stacked = [torch.stack([ps[i] for ps in per_sample]) for i in range(len(per_sample[0]))]
+    return tree._rebuild(vals[0], iter(stacked))
 
 
 def estimator_monte_carlo(integrand, /, sampler):

@@ -129,14 +129,21 @@ def uniform(key, shape=(), dtype=np.float32, *, mode: str = "partitionable", off
 
 
 def rademacher(key, shape, dtype=np.float32, *, mode: str = "partitionable",
-               x64: bool = False, offset: int = 0):
+               x64=None, offset: int = 0):
     """`jax.random.rademacher`: ``2*bernoulli(key, 0.5) - 1`` cast to `dtype`.
 
     ``bernoulli`` is ``uniform(key, shape, float_default) < 0.5`` so ``+1`` iff
     the top mantissa bit of the uniform is 0, i.e. iff the MSB of the draw is 0.
     With `jax_enable_x64` the comparison is done on a float64 uniform, which
     consumes a 64-bit draw whose MSB is the MSB of ``x0``.
+
+    ``x64=None`` (default) means "the mode in which the reference can produce `dtype`": a
+    float64 sample only exists under `jax_enable_x64`, so float64 -> x64 stream, float32 -> x32
+    stream.  Pinned for the x32 stream by the reference's README doctest
+    (`tests/golden/readme_doctest.json`).
     """
+    if x64 is None:
+        x64 = np.dtype(dtype) == np.float64
     if x64:
         bits = random_bits(key, shape, bit_width=64, mode=mode, offset=offset)
         neg = (bits >> np.uint64(63)).astype(np.int8)

@@ -144,7 +144,10 @@ def _tridiag_reortho_full(num_matvecs, *, materialize):
         matrix = (diags, offdiags)
         if materialize:
             matrix = todense_tridiag_sym(diags, offdiags)
-        return DecompResult(Q.T, matrix, v, c)  # Q transposed at :388
+        # :132,142 -- `norm` is hessenberg's init_length_inv = 1/|v| and the result is built with
+        # `init_length_inv=1.0 / norm`: the full variant returns the LENGTH, not its inverse
+        # (an upstream quirk; `reortho="none"` returns 1/|v|, :177).  Restated as is.
+        return DecompResult(Q.T, matrix, v, vec.dtype.type(1.0) / c)  # Q transposed at :388
 
     return estimate
 
@@ -217,7 +220,7 @@ def funm_lanczos_sym(dense_funm, tridiag, /):
 # --------------------------------------------------------------------------
 
 
-def sampler_signs(n, *, num, dtype=np.float32, mode="partitionable", x64=False):
+def sampler_signs(n, *, num, dtype=np.float32, mode="partitionable", x64=None):
     """`matfree/stochtrace.py:932-937,957-977` for a flat real vector of length n."""
 
     def sample(key, p0=0, p1=None):
@@ -489,13 +492,18 @@ def monte_carlo_funm_product_schatten_norm(power, bidiag_alg, /):
     return monte_carlo_funm_product(dense_funm_product_svd(lambda x: x ** (power / 2)), bidiag_alg)
 
 
-def hessenberg(num_matvecs, /, *, reortho):
-    """`matfree/decomp.py:351-477` (forward pass): returns ``(Q (k, n), H, residual, 1/|v|)``."""
+def hessenberg(num_matvecs, /, *, reortho, reortho_vjp="match"):
+    """`matfree/decomp.py:351-477` (forward pass): returns ``(Q (k, n), H, residual, 1/|v|)``.
+
+    The forward pass is called with ``reortho=reortho_vjp`` (`decomp.py:393-396`), whose default
+    is the string "match": `_hessenberg_forward_step` only tests ``reortho != "none"`` (`:466`),
+    so the second Gram-Schmidt pass runs unless ``reortho_vjp == "none"`` -- also for
+    ``reortho="none"``, which only selects the adjoint's re-projection.  Restated as is."""
     if reortho not in ("none", "full"):
         raise TypeError(f"Unexpected input for {reortho}: either of {['none', 'full']} expected.")
 
     def estimate(matvec, v):
-        Q, H, r, c = _hessenberg_forward(matvec, num_matvecs, np.asarray(v), reortho=reortho)
+        Q, H, r, c = _hessenberg_forward(matvec, num_matvecs, np.asarray(v), reortho=reortho_vjp)
         return Q.T, H, r, c
 
     return estimate

@@ -67,19 +67,20 @@ def test_svd_partial_equal_to_linalg_svd(dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("reortho", ["full", "none"])
+@pytest.mark.parametrize("reortho,reortho_vjp", [("full", "match"), ("none", "match"), ("none", "none")])
 @pytest.mark.parametrize("n,k", [(12, 7), (300, 24), (64, 64)])
-def test_hessenberg_decomposition_nonsymmetric(dtype, reortho, n, k):
+def test_hessenberg_decomposition_nonsymmetric(dtype, reortho, reortho_vjp, n, k):
     """decomp.hessenberg on a NON-symmetric dense operator: A Q^T = Q^T H + r e_k^T, orthonormal Q,
     upper-Hessenberg H, and the same H as the oracle (tests/test_decomp/test_hessenberg.py)."""
     m = mfb()
     A = (oprng.normal(oprng.prng_key(1), (n, n), dtype) / np.sqrt(n)).astype(dtype)
     v = oprng.normal(oprng.prng_key(2), (n,), dtype)
-    Q, H, r, c = m.decomp.hessenberg(k, reortho=reortho)(m.ops.dense(A), v)
+    # the forward pass re-orthogonalises unless reortho_vjp == "none" (decomp.py:393-396,466)
+    Q, H, r, c = m.decomp.hessenberg(k, reortho=reortho, reortho_vjp=reortho_vjp)(m.ops.dense(A), v)
     Q, H, r = (x.cpu().numpy().astype(np.float64) for x in (Q, H, r))
     assert Q.shape == (k, n) and H.shape == (k, k)
     tol = 2e-5 if dtype == np.float32 else 1e-11
-    if reortho == "full" or k < 30:
+    if reortho_vjp != "none" or k < 30:
         assert np.abs(Q @ Q.T - np.eye(k)).max() < 20 * tol
     assert np.abs(np.tril(H, -2)).max() == 0.0
     ek = np.eye(k)[:, -1]
@@ -87,7 +88,8 @@ def test_hessenberg_decomposition_nonsymmetric(dtype, reortho, n, k):
     assert np.abs(Ad @ Q.T - Q.T @ H - np.outer(r, ek)).max() < 20 * tol
     assert np.allclose(float(c), 1 / np.linalg.norm(v.astype(np.float64)), rtol=1e-6)
     if k <= 24:
-        oQ, oH, orr, oc = ref.hessenberg(k, reortho=reortho)(lambda x: Ad @ x, v.astype(np.float64))
+        oQ, oH, orr, oc = ref.hessenberg(k, reortho=reortho, reortho_vjp=reortho_vjp)(
+            lambda x: Ad @ x, v.astype(np.float64))
         assert np.abs(H - oH).max() < 200 * tol
 
 

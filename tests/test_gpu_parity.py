@@ -61,6 +61,37 @@ def test_sampler_signs_bit_exact(dtype, n, num):
     assert np.array_equal(got, want)
 
 
+def test_sampler_signs_x64_stream_and_config_switch():
+    """`jax_enable_x64` changes the Rademacher stream (64-bit draw, sign = MSB of x0;
+    /root/reference/matfree/backend/prng.py:26-29): float64 samplers draw it by
+    default, `config.update("jax_enable_x64", ...)` forces either stream for every dtype -- in the
+    materialised sampler AND in the fused estimator (`mf_estimate`, probes never materialised)."""
+    m = mfb()
+    key, okey = m.prng.prng_key(1), oprng.prng_key(1)
+    n, num = 515, 37
+    want64 = oprng.rademacher(okey, (num, n), np.float64, x64=True)
+    want32 = oprng.rademacher(okey, (num, n), np.float64, x64=False)
+    assert not np.array_equal(want64, want32)
+    assert np.array_equal(to_np(m.stochtrace.sampler_signs(np.ones(n, np.float64), num=num)(key)), want64)
+    As = lap_scipy((5, 103), 1.0, np.float64)
+    op = m.ops.csr_from_scipy(As)
+    trace = m.stochtrace.monte_carlo_trace()
+    try:
+        for flag, dt, want in ((True, np.float32, want64), (False, np.float64, want32), (None, np.float64, want64),
+                               (None, np.float32, want32)):
+            m.config.update("jax_enable_x64", flag)
+            s = m.stochtrace.sampler_signs(np.ones(n, dt), num=num)
+            assert np.array_equal(to_np(s(key)), want.astype(dt)), (flag, dt)
+            assert np.array_equal(to_np(m.prng.rademacher(key, shape=(num, n), dtype=dt)), want.astype(dt))
+            # fused route: per-probe v^T A v from in-kernel probes == the same from the oracle's probes
+            opd = op if dt == np.float64 else m.ops.csr_from_scipy(As.astype(np.float32))
+            got = to_np(m.stochtrace.estimator_monte_carlo(trace, s).per_probe(opd, key))
+            ref_vals = np.einsum("pn,pn->p", want, (As @ want.T).T)
+            assert np.allclose(got, ref_vals, rtol=1e-6 if dt == np.float32 else 1e-13), (flag, dt)
+    finally:
+        m.config.update("jax_enable_x64", None)
+
+
 @pytest.mark.parametrize("n,num", [(5, 7), (1000, 33)])
 def test_sampler_normal_fp32(n, num):
     m = mfb()
@@ -165,7 +196,8 @@ def test_tridiag_full_rank_reconstructs(reortho, kind):
     tol = 1e-5 if reortho == "full" else 1e-1
     assert np.allclose(Q @ Q.T, np.eye(n), atol=tol)
     assert np.allclose(Q.T @ T @ Q, A, atol=tol * n)
-    assert np.allclose(c, 1 / np.linalg.norm(v))
+    # /root/reference/matfree/decomp.py:142 vs :177 -- "full" returns |v| (1/(1/|v|)), "none" 1/|v|
+    assert np.allclose(c, np.linalg.norm(v) if reortho == "full" else 1 / np.linalg.norm(v))
 
 
 # tests/test_decomp/test_tridiag_sym.py:43-65

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.mf_abi_version() == 3
+    assert lib.mf_abi_version() == 4
     assert lib.mf_launch_count() == 0
 
 
@@ -195,3 +195,30 @@ def test_sharded_entry_points_validate_without_gpu():
     h = ctypes.c_void_p()
     with pytest.raises(ValueError, match="world must be"):
         _lib.check(lib.mf_comm_create(9, 0, 0, ctypes.byref(h)))
+
+
+def test_ravel_pytree_matches_jax_flattening_order():
+    """`matfree/backend/tree.py:15-20` (jax.flatten_util.ravel_pytree): dict keys in sorted order,
+    sequences in order, leaves raveled row-major; unravel and its batched form invert it."""
+    import torch
+
+    from matfree_b200.backend import tree
+
+    t = {"b": np.arange(6.0).reshape(2, 3), "a": [(np.array([10.0, 11.0]),), np.float64(7.0)]}
+    flat, unravel = tree.ravel_pytree(t, device="cpu")
+    assert flat.tolist() == [10.0, 11.0, 7.0, 0.0, 1.0, 2.0, 3.0, 4.0, 5.0]
+    back = unravel(flat)
+    assert list(back) == ["b", "a"] and tuple(back["b"].shape) == (2, 3) and back["a"][1].shape == ()
+    assert torch.equal(back["a"][0][0], torch.tensor([10.0, 11.0], dtype=torch.float64))
+    rows = torch.stack([flat, 2 * flat])
+    bb = unravel.batched(rows)
+    assert tuple(bb["b"].shape) == (2, 2, 3) and torch.equal(bb["b"][1], 2 * back["b"])
+    # the reference tests' vector pytree `[(v,)]` (tests/test_decomp/test_tridiag_sym.py:19-22)
+    flat2, unravel2 = tree.ravel_pytree([(np.ones(4, np.float32),)], device="cpu")
+    [(x,)] = unravel2(flat2)
+    assert tuple(x.shape) == (4,) and flat2.dtype == torch.float32
+    [(xb,)] = unravel2.batched(torch.zeros(3, 4))
+    assert tuple(xb.shape) == (3, 4)
+    # a flat array is its own pytree
+    flat3, unravel3 = tree.ravel_pytree(np.ones(5, np.float32), device="cpu")
+    assert unravel3.trivial and unravel3(flat3) is flat3
