@@ -164,6 +164,14 @@ int64_t mf_operator_split_bytes(const mf_operator_t* op);
  * kernel even when TF32 planes are present (used by the tests to cross-check). */
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores);
 int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
+/* Tuning / cross-check knobs of the CSR product (process-wide; negative / zero = keep).
+ * use_band_kernel: 1 (default) lets banded / stencil matrices on tiles of at least one warp per
+ * row take the band kernel (csrc/spmm_strip.cu: register window over adjacent diagonals, TMA bulk
+ * copies of the CSR metadata), 0 forces the row-group gather kernel -- both produce the same bits.
+ * rows_per_chunk (default 64), prefetch_rows (L2 prefetch distance, default 2; 0 = off),
+ * min_ctas_per_sm (3 or 4: register budget 80 / 64). */
+int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t prefetch_rows,
+                       int32_t min_ctas_per_sm);
 
 /* The user matvec (matfree/stochtrace.py:47-49, funm.py:231-235,
  * decomp.py:163-164) applied to a whole probe block:

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mf_probe_gen_rows": (c_int32, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_int64, c_int64,
                                     c_int64, c_uint32, c_uint32, c_int32, c_int32, c_void_p]),
     "mf_gemm_config": (c_int32, [c_int32, c_int32]),
+    "mf_spmm_config": (c_int32, [c_int32, c_int32, c_int32, c_int32]),
     "mf_operator_split_bytes": (c_int64, [_OP]),
     "mf_operator_split": (c_int32, [_OP, c_void_p, c_void_p]),
     "mf_matmat_workspace_bytes": (c_int64, [_OP, c_int64]),

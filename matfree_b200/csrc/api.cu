@@ -655,6 +655,12 @@ int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores) {
   return MF_OK;
 }
 
+int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t prefetch_rows,
+                       int32_t min_ctas_per_sm) {
+  spmm_strip_config(use_band_kernel, rows_per_chunk, prefetch_rows, min_ctas_per_sm);
+  return MF_OK;
+}
+
 int64_t mf_operator_split_bytes(const mf_operator_t* op) {
   if (validate_op(op) != MF_OK) return -1;
   if (op->dtype != MF_F32 || (op->kind != MF_OP_DENSE && op->kind != MF_OP_GRAM)) return 0;

@@ -111,6 +111,15 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
                         void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
                         cudaStream_t st, void* irregular_scratch = nullptr);
 
+// ---- spmm_strip.cu : the band route of launch_spmm_csr (stencil / banded matrices, tiles wide
+// enough that a row is at least one warp).  *taken = false: not applicable, nothing launched.
+int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const void* data,
+                          int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
+                          void* W, int64_t ld, const Reduce* red, unsigned int* progress,
+                          cudaStream_t st, bool* taken);
+
+void spmm_strip_config(int use_strip, int rows, int pfd, int minb);
+
 // ---- gemm_simt.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)
 // colscale (optional, [ld]): C[:, c] is multiplied by colscale[c] in the epilogue

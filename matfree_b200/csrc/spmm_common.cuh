@@ -1,0 +1,70 @@
+// Helpers shared by the CSR product kernels (spmm_csr.cu, spmm_strip.cu).
+#pragma once
+
+#include <cstdlib>
+
+#include "internal.h"
+
+namespace mf {
+namespace {
+
+constexpr int kCap = 1024;     // non-zeros of a chunk staged in shared memory
+constexpr int kMaxRows = 256;  // rows per chunk, upper bound
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t saddr, const void* g) {
+  if constexpr (BYTES == 16) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+  } else if constexpr (BYTES == 8) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
+  } else {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void ldx(const T* __restrict__ X, int64_t off, T (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    v[0] = __ldg(X + off);
+  } else {
+    vec_load_nc<T>(X + off, v);
+  }
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void stw(T* __restrict__ W, int64_t off, const T (&v)[VEC]) {
+  if constexpr (VEC == 1) {
+    __stcs(W + off, v[0]);
+  } else {
+    using V = typename Vec<T>::type;
+    V t;
+    T* e = reinterpret_cast<T*>(&t);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) e[i] = v[i];
+    __stcs(reinterpret_cast<V*>(W + off), t);  // streaming: W is not re-read by this kernel
+  }
+}
+
+struct SpmmParams {
+  int ld;              // tile width (power of two)
+  int rows_per_chunk;  // R, a multiple of the CTA sweep
+  int prefetch;        // L2 prefetch of the rows one window ahead
+  int l1pf;            // L1 prefetch of the gathers of the row `l1pf` sweeps ahead (0 = off)
+  int window;          // throttle: a chunk may start when done + window > chunk
+  int pfd;             // L2 prefetch of the CTA's own X rows `pfd` sweeps ahead (0 = off)
+};
+
+inline int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+
+}  // namespace
+}  // namespace mf

@@ -34,52 +34,10 @@
 #include <unordered_map>
 
 #include "internal.h"
+#include "spmm_common.cuh"
 
 namespace mf {
 namespace {
-
-constexpr int kCap = 1024;     // non-zeros of a chunk staged in shared memory
-constexpr int kMaxRows = 256;  // rows per chunk, upper bound
-
-template <int BYTES>
-__device__ __forceinline__ void cp_async(uint32_t saddr, const void* g) {
-  if constexpr (BYTES == 16) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-  } else if constexpr (BYTES == 8) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(saddr), "l"(g) : "memory");
-  } else {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
-  }
-}
-__device__ __forceinline__ void cp_async_commit() {
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <typename T, int VEC>
-__device__ __forceinline__ void ldx(const T* __restrict__ X, int64_t off, T (&v)[VEC]) {
-  if constexpr (VEC == 1) {
-    v[0] = __ldg(X + off);
-  } else {
-    vec_load_nc<T>(X + off, v);
-  }
-}
-
-template <typename T, int VEC>
-__device__ __forceinline__ void stw(T* __restrict__ W, int64_t off, const T (&v)[VEC]) {
-  if constexpr (VEC == 1) {
-    __stcs(W + off, v[0]);
-  } else {
-    using V = typename Vec<T>::type;
-    V t;
-    T* e = reinterpret_cast<T*>(&t);
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) e[i] = v[i];
-    __stcs(reinterpret_cast<V*>(W + off), t);  // streaming: W is not re-read by this kernel
-  }
-}
 
 // Irregular matrices (power-law graphs, BASELINE config 5): rows longer than kLongRow are not
 // multiplied by the row-group that meets them; they are cut into segments of kSegNnz non-zeros
@@ -101,15 +59,6 @@ struct LongList {
   int64_t max_segs, max_slots;
 };
 static_assert(sizeof(LongSeg) == 32, "scratch sizing assumes 32-byte list entries");
-
-struct SpmmParams {
-  int ld;              // tile width (power of two)
-  int rows_per_chunk;  // R, a multiple of the CTA sweep
-  int prefetch;        // L2 prefetch of the rows one window ahead
-  int l1pf;            // L1 prefetch of the gathers of the row `l1pf` sweeps ahead (0 = off)
-  int window;          // throttle: a chunk may start when done + window > chunk
-  int pfd;             // L2 prefetch of the CTA's own X rows `pfd` sweeps ahead (0 = off)
-};
 
 // The gathers of one row held in registers: up to SEGL non-zeros (a whole stencil row);
 // longer rows finish in a serial tail.
@@ -523,11 +472,6 @@ spmm_long_rows_kernel(const int32_t* __restrict__ indices, const T* __restrict__
   }
 }
 
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
 }  // namespace
 
 int resident_grid(const void* kernel, int block, size_t smem, int64_t want) {
@@ -639,6 +583,13 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   const int nv = dtype == MF_F64 ? 2 : 4;
   const int vec = ld >= nv ? nv : 1;
   const int rps = kBlock / (int)(ld / vec);
+  {
+    // banded / stencil matrices on wide tiles: the strip kernel (spmm_strip.cu)
+    bool taken = false;
+    const int32_t rc = launch_spmm_strip(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red,
+                                         progress, st, &taken);
+    if (taken) return rc;
+  }
   static const int env_rows = env_int("MF_SPMM_ROWS", 0);
   static const int env_prefetch = env_int("MF_SPMM_PREFETCH", 0);
   static const int env_l1pf = env_int("MF_SPMM_L1PF", 0);

@@ -261,6 +261,8 @@ def bidiag(num_matvecs: int, /, materialize: bool = True, reortho: str = "full")
                 raise TypeError("bidiag: a registered matvec must be ops.rect(A)")
             op = Av
             v = _device.as_device(v0, op.dtype).reshape(-1)
+        elif not callable(Av):
+            raise TypeError(f"bidiag: matvec must be ops.rect(A) or a callable, got {type(Av).__name__}")
         else:
             # any callable of device tensors: the vector-matrix product comes from its VJP
             # (decomp.py:703,712 use jax.vjp; here torch.func.vjp)

@@ -68,7 +68,9 @@ def test_bidiag_argument_checks():
     with pytest.raises(ValueError, match="exceeds"):
         m.decomp.bidiag(-1)(op, np.ones(4, np.float32))
     with pytest.raises(TypeError):
-        m.decomp.bidiag(2)(lambda v: v, np.ones(4, np.float32))
+        m.decomp.bidiag(2)(3.0, np.ones(4, np.float32))  # neither a registered operator nor a callable
+    with pytest.raises(TypeError, match="ops.rect"):
+        m.decomp.bidiag(2)(m.ops.gram(np.ones((5, 4), np.float32)), np.ones(4, np.float32))
     (U, V), B, res, ln = m.decomp.bidiag(0)(op, np.ones(4, np.float32))
     assert U.shape == (0, 5) and V.shape == (0, 4) and float(res.abs().max()) == 0.0
 

@@ -167,11 +167,22 @@ def test_matmat_dense_and_gram(dtype, n, P):
     assert np.allclose(gotg, wantg, rtol=tol, atol=tol * np.abs(wantg).max())
 
 
-def test_unregistered_callable_raises():
+def test_callable_takes_the_generic_route_and_the_fused_entry_points_refuse_it():
+    """A callable of device tensors is accepted by the decompositions (the product is the
+    callable's, the recurrence the library's); the fused kernel chain needs the operator's buffers
+    and says so; anything else is a TypeError.  There is no CPU route either way."""
     m = mfb()
     A = spd_dense(8, np.float32)
+    At = torch.as_tensor(A, device="cuda")
+    Q, T, r, c = m.decomp.tridiag_sym(3)(lambda v: At @ v, np.ones(8, np.float32))
+    Q2, T2, r2, c2 = m.decomp.tridiag_sym(3)(m.ops.dense(A), np.ones(8, np.float32))
+    assert np.allclose(to_np(T), to_np(T2), atol=1e-5)
     with pytest.raises(TypeError, match="registered operator"):
-        m.decomp.tridiag_sym(3)(lambda v: A @ v, np.ones(8, np.float32))
+        m.decomp.tridiag_sym(3)("not a matvec", np.ones(8, np.float32))
+    from matfree_b200 import _generic
+
+    with pytest.raises(TypeError, match="registered"):
+        _generic.CallableOperator(lambda v: v, 8, torch.float32)._struct()
 
 
 # ------------------------------------------------------------------ decomp.tridiag_sym

@@ -1,0 +1,106 @@
+"""The band route of the CSR product (csrc/spmm_strip.cu: register window over adjacent diagonals,
+TMA bulk copies of the CSR metadata) against SciPy and, bit for bit, against the row-group gather
+kernel it replaces on stencil matrices (`mf_spmm_config` switches between the two)."""
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def mfb():
+    import matfree_b200
+
+    return matfree_b200
+
+
+def scipy_csr(ip, ix, d, n):
+    import scipy.sparse as sp
+
+    return sp.csr_matrix((d.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+
+
+@pytest.fixture()
+def spmm_knobs():
+    from matfree_b200 import _lib
+
+    lib = _lib.load()
+    yield lib
+    lib.mf_spmm_config(1, 64, 2, 4)
+
+
+@pytest.mark.parametrize("dtype,ld", [("float32", 256), ("float32", 128), ("float64", 256), ("float64", 64)])
+@pytest.mark.parametrize("shape", [(37, 70), (5, 103), (64, 256), (9, 10, 33), (3, 40, 64), (700,)])
+def test_band_kernel_matches_scipy_and_gather_kernel_bitwise(spmm_knobs, dtype, ld, shape):
+    from matfree_b200 import workloads
+
+    m = mfb()
+    lib = spmm_knobs
+    n = int(np.prod(shape))
+    ip, ix, d = workloads.laplacian_csr(shape, shift=0.5, dtype=dtype, device="cuda")
+    # distinct values per entry, so that a wrong value <-> column pairing cannot cancel
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    d = d * (1.0 + 0.25 * torch.rand(d.shape, generator=gen, device="cuda", dtype=d.dtype))
+    op = m.ops.csr(ip, ix, d)
+    X = torch.randn((n, ld), generator=gen, device="cuda", dtype=d.dtype)
+    results = {}
+    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, 4, 4)):
+        lib.mf_spmm_config(band, rows, pfd, minb)
+        results[(band, rows)] = op.matmat_blocked(X)
+    want = scipy_csr(ip, ix, d, n) @ X.cpu().numpy()
+    tol = 1e-5 if dtype == "float32" else 1e-13
+    base = results[(0, 64)]
+    assert np.allclose(base.cpu().numpy(), want, rtol=tol, atol=tol * 10)
+    for key, W in results.items():
+        assert torch.equal(W, base), key  # the FMA order per row is the CSR order on every route
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_band_kernel_fused_alpha_dot_in_slq(spmm_knobs, dtype):
+    """The Lanczos alpha (`decomp.py:288`) is reduced inside the product kernel: per-probe SLQ
+    values with the band kernel == with the gather kernel == the oracle."""
+    from matfree_b200 import workloads
+    from oracle import prng as oprng
+    from oracle import ref
+
+    m = mfb()
+    lib = spmm_knobs
+    shape, P, k = (40, 64), 130, 9
+    n = shape[0] * shape[1]
+    ip, ix, d = workloads.laplacian_csr(shape, shift=1.0, dtype=np.dtype(dtype).name, device="cuda")
+    op = m.ops.csr(ip, ix, d)
+    key = m.prng.prng_key(1)
+    sampler = m.stochtrace.sampler_signs(np.ones(n, dtype), num=P)
+    integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+    est = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+    vals = {}
+    for band in (0, 1):
+        lib.mf_spmm_config(band, 64, 2, 4)
+        vals[band] = est.per_probe(op, key, tile=128).cpu().numpy()
+    tol = 1e-5 if dtype == np.float32 else 1e-10
+    assert np.allclose(vals[0], vals[1], rtol=tol * 0.1, atol=0)
+    A = scipy_csr(ip, ix, d, n)
+    V = oprng.rademacher(oprng.prng_key(1), (P, n), dtype)
+    oq, _ = ref.slq_batched(lambda X: (A @ X.T).T, V, k, reortho="none")
+    assert np.max(np.abs(vals[1] - oq)) <= 3 * tol * np.abs(oq).mean()
+
+
+def test_band_kernel_irregular_matrix_falls_back_row_by_row(spmm_knobs):
+    """avg <= 5 non-zeros per row but no band structure at all: every strip takes the gather path."""
+    import scipy.sparse as sp
+
+    m = mfb()
+    rng = np.random.default_rng(0)
+    n, ld = 5000, 128
+    A = sp.random(n, n, density=4.0 / n, random_state=rng, format="csr", dtype=np.float32)
+    A.sort_indices()
+    op = m.ops.csr_from_scipy(A)
+    X = torch.randn((n, ld), device="cuda")
+    spmm_knobs.mf_spmm_config(1, 64, 2, 4)
+    W1 = op.matmat_blocked(X)
+    spmm_knobs.mf_spmm_config(0, 64, 2, 4)
+    W0 = op.matmat_blocked(X)
+    assert torch.equal(W0, W1)
+    assert np.allclose(W1.cpu().numpy(), A @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
