@@ -165,11 +165,12 @@ int64_t mf_operator_split_bytes(const mf_operator_t* op);
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores);
 int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
 /* Tuning / cross-check knobs of the CSR product (process-wide; negative / zero = keep).
- * use_band_kernel: 1 (default) lets banded / stencil matrices on tiles of at least one warp per
- * row take the band kernel (csrc/spmm_strip.cu: register window over adjacent diagonals, TMA bulk
- * copies of the CSR metadata), 0 forces the row-group gather kernel -- both produce the same bits.
+ * use_band_kernel: 1 lets banded / stencil matrices on tiles of at least one warp per row take
+ * the band kernel (csrc/spmm_strip.cu: register window over adjacent diagonals, TMA bulk copies
+ * of the CSR metadata), 0 (default: it is the faster one on B200, see profiles/) the row-group
+ * gather kernel -- both produce the same bits.
  * rows_per_chunk (default 64), prefetch_rows (L2 prefetch distance, default 2; 0 = off),
- * min_ctas_per_sm (3 or 4: register budget 80 / 64). */
+ * min_ctas_per_sm (3 or 4: register budget 80 / 64) configure the band kernel. */
 int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t prefetch_rows,
                        int32_t min_ctas_per_sm);
 
@@ -368,6 +369,29 @@ int32_t mf_funm_lanczos(const mf_operator_t* op, const void* V0, int64_t ld, int
 int32_t mf_hutch_rows(const void* A, const void* B, int32_t dtype, int64_t n, int64_t ld,
                       int64_t num_probes, int32_t accumulate, double* rowsum, double* rowsumsq,
                       void* stream);
+
+/* ------------------------------------------------------------------ adjoints (gradients)
+ * The custom VJPs of the reference's decompositions -- matfree/decomp.py:184-217,295-348
+ * (`_tridiag_adjoint`) and :398-423,480-600 (`_hessenberg_adjoint`), Kraemer et al. 2024 -- are
+ * backward recurrences of k more operator products plus the same dots / projections / basis
+ * combinations as the forward pass.  They are enqueued from the host layer
+ * (matfree_b200/adjoint.py) with the building blocks above (mf_block_dot, mf_reorth_dots,
+ * mf_reorth_update, mf_basis_combine, mf_matmat, mf_matmat_rect) and these two:
+ *   mf_lincomb    out[n][ld] = sum_t h_scales[t] * coeffs[t][col] * vectors[t][n][ld], t < nterms
+ *                 <= 6, summed left to right (coeffs[t] may be NULL = 1; `vectors`, `coeffs`,
+ *                 `h_scales` are HOST arrays of device pointers / host doubles): one adjoint step's
+ *                 `lambda = -xi + mu x+ + nu x` or `xi = -dx - A lambda + a lambda + b lambda+ -
+ *                 b nu x+` (decomp.py:342,349) in one pass;
+ *   mf_sddmm_csr  parameter gradient of a CSR operator: the reference accumulates
+ *                 vjp(p -> matvec(v, p)) per step (decomp.py:345-346,588-590); for a CSR operator
+ *                 that is the outer product cot arg^T on the sparsity pattern:
+ *                 out_data[j] (+)= sum_{i<k} C[row_j][i] * G[col_j][i], C / G blocked [n][ld]
+ *                 holding the k cotangent / argument vectors of the k steps as columns. */
+int32_t mf_lincomb(const void* const* vectors, const void* const* coeffs, const double* h_scales,
+                   int32_t nterms, void* out, int32_t dtype, int64_t n, int64_t ld, void* stream);
+int32_t mf_sddmm_csr(const int32_t* indptr, const int32_t* indices, int64_t n, const void* C,
+                     const void* G, int64_t ld, int64_t k, int32_t accumulate, void* out_data,
+                     int32_t dtype, void* stream);
 
 /* ------------------------------------------------------------------ multi-GPU (row sharding)
  * One process per GPU.  A communicator owns one device region per rank -- a control block plus

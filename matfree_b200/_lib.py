@@ -134,6 +134,10 @@ SIGNATURES = {
                                  c_int64, c_void_p]),
     "mf_hutch_rows": (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int64, c_int32,
                                 c_void_p, c_void_p, c_void_p]),
+    "mf_lincomb": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int64,
+                             c_void_p]),
+    "mf_sddmm_csr": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int32,
+                               c_void_p, c_int32, c_void_p]),
     "mf_comm_create": (c_int32, [c_int32, c_int32, c_int64, POINTER(c_void_p)]),
     "mf_comm_handle": (c_int32, [c_void_p, c_void_p]),
     "mf_comm_connect": (c_int32, [c_void_p, c_void_p]),

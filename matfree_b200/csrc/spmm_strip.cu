@@ -352,10 +352,15 @@ spmm_strip_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
 }
 
 // process-wide knobs (mf_spmm_config; initial values from the environment)
-std::atomic<int> g_strip{env_int("MF_SPMM_STRIP", 1)};
+// Off by default: measured on BASELINE config 2 (profiles/r2b_spmm_sweep.jsonl, r2c_spmm_instep.jsonl)
+// the band kernel moves 40 % fewer bytes through L1 but holds only 3 instead of 5 gathers per warp
+// in flight (36 KB instead of 80 KB per SM at its register budget), and the product is bound by
+// the latency of the gathers: 8.7 ms per launch inside the Lanczos step against 8.6 ms for the
+// row-group kernel (8.5 against 6.7 ms stand-alone).  Results are bit-identical either way.
+std::atomic<int> g_strip{env_int("MF_SPMM_STRIP", 0)};
 std::atomic<int> g_rows{env_int("MF_SPMM_STRIP_ROWS", 64)};
 std::atomic<int> g_pfd{env_int("MF_SPMM_STRIP_PFD", 2)};
-std::atomic<int> g_minb{env_int("MF_SPMM_STRIP_MINB", 4)};
+std::atomic<int> g_minb{env_int("MF_SPMM_STRIP_MINB", 3)};
 
 }  // namespace
 

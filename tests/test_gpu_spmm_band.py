@@ -28,7 +28,7 @@ def spmm_knobs():
 
     lib = _lib.load()
     yield lib
-    lib.mf_spmm_config(1, 64, 2, 4)
+    lib.mf_spmm_config(0, 64, 2, 3)  # the library defaults
 
 
 @pytest.mark.parametrize("dtype,ld", [("float32", 256), ("float32", 128), ("float64", 256), ("float64", 64)])
