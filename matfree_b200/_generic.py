@@ -59,11 +59,15 @@ def wrap(matvec, vec, params, dtype=None):
         raise TypeError(f"matvec must be a registered operator or a callable, got {type(matvec).__name__}")
     v_flat, unravel = tree.ravel_pytree(vec, dtype)
 
-    def fn_flat(x):
-        out = matvec(unravel(x), *params)
-        return tree.ravel_pytree(out, x.dtype)[0]
+    def fn_flat_params(x, *p):
+        return tree.ravel_pytree(matvec(unravel(x), *p), x.dtype)[0]
 
-    return CallableOperator(fn_flat, v_flat.shape[0], v_flat.dtype), v_flat, unravel
+    def fn_flat(x):
+        return fn_flat_params(x, *params)
+
+    op = CallableOperator(fn_flat, v_flat.shape[0], v_flat.dtype)
+    op.fn_params, op.params = fn_flat_params, tuple(params)  # for the adjoints (parameter VJPs)
+    return op, v_flat, unravel
 
 
 def _backend(ld, k):

@@ -127,6 +127,14 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
             raise ValueError(_error_num_matvecs(k, maxval=n_total, minval=0))
         if n != op.n:
             raise ValueError(f"vector has length {n}, operator dimension is {op.n}")
+        from matfree_b200 import adjoint
+
+        diff = adjoint.diff_tensors_of(op, params)
+        if k > 0 and adjoint._needs_grad(vec_t, *diff):
+            if not custom_vjp:
+                raise NotImplementedError("custom_vjp=False: the CUDA kernels cannot be differentiated by "
+                                          "autodiff; use the adjoints (custom_vjp=True)")
+            return _tridiag_with_grad(op, vec_t, unravel, params, diff, k, reortho, materialize)
         V0b = vec_t.reshape(n, 1)
         alphas, betas, init_len, Q, residual = lanczos_blocked(
             op, V0b, k, reortho, want_Q=True, want_residual=True)
@@ -157,6 +165,78 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
     decompose._mf_spec = {"kind": "tridiag_sym", "num_matvecs": k, "reortho": reortho,
                           "materialize": materialize}
     return decompose
+
+
+def _grad_spec(op, params, forward, reortho):
+    from matfree_b200 import _generic
+
+    spec = {"op": op, "forward": forward, "reortho": reortho, "params": tuple(params)}
+    if isinstance(op, _generic.CallableOperator):
+        spec["fn_flat_params"], spec["params"] = op.fn_params, op.params
+    return spec
+
+
+def _tridiag_with_grad(op, vec_t, unravel, params, diff, k, reortho, materialize):
+    """`tridiag_sym` with the adjoints of `matfree_b200.adjoint` as its autograd backward
+    (`decomp.py:179-217` for "none"; `:125-145` on top of the Hessenberg VJP for "full")."""
+    import torch
+
+    from matfree_b200 import adjoint
+
+    n = vec_t.shape[0]
+    if reortho == "full":
+        def forward(v):
+            return _hessenberg_forward(op, v, k, second_pass=True)
+
+        Q, H, r, c = adjoint.hessenberg_fn().apply(_grad_spec(op, params, forward, "full"), vec_t, *diff)
+        T = 0.5 * (H + H.T)                                       # decomp.py:133
+        diags, offdiags = torch.diagonal(T, 0), torch.diagonal(T, 1)
+        res, inv = r, 1.0 / c                                      # :142 (the reference's quirk: |v|)
+    else:
+        def forward(v):
+            alphas, betas, _, Qb, residual = lanczos_blocked(op, v.reshape(n, 1).contiguous(), k, "none",
+                                                             want_Q=True, want_residual=True)
+            x_last = residual[:, 0] / betas[k - 1, 0]               # residual = b_{k-1} v_k (:167)
+            return (torch.cat([Qb[:, :, 0], x_last[None]]).contiguous(), alphas[:, 0].clone(),
+                    betas[:, 0].clone())
+
+        xs, al, be_ = adjoint.tridiag_fn().apply(_grad_spec(op, params, forward, "none"), vec_t, *diff)
+        Q, diags, offdiags = xs[:-1], al, be_[:-1]
+        res = be_[-1] * xs[-1]                                     # :167
+        inv = 1.0 / torch.linalg.vector_norm(vec_t)                # :176-177
+    matrix = (diags, offdiags)
+    if materialize:
+        matrix = torch.diag(diags) + torch.diag(offdiags, 1) + torch.diag(offdiags, -1)
+    return _DecompResult(Q_tall=unravel.batched(Q), J_small=matrix, residual=unravel(res), init_length_inv=inv)
+
+
+def _hessenberg_forward(op, vec, k, *, second_pass):
+    """`_hessenberg_forward` (`decomp.py:426-477`): ``(Q (k, n), H (k, k), residual (n,),
+    1/|vec|)`` for a registered operator (`mf_hessenberg`) or a callable (`_generic.arnoldi`)."""
+    import torch
+
+    from matfree_b200 import _generic
+
+    n = vec.shape[0]
+    dt, dev = op.dtype, vec.device
+    if isinstance(op, _generic.CallableOperator):
+        _, _, init_len, Q, residual, H = _generic.arnoldi(op, vec.reshape(n, 1).contiguous(), k,
+                                                          second_pass=second_pass, want_H=True)
+        Qk = Q[:, :, 0] if k > 0 else torch.zeros((0, n), dtype=dt, device=dev)
+        return Qk, H[:, :, 0], residual[:, 0], 1.0 / init_len[0]
+    lib = _lib.load()
+    st = op._struct()
+    ws = _device.workspace(lib.mf_hessenberg_workspace_bytes(ctypes.byref(st), 1, k))
+    H = torch.zeros((k, k, 1), dtype=dt, device=dev)
+    Q = torch.zeros((max(k, 1), n, 1), dtype=dt, device=dev)
+    init_len = torch.empty((1,), dtype=dt, device=dev)
+    residual = torch.empty((n, 1), dtype=dt, device=dev)
+    rflag = _lib.MF_REORTHO_FULL if second_pass else _lib.MF_REORTHO_NONE
+    vec = vec.contiguous()
+    _lib.check(lib.mf_hessenberg(ctypes.byref(st), vec.data_ptr(), 1, k, rflag, H.data_ptr(),
+                                 init_len.data_ptr(), Q.data_ptr(), residual.data_ptr(),
+                                 ws.data_ptr(), ws.numel(), _device.stream()))
+    return Q[:k, :, 0], H[:, :, 0], residual[:, 0], 1.0 / init_len[0]
 
 
 def bidiag_blocked(op, V0b, k: int, reortho: str):
@@ -291,8 +371,8 @@ def hessenberg(num_matvecs, /, *, reortho: str, custom_vjp: bool = True, reortho
     As in the reference the forward pass runs with ``reortho=reortho_vjp`` (`decomp.py:393-396`):
     with the default "match" the second Gram-Schmidt pass is applied whatever `reortho` says
     (`:466` only tests ``!= "none"``); `reortho` itself selects the adjoint's re-projection
-    (`matfree_b200.adjoint`)."""
-    del custom_vjp
+    (`matfree_b200.adjoint`), which is the backward pass of the result under `torch.autograd`
+    when ``custom_vjp=True``."""
     if reortho not in ("none", "full"):
         raise TypeError(f"Unexpected input for {reortho}: either of {['none', 'full']} expected.")  # :375-378
     k = int(num_matvecs)
@@ -312,27 +392,23 @@ def hessenberg(num_matvecs, /, *, reortho: str, custom_vjp: bool = True, reortho
             raise ValueError(_error_num_matvecs(k, maxval=n, minval=0))
         if n != op.n:
             raise ValueError(f"vector has length {n}, operator dimension is {op.n}")
-        dt, dev = op.dtype, vec.device
         second = reortho_vjp != "none"
-        if isinstance(op, _generic.CallableOperator):
-            _, _, init_len, Q, residual, H = _generic.arnoldi(op, vec.reshape(n, 1).contiguous(), k,
-                                                              second_pass=second, want_H=True)
-            Qk = Q[:, :, 0] if k > 0 else torch.zeros((0, n), dtype=dt, device=dev)
-            return _DecompResult(Q_tall=unravel.batched(Qk), J_small=H[:, :, 0],
-                                 residual=unravel(residual[:, 0]), init_length_inv=1.0 / init_len[0])
-        lib = _lib.load()
-        st = op._struct()
-        ws = _device.workspace(lib.mf_hessenberg_workspace_bytes(ctypes.byref(st), 1, k))
-        H = torch.zeros((k, k, 1), dtype=dt, device=dev)
-        Q = torch.zeros((max(k, 1), n, 1), dtype=dt, device=dev)
-        init_len = torch.empty((1,), dtype=dt, device=dev)
-        residual = torch.empty((n, 1), dtype=dt, device=dev)
-        rflag = _lib.MF_REORTHO_FULL if second else _lib.MF_REORTHO_NONE
-        _lib.check(lib.mf_hessenberg(ctypes.byref(st), vec.data_ptr(), 1, k, rflag, H.data_ptr(),
-                                     init_len.data_ptr(), Q.data_ptr(), residual.data_ptr(),
-                                     ws.data_ptr(), ws.numel(), _device.stream()))
-        return _DecompResult(Q_tall=unravel.batched(Q[:k, :, 0]), J_small=H[:, :, 0],
-                             residual=unravel(residual[:, 0]), init_length_inv=1.0 / init_len[0])
+        from matfree_b200 import adjoint
+
+        diff = adjoint.diff_tensors_of(op, params)
+        if adjoint._needs_grad(vec, *diff):
+            if not custom_vjp:
+                raise NotImplementedError("custom_vjp=False: the CUDA kernels cannot be differentiated by "
+                                          "autodiff; use the adjoint (custom_vjp=True)")
+
+            def forward(v):
+                return _hessenberg_forward(op, v, k, second_pass=second)
+
+            # k = 0 raises in the backward pass, like the reference (decomp.py:483-486)
+            Q, H, r, c = adjoint.hessenberg_fn().apply(_grad_spec(op, params, forward, reortho), vec, *diff)
+        else:
+            Q, H, r, c = _hessenberg_forward(op, vec, k, second_pass=second)
+        return _DecompResult(Q_tall=unravel.batched(Q), J_small=H, residual=unravel(r), init_length_inv=c)
 
     estimate._mf_spec = {"kind": "hessenberg", "num_matvecs": k, "reortho": reortho}
     return estimate

@@ -167,8 +167,14 @@ def monte_carlo_funm_sym(dense_funm, tridiag_sym, /):
             return _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters)
         from matfree_b200 import _generic
 
+        from matfree_b200 import adjoint
+
         # funm.py:226-235: any pytree `v0`, any callable `matvec(v0, *parameters)`
         op, v, _ = _generic.wrap(matvec, v0, parameters)
+        if adjoint._needs_grad(v, *adjoint.diff_tensors_of(op, parameters)):
+            # differentiable route: the decomposition's adjoint (matfree_b200.adjoint) under
+            # torch.autograd, the k x k function through torch.linalg.eigh
+            return _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters)
         k = spec["num_matvecs"]
         n_total = getattr(op, "n_global", v.shape[0])
         if k < 0 or k > n_total:
@@ -197,6 +203,8 @@ def _quadform_generic(dense_funm, tridiag_sym, matvec, v0, *parameters):
 
     mv = matvec if isinstance(matvec, ops.Operator) else matvec_flat
     _, dense, *_ = tridiag_sym(mv, v0_flat / length, *parameters)
+    if isinstance(dense, tuple):  # materialize=False
+        dense = torch.diag(dense[0]) + torch.diag(dense[1], 1) + torch.diag(dense[1], -1)
     fA = dense_funm(dense)
     return length**2 * fA[0, 0]
 

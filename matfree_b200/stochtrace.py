@@ -446,6 +446,10 @@ def _fused_values(integrand, sampler, matvec, key, parameters, *, tile=None, ret
     sspec = getattr(sampler, "_mf_sampler", None)
     if ispec is None or sspec is None or not isinstance(matvec, ops.Operator) or parameters:
         return None
+    from matfree_b200 import adjoint
+
+    if adjoint._needs_grad(*adjoint.diff_tensors_of(matvec, ())):
+        return None  # gradients wrt the operator's values: the differentiable per-sample route
     if ispec["kind"] in _BLOCK_KINDS:
         return None  # handled by _hutchinson_block
     if ispec["kind"] == "product":
