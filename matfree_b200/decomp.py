@@ -104,10 +104,13 @@ def tridiag_sym(num_matvecs: int, /, *, materialize: bool = True, reortho: str =
                 custom_vjp: bool = True):
     """Construct an implementation of tridiagonalisation (`matfree/decomp.py:30-122`).
 
-    `custom_vjp` is accepted for signature compatibility; gradients are out of
-    scope of the B200 hot path.
+    With ``custom_vjp=True`` (default) the result is differentiable through `torch.autograd` with
+    the reference's adjoints as the backward pass (`matfree_b200.adjoint`: `_tridiag_adjoint` for
+    ``reortho="none"``, `_hessenberg_adjoint` for ``"full"``), with respect to the start vector and
+    to the operator's values (dense / CSR) or the callable's parameters.  ``custom_vjp=False``
+    means "differentiate the forward pass itself" in the reference; the CUDA kernels have no
+    autodiff, so a gradient request then raises.
     """
-    del custom_vjp
     if reortho not in ("full", "none"):
         msg = f"reortho={reortho} unsupported. Choose eiter {'full', 'none'}."
         raise ValueError(msg)
