@@ -25,7 +25,16 @@ Metric: probe.Lanczos-steps / second = (probes of all ranks * depth) / step time
             cores, on a bounded probe sample of the same operator (N = 1, rank 0 only).
 
 `--impl reference` times that CPU port instead (the reference itself needs JAX, which
-is not installable here -- see DESIGN.md); each step is a bounded probe sample.
+is not installable here -- see DESIGN.md); each step is a bounded probe sample, on all host
+cores whatever OMP_NUM_THREADS the launcher exported.
+
+Extra keys of the default line (supplementary evidence, outside the timed region of `value`):
+  N = 1:  "c3"     -- BASELINE configs[2]: dense Gram operator on the tcgen05 tensor cores
+          "c2_3d"  -- north_star's literal target: 3-D 7-point Laplacian 256^3, depth 30
+  N > 1:  "multi_gpu_checks" -- sharded paths vs the single-GPU paths on the live process group
+          "c4_rowshard"      -- BASELINE configs[3]: row-sharded tridiag_sym(reortho=full), depth
+                                100, 256^3, peer-memory route and NCCL route
+(`--no-extras` skips them.)
 """
 
 from __future__ import annotations
@@ -53,12 +62,13 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
-                    help="c2 (default, the headline): CSR Laplacian; c3: dense Gram operator A^T A "
-                         "(tensor-core path), reported as a supplementary line")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2-3d", "c3"],
+                    help="c2 (default, the headline): 2-D CSR Laplacian; c2-3d: the 3-D 7-point Laplacian "
+                         "256^3 of north_star's target sentence; c3: dense Gram operator A^T A "
+                         "(tensor-core path); the last two are supplementary lines")
     ap.add_argument("--gram-rows", type=int, default=65536)
     ap.add_argument("--gram-cols", type=int, default=16384)
-    ap.add_argument("--grid", type=int, default=4096, help="grid side m (n = m*m rows)")
+    ap.add_argument("--grid", type=int, default=0, help="grid side m (default 4096 for c2: n = m^2; 256 for c2-3d: n = m^3)")
     ap.add_argument("--depth", type=int, default=30)
     ap.add_argument("--probes-per-gpu", type=int, default=1024)
     ap.add_argument("--tile", type=int, default=256)
@@ -66,6 +76,8 @@ def parse_args():
                     help="probe sample of the CPU baseline (64 probes x depth 30 = about 13 s on 16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the supplementary keys (c3 / c2_3d at N = 1, multi-GPU checks and C4 at N > 1)")
     ap.add_argument("--profile", action="store_true", help="profiling run: honour --warmup below 3")
     return ap.parse_args()
 
@@ -76,9 +88,17 @@ def workload_name(a, world):
                 f"(jax.random.normal(PRNGKey(2)) / sqrt(rows)), depth {a.depth}, reortho=none, "
                 f"{a.probes_per_gpu} Rademacher probes per GPU ({a.probes_per_gpu * world} total), "
                 f"key PRNGKey(1)")
+    if a.workload == "c2-3d":
+        return (f"north_star target: SLQ logdet, 3-D 7-pt Laplacian {a.grid}^3 (n={a.grid ** 3}) CSR + 1.0*I, fp32, "
+                f"depth {a.depth}, reortho=none, {a.probes_per_gpu} Rademacher probes per GPU "
+                f"({a.probes_per_gpu * world} total), key PRNGKey(1)")
     return (f"C2: SLQ logdet, 2-D 5-pt Laplacian {a.grid}^2 (n={a.grid * a.grid}) CSR + 1.0*I, fp32, "
             f"depth {a.depth}, reortho=none, {a.probes_per_gpu} Rademacher probes per GPU "
             f"({a.probes_per_gpu * world} total), key PRNGKey(1)")
+
+
+def grid_shape(a):
+    return (a.grid,) * (3 if a.workload == "c2-3d" else 2)
 
 
 # --------------------------------------------------------------------------- clocks
@@ -161,10 +181,10 @@ class ClockSampler:
 # --------------------------------------------------------------------------- CPU arm
 
 
-def cpu_csr_arrays(grid):
+def cpu_csr_arrays(shape):
     from matfree_b200 import workloads
 
-    ip, ix, d = workloads.laplacian_csr((grid, grid), shift=1.0)
+    ip, ix, d = workloads.laplacian_csr(shape, shift=1.0)
     return ip.numpy(), ix.numpy(), d.numpy()
 
 
@@ -227,16 +247,21 @@ def run_reference(a, rank, world):
         sample = f"{probes} probes x depth {a.depth} on the full {a.gram_rows}x{a.gram_cols} operator per step"
     else:
         port.build()
-        csr = cpu_csr_arrays(a.grid)
-        probes = min(a.cpu_probes, 8)
+        # all host cores, whatever OMP_NUM_THREADS says (torch.distributed.run exports 1)
+        cores = port.set_threads()
+        csr = cpu_csr_arrays(grid_shape(a))
+        # a step = a bounded probe sample of the workload: 64 probes (about 13 s on 16 cores) when
+        # the run is short, 32 when the driver asks for many steps, so the arm ends within minutes
+        probes = a.cpu_probes if (a.steps + a.warmup) <= 12 else max(8, a.cpu_probes // 2)
         for _ in range(a.warmup):
             cpu_sample(csr, probes, a.depth)
         t0 = time.perf_counter()
         for _ in range(a.steps):
             cpu_sample(csr, probes, a.depth)
         dt = (time.perf_counter() - t0) / max(a.steps, 1)
-        cores, kind_note = port.num_threads(), "oracle/slq_port.c (OpenMP C restatement)"
-        sample = f"{probes} probes x depth {a.depth} on the full {a.grid}^2 operator per step"
+        kind_note = "oracle/slq_port.c (OpenMP C restatement)"
+        sample = (f"{probes} probes x depth {a.depth} on the full {'x'.join(str(g) for g in grid_shape(a))} "
+                  f"operator per step, {cores} OpenMP threads")
     value = probes * a.depth / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
@@ -288,9 +313,10 @@ def run_ours(a, rank, local_rank, world):
 
         dist.init_process_group("nccl", device_id=dev)
 
-    n = a.grid * a.grid
+    shape = grid_shape(a)
+    n = int(np.prod(shape))
     P_local, P_total, k = a.probes_per_gpu, a.probes_per_gpu * world, a.depth
-    ip, ix, d = workloads.laplacian_csr((a.grid, a.grid), shift=1.0, device=dev)
+    ip, ix, d = workloads.laplacian_csr(shape, shift=1.0, device=dev)
     nnz = int(d.numel())
     op = m.ops.csr(ip, ix, d)
     torch.cuda.empty_cache()
@@ -304,7 +330,13 @@ def run_ours(a, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
+    tile = min(a.tile, P_local)
+    est_plain = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+
     def step_resident():
+        if tile != 256:  # a non-default probe tile goes through the per-probe entry (same kernels)
+            with m.stochtrace.probe_sharding():
+                return m.stochtrace._reduce(est_plain.per_probe(op, key, tile=tile))
         with m.stochtrace.probe_sharding():
             return estimate(op, key)
 
@@ -364,12 +396,6 @@ def run_ours(a, rank, local_rank, world):
                "d2h_bytes_per_step": 2 * 4, "ms_per_step": ms_e2e,
                "what": "ops.csr(host pinned CSR arrays) -> estimate(op, key) -> float(mean), float(sem)"}
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    # ---- roofline of the dominant kernel class
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -377,43 +403,74 @@ def run_ours(a, rank, local_rank, world):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- N > 1: multi-GPU parity on the live process group + BASELINE config 4 (collective: all ranks)
+    extras = {}
+    if world > 1 and not a.no_extras and a.workload == "c2":
+        from matfree_b200 import _multicheck
+
+        del op
+        torch.cuda.empty_cache()
+        try:
+            extras["multi_gpu_checks"] = {"probe_sharding": _multicheck.probe_sharding(dev),
+                                          "row_sharding": _multicheck.row_sharding(dev)}
+            extras["multi_gpu_checks"]["all_ok"] = all(
+                v for grp in ("probe_sharding", "row_sharding")
+                for v in extras["multi_gpu_checks"][grp].values() if isinstance(v, bool))
+        except Exception as exc:  # never lose the headline line
+            extras["multi_gpu_checks"] = {"all_ok": False, "error": f"{type(exc).__name__}: {exc}"}
+        try:
+            extras["c4_rowshard"] = _multicheck.c4_rowshard(dev, hbm_gbs=peak)
+        except Exception as exc:
+            extras["c4_rowshard"] = {"parity_ok": False, "error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     total_ms = sum(v[0] for v in per_class.values()) or 1.0
     kernels = {}
     for cls, (ms, cnt) in sorted(per_class.items(), key=lambda kv: -kv[1][0]):
         ent = {"ms_per_launch": ms / cnt, "launches": int(cnt), "share": ms / total_ms}
-        ab = algorithmic_bytes(cls, n, min(a.tile, P_local), nnz)
+        ab = algorithmic_bytes(cls, n, tile, nnz)
         if ab:
             ent["achieved_gbs"] = ab / (ms / cnt * 1e-3) / 1e9
             ent["frac_of_peak"] = ent["achieved_gbs"] / peak
         kernels[cls] = ent
     top = next(iter(kernels))
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of
-    # this very configuration (profiles/r1o_full.txt; grid 4096, tile 256): equals the algorithmic
-    # bytes to 0.2 % (lanczos_update) / 2 % (spmm_csr), i.e. no wasted re-reads
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run (ncu cannot
+    # run inside a timed bench) -- a static number from the committed ncu --set full capture of this
+    # very configuration (grid 4096, tile 256; these two kernels are unchanged since): it equals the
+    # algorithmic bytes to 0.2 % (lanczos_update) / 2 % (spmm_csr), i.e. no wasted re-reads
     ncu_traffic = {"lanczos_update": 51.686667e9 + 17.160440e9, "spmm_csr": 18.537456e9 + 17.154800e9,
                    "probe_gen": 0.003344e9 + 17.124462e9}
-    traffic = ncu_traffic.get(top) if (a.grid == 4096 and min(a.tile, P_local) == 256) else None
+    traffic = ncu_traffic.get(top) if (a.workload == "c2" and a.grid == 4096 and tile == 256) else None
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top].get("achieved_gbs"),
                 "peak": peak, "unit": "GB/s", "frac": kernels[top].get("frac_of_peak"),
-                "traffic": traffic, "traffic_source": "ncu --set full, profiles/r1o_full.txt" if traffic else None,
+                "traffic": traffic,
+                "traffic_source": ("static: ncu --set full capture profiles/r1o_full.txt of this configuration "
+                                   "(not measured in this run)") if traffic else None,
                 "peak_source": peak_kind, "share_of_step": kernels[top]["share"],
                 "note": ("the peak is the driver's copy benchmark (1 read : 1 write); this kernel streams "
                          "3 reads : 1 write, which HBM serves slightly faster, so frac can exceed 1"
                          if (kernels[top].get("frac_of_peak") or 0) > 0.97 and top == "lanczos_update" else None),
-                "algorithmic_bytes_per_launch": algorithmic_bytes(top, n, min(a.tile, P_local), nnz)}
+                "algorithmic_bytes_per_launch": algorithmic_bytes(top, n, tile, nnz)}
     # whole-step roofline: SURVEY section 8(d): 6*n*s + matrix/B_tile per probe*step
-    step_bytes = 6 * n * 4 + (nnz * 8 + 4 * (n + 1)) / min(a.tile, P_local)
+    step_bytes = 6 * n * 4 + (nnz * 8 + 4 * (n + 1)) / tile
     whole = {"algorithmic_bytes_per_probe_step": step_bytes,
              "achieved_gbs": value / world * step_bytes / 1e9,
              "frac_of_peak": value / world * step_bytes / 1e9 / peak}
 
-    truth = workloads.laplacian_logdet((a.grid, a.grid), 1.0)
+    truth = workloads.laplacian_logdet(shape, 1.0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
         "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, world), "tile": min(a.tile, P_local),
+        "config": {"workload": workload_name(a, world), "tile": tile,
                    "l2": "working set per tile (4 block vectors x 17 GB) >> 126 MB L2; no flush needed",
                    "parallelism": f"probe-sharded x{world}"},
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
@@ -421,6 +478,7 @@ def run_ours(a, rank, local_rank, world):
         "result": {"logdet_estimate": mean, "sem": sem, "closed_form_logdet": truth,
                    "rel_err": abs(mean - truth) / abs(truth)},
     }
+    line.update(extras)
 
     # ---- CPU baseline (rank 0, N = 1 only), bounded sample
     if world == 1 and not a.no_cpu_baseline:
@@ -428,7 +486,9 @@ def run_ours(a, rank, local_rank, world):
             from oracle import port
 
             port.build()
-            del op, ip, ix, d
+            port.set_threads()
+            op = None
+            del ip, ix, d
             torch.cuda.empty_cache()
             csr = (h_ip.numpy(), h_ix.numpy(), h_d.numpy())
             dt = cpu_sample(csr, a.cpu_probes, k)
@@ -440,9 +500,42 @@ def run_ours(a, rank, local_rank, world):
         except Exception as exc:  # the baseline must never lose the GPU line
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": f"failed: {exc}"}
+    # ---- N = 1: supplementary workloads (tensor-core evidence for C3, the literal 3-D target)
+    if world == 1 and not a.no_extras and a.workload == "c2":
+        op = None
+        h_ip = h_ix = h_d = None
+        torch.cuda.empty_cache()
+        for key_, wl in (("c3", "c3"), ("c2_3d", "c2-3d")):
+            try:
+                line[key_] = supplementary_line(wl)
+            except Exception as exc:
+                line[key_] = {"error": f"{type(exc).__name__}: {exc}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def supplementary_line(workload):
+    """Run `bench.py --workload <workload>` (short: 2 steps) in a fresh process on this GPU and
+    return the fields of its line that matter as evidence."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload, "--steps", "2", "--warmup", "3",
+           "--no-cpu-baseline", "--no-e2e", "--no-extras"]
+    if workload == "c2-3d":
+        cmd += ["--tile", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if out.returncode != 0 or not lines:
+        raise RuntimeError((out.stderr or out.stdout)[-400:])
+    d = json.loads(lines[-1])
+    keep = {k_: d.get(k_) for k_ in ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "gpu_launches",
+                                     "roofline", "step_roofline", "result", "clocks")}
+    keep["workload"] = d["config"]["workload"]
+    keep["tile"] = d["config"].get("tile")
+    keep["kernels"] = {k_: {kk: vv for kk, vv in v.items() if kk in ("ms_per_launch", "launches", "share",
+                                                                     "frac_of_peak", "tf32_tflops_issued",
+                                                                     "fp32_tflops", "achieved_gbs")}
+                       for k_, v in (d.get("kernels") or {}).items()}
+    return keep
 
 
 def run_ours_c3(a, rank, local_rank, world):
@@ -603,6 +696,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if a.workload == "c3" and a.probes_per_gpu == 1024 and a.depth == 30:
         a.probes_per_gpu, a.depth = 2048, 20  # C3's own numbers (16384 probes over 8 GPUs)
+    if a.grid <= 0:
+        a.grid = 256 if a.workload == "c2-3d" else 4096
     if a.impl == "reference":
         run_reference(a, rank, world)
         return

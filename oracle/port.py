@@ -27,6 +27,8 @@ def load():
         lib = ctypes.CDLL(LIB)
         i64, u32, vp = ctypes.c_int64, ctypes.c_uint32, ctypes.c_void_p
         lib.slq_port_num_threads.restype = ctypes.c_int
+        lib.slq_port_set_threads.restype = None
+        lib.slq_port_set_threads.argtypes = [ctypes.c_int]
         lib.slq_port_csr_logdet.restype = ctypes.c_int
         lib.slq_port_csr_logdet.argtypes = [vp, vp, vp, i64, i64, i64, i64, u32, u32, vp, vp, vp]
         lib.slq_port_csr_trace.restype = ctypes.c_int
@@ -39,6 +41,18 @@ def load():
 
 def num_threads() -> int:
     return int(load().slq_port_num_threads())
+
+
+def set_threads(n: int | None = None) -> int:
+    """Use `n` OpenMP threads (default: every core this process may run on), whatever
+    OMP_NUM_THREADS says -- `torch.distributed.run` sets it to 1 in its workers."""
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    load().slq_port_set_threads(int(n))
+    return num_threads()
 
 
 def _ptr(a):

@@ -50,6 +50,16 @@ static inline void threefry2x32(uint32_t k0, uint32_t k1, uint32_t* px0, uint32_
   *px1 = x1;
 }
 
+/* OpenMP thread count for the following calls (torchrun exports OMP_NUM_THREADS=1 to its
+ * workers; the CPU arm of the benchmark must still use all the cores it can). */
+void slq_port_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int slq_port_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
