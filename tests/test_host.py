@@ -222,3 +222,37 @@ def test_ravel_pytree_matches_jax_flattening_order():
     # a flat array is its own pytree
     flat3, unravel3 = tree.ravel_pytree(np.ones(5, np.float32), device="cpu")
     assert unravel3.trivial and unravel3(flat3) is flat3
+
+
+def test_ffi_shim_compiles_and_matches_integration_doc(tmp_path):
+    """The XLA-FFI shim (csrc/ffi_xla.cc) is compiled against a stand-in of the FFI API
+    (tests/ffi_stub): every handler's signature must match its binding (static_assert in `To`),
+    every `*_ffi` target INTEGRATION.md registers must be defined by the shim, and every mf_*
+    entry point the shim calls must be exported by the library with the header's signature
+    (the compiler checks the call against include/matfree_b200.h)."""
+    from matfree_b200 import _lib
+
+    shim = os.path.join(ROOT, "matfree_b200", "csrc", "ffi_xla.cc")
+    obj = str(tmp_path / "ffi_xla.o")
+    cuda_inc = "/usr/local/cuda/include"
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-c", "-I", os.path.join(ROOT, "tests", "ffi_stub"),
+                        "-I", cuda_inc, shim, "-o", obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    nm = subprocess.run(["nm", obj], capture_output=True, text=True, check=True).stdout
+    defined = set(re.findall(r" T (mf_[a-z0-9_]+_ffi)\b", nm))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    in_doc = set(re.findall(r"\b(mf_[a-z0-9_]+_ffi)\b", doc))
+    # brace patterns like mf_lanczos_{csr,dense,gram}_ffi are prose; the registration loop spells all names
+    assert in_doc and in_doc <= defined, sorted(in_doc - defined)
+    assert len(defined) == 10
+    registered = set(re.findall(r'"(mf_[a-z0-9_]+_ffi)"', doc))
+    assert registered == defined, sorted(registered ^ defined)
+    # every ffi_call target in the doc is a registered name without the suffix
+    targets = set(re.findall(r'ffi_call\("(mf_[a-z0-9_]+)"', doc))
+    assert targets and all(t + "_ffi" in defined for t in targets), sorted(targets)
+    src = open(shim).read()
+    called = set(re.findall(r"\b(mf_[a-z0-9_]+)\s*\(", src)) - {"mf_dtype_of"}
+    called = {c for c in called if not c.endswith("_ffi")}
+    lib = _lib.load()
+    for name in called:
+        assert hasattr(lib, name) and name in _lib.SIGNATURES, name
