@@ -146,6 +146,81 @@ def test_c5_scaled_powerlaw_expm_action():
     assert np.allclose(one, ofun(lambda x: L32 @ x, V[3]), rtol=1e-4, atol=2e-5)
 
 
+def _free_gb():
+    free, _ = torch.cuda.mem_get_info()
+    return free / 2**30
+
+
+def test_c3_full_size_subset_parity():
+    """BASELINE config 3 at its FULL size -- Gram operator of A (65536 x 16384) fp32, depth 20 --
+    on a subset of the probes: per-probe SLQ quadratic forms of probes 0 and 1 of PRNGKey(1)
+    through the tcgen05 3xTF32 contraction (K = 16384 in A X, K = 65536 in A^T (A X): the long
+    contraction the split TMEM accumulation exists for) against the oracle evaluated in fp64 NumPy
+    on the same matrix (~170 GFLOP on the host).  Tolerance 1e-5 relative (north_star, fp32)."""
+    if _free_gb() < 24:
+        pytest.skip("needs 24 GB of free device memory")
+    m = mfb()
+    rows, n, k, P = 65536, 16384, 20, 2
+    A = m.prng.normal(m.prng.prng_key(2), shape=(rows, n), dtype=np.float32)
+    A.mul_(1.0 / float(np.sqrt(rows)))
+    # the generator itself is pinned at small sizes; spot-check this instance against the oracle
+    head = (oprng.normal(oprng.prng_key(2), (1, 64), np.float32) / np.float32(np.sqrt(rows))).astype(np.float32)
+    assert np.allclose(A[0, :64].cpu().numpy(), head[0], rtol=4e-6, atol=1e-9)
+    op = m.ops.gram(A)
+    assert op._planes is not None
+    sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1), (n,)), num=P)
+    integrand = m.funm.integrand_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
+    est = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+    from matfree_b200 import _lib
+
+    _lib.timing_enable(True)
+    quad = est.per_probe(op, m.prng.prng_key(1), tile=32).cpu().numpy()   # tile 32: tensor-core envelope
+    torch.cuda.synchronize()
+    classes = _lib.timing_collect()
+    _lib.timing_enable(False)
+    assert classes.get("gemm", (0, 0))[1] >= 2 * k, "the Gram operator did not run on the GEMM kernels"
+    A64 = A.cpu().numpy().astype(np.float64)
+    del op, A
+    torch.cuda.empty_cache()
+    V = oprng.rademacher(oprng.prng_key(1), (P, n), np.float32).astype(np.float64)
+    oq, _ = ref.slq_batched(lambda X: (X @ A64.T) @ A64, V, k, reortho="none")
+    err = np.abs(quad - oq) / np.abs(oq)
+    assert err.max() <= 1e-5, (quad, oq, err)
+
+
+def test_c5_full_size_subset_parity():
+    """BASELINE config 5 at its FULL size -- power-law graph Laplacian, 10^7 nodes, ~10^8 stored
+    non-zeros, exp(-t L) v by Lanczos, depth 30 -- on 2 normal probes of PRNGKey(1): the two-pass
+    `funm_lanczos_sym` (load-balanced SpMM route for the hub rows) against the oracle
+    (`oracle/ref.py` with a SciPy CSR product) on the same matrix and vectors."""
+    import scipy.sparse as sp
+
+    from matfree_b200 import workloads
+
+    if _free_gb() < 24:
+        pytest.skip("needs 24 GB of free device memory")
+    m = mfb()
+    n, P, k = 10_000_000, 2, 30
+    ip, ix, d, dmax = workloads.powerlaw_laplacian_csr(n, 50_000_000, device="cuda")
+    assert d.numel() > 9e7 and dmax > 128       # hubs: the irregular route
+    op = m.ops.csr(ip, ix, d)
+    t = 1.0 / dmax
+    V = m.stochtrace.sampler_normal(np.broadcast_to(np.float32(1), (n,)), num=P)(m.prng.prng_key(1))
+    fun = m.funm.funm_lanczos_sym(m.funm.dense_funm_sym_eigh(("exp", -t)), m.decomp.tridiag_sym(k, reortho="none"))
+    got = fun.batched(op, V).cpu().numpy()
+    L32 = sp.csr_matrix((d.cpu().numpy(), ix.cpu().numpy(), ip.cpu().numpy()), shape=(n, n))
+    Vh = V.cpu().numpy()
+    del op, ip, ix, d
+    torch.cuda.empty_cache()
+    ofun = ref.funm_lanczos_sym(ref.dense_funm_sym_eigh(lambda x: np.exp(-t * x)), ref.tridiag_sym(k, reortho="none"))
+    for p in range(P):
+        want = ofun(lambda x: L32 @ x, Vh[p])
+        scale = np.abs(want).max()
+        assert np.abs(got[p] - want).max() <= 2e-5 * scale, (p, np.abs(got[p] - want).max() / scale)
+    # size-independent property: exp(-tL) preserves the mean of a vector (L 1 = 0, L symmetric)
+    assert np.allclose(got.mean(axis=1, dtype=np.float64), Vh.mean(axis=1, dtype=np.float64), atol=5e-6)
+
+
 def test_c2_full_size_subset_parity_and_properties():
     """BASELINE config 2 at its FULL size (2-D 5-point Laplacian 4096^2 = 16.7M rows, depth 30):
     the reference cannot even allocate this, so parity is asserted per probe on a
