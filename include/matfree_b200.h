@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 4
+#define MF_ABI_VERSION 5
 
 /* status codes */
 #define MF_OK 0
@@ -101,6 +101,10 @@ typedef struct mf_operator {
   int32_t csr_max_row_nnz; /* CSR, optional hint: longest row.  Above 128 the product takes
                             * the load-balanced route for irregular matrices (long rows cut
                             * into 512-non-zero segments, one CTA each); 0 = unknown/regular */
+  int64_t csr_bandwidth;   /* CSR, optional hint: max |column - row|; 0 = unknown.  When the rows
+                            * `bandwidth` apart (the planes of a 3-D stencil) would not survive
+                            * in L2 between their uses, the product walks the rows in a blocked
+                            * order (see csrc/spmm_csr.cu) -- same results, fewer DRAM re-reads */
 } mf_operator_t;
 
 const char* mf_last_error(void);

@@ -34,6 +34,7 @@ class MfOperator(Structure):
         ("lda", c_int64),
         ("split_planes", c_void_p),
         ("csr_max_row_nnz", c_int32),
+        ("csr_bandwidth", c_int64),
     ]
 
 

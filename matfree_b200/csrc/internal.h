@@ -109,7 +109,7 @@ int64_t spmm_irregular_scratch_bytes(int64_t nnz, int64_t ld, int32_t dtype);
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
-                        cudaStream_t st, void* irregular_scratch = nullptr);
+                        cudaStream_t st, void* irregular_scratch = nullptr, int64_t bandwidth = 0);
 
 // ---- spmm_strip.cu : the band route of launch_spmm_csr (stencil / banded matrices, tiles wide
 // enough that a row is at least one warp).  *taken = false: not applicable, nothing launched.

@@ -58,7 +58,26 @@ struct SpmmParams {
   int l1pf;            // L1 prefetch of the gathers of the row `l1pf` sweeps ahead (0 = off)
   int window;          // throttle: a chunk may start when done + window > chunk
   int pfd;             // L2 prefetch of the CTA's own X rows `pfd` sweeps ahead (0 = off)
+  // Blocked row order (0 = rows in ascending order).  For a matrix whose far diagonals are
+  // `outer_stride` rows away (the planes of a 3-D stencil) and too far apart to stay in L2, the
+  // rows are walked block by block: for jb: for i: rows [i * outer_stride + jb * block_rows, +
+  // block_rows) -- the same row range of consecutive planes back to back, so that X[r +- stride]
+  // is reused within 2 * block_rows rows instead of 2 * outer_stride.
+  int64_t outer_stride;
+  int block_rows;      // a multiple of rows_per_chunk that divides outer_stride
+  int num_outer;       // n / outer_stride
 };
+
+// first row of chunk c under the row order of `p` (R = p.rows_per_chunk)
+__device__ __forceinline__ int64_t chunk_row0(int64_t c, const SpmmParams& p) {
+  if (p.block_rows == 0) return c * p.rows_per_chunk;
+  const int cpb = p.block_rows / p.rows_per_chunk;  // chunks per block
+  const int64_t sb = c / cpb;
+  const int w = (int)(c - sb * cpb);
+  const int64_t jb = sb / p.num_outer;
+  const int64_t i = sb - jb * p.num_outer;
+  return i * p.outer_stride + jb * p.block_rows + (int64_t)w * p.rows_per_chunk;
+}
 
 inline int env_int(const char* name, int dflt) {
   const char* v = getenv(name);

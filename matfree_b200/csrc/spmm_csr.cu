@@ -99,7 +99,7 @@ __device__ __forceinline__ void prefetch_row_l1(const int32_t* __restrict__ ptrb
 // IMAD.WIDE per gather); LD == 0: any power of two, read from p.ld.
 // PIPE: the gathers of the next row are issued before the current row is multiplied.
 template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT, bool DEFER = false>
-__global__ void __launch_bounds__(kBlock, (PIPE || DEFER) ? 3 : 4)
+__global__ void __launch_bounds__(kBlock, (PIPE || DEFER || SEGL == 7) ? 3 : 4)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
@@ -130,7 +130,7 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   // ---- metadata pipeline (all threads): cp.async into multi-buffered shared memory --------
   auto issue_ptr = [&](int64_t c, int buf) {  // row pointers of chunk c -> s_ptr[buf]
     if (c < nchunks) {
-      const int64_t r0 = c * R;
+      const int64_t r0 = chunk_row0(c, p);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       for (int i = threadIdx.x; i <= nr; i += kBlock)
         cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf][i]), indptr + r0 + i);
@@ -138,7 +138,7 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   };
   auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
     if (c < nchunks) {
-      const int64_t r0 = c * R;
+      const int64_t r0 = chunk_row0(c, p);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       const int32_t base = s_ptr[pbuf][0];
       const int total = s_ptr[pbuf][nr] - base;
@@ -217,10 +217,10 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     issue_ptr(ch + 2 * G, (int)((t + 2) % 3));
     cp_async_commit();
 
-    const int64_t r0 = ch * R;
+    const int64_t r0 = chunk_row0(ch, p);
     const int nr = (int)((n - r0) < R ? (n - r0) : R);
     if (p.prefetch) {
-      const int64_t pr0 = r0 + G * R;
+      const int64_t pr0 = ch + G < nchunks ? chunk_row0(ch + G, p) : n;
       if (pr0 < n) {
         const int64_t pnr = (n - pr0) < R ? (n - pr0) : R;
         const char* pbase = reinterpret_cast<const char*>(X + pr0 * ld);
@@ -346,7 +346,8 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
             const int lines = (ld * (int)sizeof(T) + 127) / 128;
             if (lane_in_row < lines) {
               const int lp = lr + p.pfd * rps;
-              const int64_t prow = lp < R ? r0 + lp : r0 + G * R + (lp - R);
+              const int64_t prow = lp < R ? r0 + lp
+                                          : (ch + G < nchunks ? chunk_row0(ch + G, p) + (lp - R) : n);
               if (prow < n)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(
                     reinterpret_cast<const char*>(X + prow * ld) + lane_in_row * 128));
@@ -535,7 +536,7 @@ int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T*
   R = R / rps * rps;
   if (R < rps) R = rps;
   const int64_t nchunks = (n + R - 1) / R;
-  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, 0};
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, 0, 0, 0, 0};
   {
     auto kern = spmm_csr_kernel<T, VEC, 0, 8, false, false, true>;
     const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);
@@ -555,7 +556,7 @@ int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T*
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* progress,
-                        cudaStream_t st, void* irregular_scratch) {
+                        cudaStream_t st, void* irregular_scratch, int64_t bandwidth) {
   MF_KSCOPE(MF_KC_SPMM_CSR, st);
   if (n <= 0) return MF_OK;
   if (irregular_scratch != nullptr) {
@@ -617,7 +618,29 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   // 7.40 / 7.18 / 7.11 ms at 1 / 2 / 3 sweeps ahead, worse from 4 on (the prefetched rows then
   // leave the window the L2 holds)
   static const int env_pfd = env_int("MF_SPMM_PFD", 3);
-  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd};
+  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd, 0, 0, 0};
+  {
+    // Blocked row order for stencil-like matrices whose far diagonals (`bandwidth` rows away: the
+    // planes of a 3-D grid) are too far apart to stay in L2 between their uses.  Measured on the
+    // 3-D 7-point Laplacian 256^3 at ld = 256 (profiles/r2f_spmm_3d_t256.txt): 51.5 GB of DRAM
+    // reads per product in ascending row order, i.e. X three times.
+    static const int env_block = env_int("MF_SPMM_BLOCKED", 1);
+    static const int env_block_mb = env_int("MF_SPMM_BLOCK_MB", 12);
+    const int64_t row_bytes = ld * (int64_t)dtype_size(dtype);
+    if (env_block && bandwidth > 0 && avg <= 8.0 && n % bandwidth == 0 && n / bandwidth > 2 &&
+        n / bandwidth < (1ll << 30) && 2 * bandwidth * row_bytes > (40ll << 20)) {
+      const int64_t target = ((int64_t)env_block_mb << 20) / row_bytes;
+      int64_t d = target / R * R;
+      if (d > bandwidth) d = bandwidth / R * R;
+      for (; d >= R; d -= R)
+        if (bandwidth % d == 0) break;
+      if (d >= R && d <= (1 << 30)) {
+        prm.outer_stride = bandwidth;
+        prm.block_rows = (int)d;
+        prm.num_outer = (int)(n / bandwidth);
+      }
+    }
+  }
 #define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
   do {                                                                                         \
     auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT>;                                  \

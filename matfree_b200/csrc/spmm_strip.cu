@@ -153,7 +153,7 @@ spmm_strip_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
 
   auto issue_ptr = [&](int64_t c, int buf) {  // row pointers of chunk c -> s_ptr[buf]
     if (c < nchunks) {
-      const int64_t r0 = c * R;
+      const int64_t r0 = chunk_row0(c, p);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       for (int i = threadIdx.x; i <= nr; i += kBlock)
         cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf][i]), indptr + r0 + i);
@@ -165,7 +165,7 @@ spmm_strip_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
   // (oversized chunks with 0 bytes) so the phase parity is a function of the chunk count alone.
   auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {
     if (c < nchunks && threadIdx.x == 0) {
-      const int64_t r0 = c * R;
+      const int64_t r0 = chunk_row0(c, p);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       const int32_t base = s_ptr[pbuf][0];
       const int total = s_ptr[pbuf][nr] - base;
@@ -226,7 +226,7 @@ spmm_strip_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
     issue_ptr(ch + 2 * G, (int)((t + 2) % 3));
     cp_async_commit();
 
-    const int64_t r0 = ch * R;
+    const int64_t r0 = chunk_row0(ch, p);
     const int nr = (int)((n - r0) < R ? (n - r0) : R);
     const int32_t* __restrict__ ptrb = s_ptr[pb];
     const int32_t base = ptrb[0];
@@ -403,7 +403,7 @@ int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const v
     fin = red->fin;
     partial = red->partial;
   }
-  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, env_pfd};
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, env_pfd, 0, 0, 0};
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;  // timed under the caller's MF_KC_SPMM_CSR scope
 #define MF_STRIP_L(T, VEC, LD, SEGL, DOT, MINB)                                                  \

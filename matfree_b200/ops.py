@@ -131,13 +131,24 @@ class CsrOperator(Operator):
         if self.indices.shape[0] != self.nnz:
             raise ValueError("ops.csr: indices and data must have the same length")
         # longest row: above 128 non-zeros the SpMM takes its load-balanced route
-        self.max_row_nnz = int((self.indptr[1:] - self.indptr[:-1]).max()) if self.n > 0 else 0
+        counts = self.indptr[1:] - self.indptr[:-1]
+        self.max_row_nnz = int(counts.max()) if self.n > 0 else 0
+        # bandwidth max |col - row| from the first / last entry of every row (columns ascending):
+        # lets the product pick a blocked row order when planes of a 3-D stencil exceed the L2
+        self.bandwidth = 0
+        if self.nnz > 0:
+            rows = torch.arange(self.n, device=self.indptr.device, dtype=torch.int64)
+            ne = counts > 0
+            first = self.indices[self.indptr[:-1][ne].long()].long()
+            last = self.indices[(self.indptr[1:][ne] - 1).long()].long()
+            self.bandwidth = int(torch.maximum((first - rows[ne]).abs(), (last - rows[ne]).abs()).max())
 
     def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
-                               lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz)
+                               lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz,
+                               csr_bandwidth=self.bandwidth)
 
 
 class GramOperator(Operator):

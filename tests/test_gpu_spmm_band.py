@@ -104,3 +104,36 @@ def test_band_kernel_irregular_matrix_falls_back_row_by_row(spmm_knobs):
     W0 = op.matmat_blocked(X)
     assert torch.equal(W0, W1)
     assert np.allclose(W1.cpu().numpy(), A @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical():
+    """A 3-D stencil whose planes (bandwidth = 256^2 rows of 1 KB) exceed what L2 keeps between
+    their uses is walked in a blocked row order (mf_operator_t::csr_bandwidth, csrc/spmm_csr.cu);
+    a narrow tile of the same operator is walked in ascending order.  Row arithmetic is the same,
+    so the common columns agree bit for bit -- and with SciPy to rounding."""
+    from matfree_b200 import workloads
+
+    m = mfb()
+    shape = (6, 256, 256)
+    n = int(np.prod(shape))
+    ip, ix, d = workloads.laplacian_csr(shape, shift=0.5, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    d = d * (1.0 + 0.25 * torch.rand(d.shape, generator=gen, device="cuda"))
+    op = m.ops.csr(ip, ix, d)
+    assert op.bandwidth == 256 * 256
+    X = torch.randn((n, 256), generator=gen, device="cuda")
+    W = op.matmat_blocked(X)                      # 2 * 64 MB planes: blocked order
+    Xn = X[:, :32].contiguous()
+    Wn = op.matmat_blocked(Xn)                    # 2 * 8 MB planes: ascending order
+    assert torch.equal(W[:, :32], Wn)
+    rows = torch.tensor([0, 1, 255, 256, 65535, 65536, 65537, n // 2 + 3, n - 65537, n - 1], device="cuda")
+    A = scipy_csr(ip, ix, d, n)
+    want = A[rows.cpu().numpy()] @ X.cpu().numpy()
+    assert np.allclose(W[rows].cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # the fused alpha dot rides on the same order: SLQ on the blocked order == narrow tiles
+    sampler = m.stochtrace.sampler_signs(np.broadcast_to(np.float32(1), (n,)), num=256)
+    integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(4, reortho="none"))
+    est = m.stochtrace.estimator_monte_carlo(integrand, sampler)
+    a = est.per_probe(op, m.prng.prng_key(2), tile=256)
+    b = est.per_probe(op, m.prng.prng_key(2), tile=32)
+    assert torch.allclose(a, b, rtol=1e-6)

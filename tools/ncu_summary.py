@@ -57,6 +57,28 @@ def launches(path):
         print(f"{k:70s} {v[0]:8d} {v[1]:10.3f} {v[1] / tot:6.3f} {v[1] / v[0]:9.4f}")
 
 
+def wide(path, pattern=None):
+    """Every metric of the raw page whose name matches WIDE (memory hierarchy, L1 data pipe,
+    occupancy, stalls): used on the GPU box, where only the text summary is brought back."""
+    keep = re.compile(r"^(gpu__time|dram__|lts__t_bytes|lts__throughput|lts__t_sector|lts__t_sectors_srcunit_tex"
+                      r"|l1tex__|sm__throughput|sm__warps_active|sm__inst_executed_pipe_(lsu|fp64|alu|fma)"
+                      r"|smsp__inst_executed\.sum|launch__(registers|grid|block|occupancy|shared)|smsp__average_warp"
+                      r"|smsp__cycles_active\.avg|sm__cycles_elapsed\.max|smsp__warp_issue_stalled.*_per_warp_active)")
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full, all memory-hierarchy metrics of {path}")
+    for r in rows[2:]:
+        name = short(r[idx["Kernel Name"]])
+        if pattern and not re.search(pattern, name):
+            continue
+        print(f"\n== {name}  (launch id {r[idx['ID']]})")
+        for h in hdr:
+            if keep.search(h):
+                print(f"  {h:95s} {r[idx[h]]:>18s} {units[idx[h]]}")
+
+
 def full(path, pattern=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -76,5 +98,7 @@ def full(path, pattern=None):
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "wide":
+        wide(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
