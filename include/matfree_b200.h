@@ -173,8 +173,9 @@ int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
  * the band kernel (csrc/spmm_strip.cu: register window over adjacent diagonals, TMA bulk copies
  * of the CSR metadata), 0 (default: it is the faster one on B200, see profiles/) the row-group
  * gather kernel -- both produce the same bits.
- * rows_per_chunk (default 64), prefetch_rows (L2 prefetch distance, default 2; 0 = off),
- * min_ctas_per_sm (3 or 4: register budget 80 / 64) configure the band kernel. */
+ * rows_per_chunk (default 64), prefetch_rows (> 0: L2 prefetch distance, < 0: L1 prefetch
+ * distance, 0: off; <= -100 keeps the current value), min_ctas_per_sm (3 or 4: register budget
+ * 80 / 64) configure the band kernel. */
 int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t prefetch_rows,
                        int32_t min_ctas_per_sm);
 

@@ -116,7 +116,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
 int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const void* data,
                           int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                           void* W, int64_t ld, const Reduce* red, unsigned int* progress,
-                          cudaStream_t st, bool* taken);
+                          cudaStream_t st, bool* taken, int64_t bandwidth = 0);
 
 void spmm_strip_config(int use_strip, int rows, int pfd, int minb);
 

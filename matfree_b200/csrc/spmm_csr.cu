@@ -25,7 +25,7 @@
 //   * per row all gathers (a whole 5- or 7-point stencil row) are issued
 //     back to back into registers before the first FMA, one IMAD.WIDE + one
 //     LDG.128 per non-zero (tile width is a template constant).
-// Variants that were measured and rejected (tools/runs/gpu_run*.sh, profiles/README.md):
+// Variants that were measured and rejected (profiles/README.md, "SpMM tuning log"):
 // dynamic chunk tickets (same speed, not reproducible), a cp.async ring in shared
 // memory as the landing zone (2x the instructions, fewer warps: slower), register
 // software pipelining across rows (spills), L1/L2 software prefetch (no gain).
@@ -588,7 +588,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     // banded / stencil matrices on wide tiles: the strip kernel (spmm_strip.cu)
     bool taken = false;
     const int32_t rc = launch_spmm_strip(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red,
-                                         progress, st, &taken);
+                                         progress, st, &taken, bandwidth);
     if (taken) return rc;
   }
   static const int env_rows = env_int("MF_SPMM_ROWS", 0);
@@ -619,28 +619,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   // leave the window the L2 holds)
   static const int env_pfd = env_int("MF_SPMM_PFD", 3);
   SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd, 0, 0, 0};
-  {
-    // Blocked row order for stencil-like matrices whose far diagonals (`bandwidth` rows away: the
-    // planes of a 3-D grid) are too far apart to stay in L2 between their uses.  Measured on the
-    // 3-D 7-point Laplacian 256^3 at ld = 256 (profiles/r2f_spmm_3d_t256.txt): 51.5 GB of DRAM
-    // reads per product in ascending row order, i.e. X three times.
-    static const int env_block = env_int("MF_SPMM_BLOCKED", 1);
-    static const int env_block_mb = env_int("MF_SPMM_BLOCK_MB", 12);
-    const int64_t row_bytes = ld * (int64_t)dtype_size(dtype);
-    if (env_block && bandwidth > 0 && avg <= 8.0 && n % bandwidth == 0 && n / bandwidth > 2 &&
-        n / bandwidth < (1ll << 30) && 2 * bandwidth * row_bytes > (40ll << 20)) {
-      const int64_t target = ((int64_t)env_block_mb << 20) / row_bytes;
-      int64_t d = target / R * R;
-      if (d > bandwidth) d = bandwidth / R * R;
-      for (; d >= R; d -= R)
-        if (bandwidth % d == 0) break;
-      if (d >= R && d <= (1 << 30)) {
-        prm.outer_stride = bandwidth;
-        prm.block_rows = (int)d;
-        prm.num_outer = (int)(n / bandwidth);
-      }
-    }
-  }
+  choose_row_order(&prm, n, avg, bandwidth, ld, dtype);
 #define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
   do {                                                                                         \
     auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT>;                                  \

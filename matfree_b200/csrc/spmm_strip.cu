@@ -297,7 +297,20 @@ spmm_strip_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict_
 #pragma unroll
           for (int u = 0; u < SEGL; ++u)
             if (u < UD - 1 || u > UD) ldx<T, VEC>(Xc, (int64_t)(cb[u] + i + 1) * LD, x[u]);
-          if (p.pfd) {
+          if (p.pfd < 0) {
+            // L1 prefetch of this thread's own segment of the X rows the strip loads -pfd rows
+            // from now (every eighth lane starts a 128-byte line): the later LDG hits L1, so the
+            // few gathers a warp keeps in flight no longer bound the kernel by their latency
+            if ((lane & 7) == 0) {
+#pragma unroll
+              for (int u = 0; u < SEGL; ++u)
+                if (u < UD - 1 || u > UD) {
+                  int64_t pr = (int64_t)cb[u] + i + 1 - p.pfd;
+                  pr = pr < n ? pr : n - 1;
+                  asm volatile("prefetch.global.L1 [%0];" ::"l"(Xc + pr * ld));
+                }
+            }
+          } else if (p.pfd) {
             // L2 prefetch of the X rows this strip loads `pfd` rows from now: one 128-byte line
             // per lane of the group's first lanes
             constexpr int lines = (LD * (int)sizeof(T) + 127) / 128;
@@ -367,14 +380,14 @@ std::atomic<int> g_minb{env_int("MF_SPMM_STRIP_MINB", 3)};
 void spmm_strip_config(int use_strip, int rows, int pfd, int minb) {
   if (use_strip >= 0) g_strip.store(use_strip);
   if (rows > 0) g_rows.store(rows);
-  if (pfd >= 0) g_pfd.store(pfd);
+  if (pfd > -100) g_pfd.store(pfd);  // > 0: L2 prefetch distance, < 0: L1 prefetch distance, 0: off
   if (minb > 0) g_minb.store(minb);
 }
 
 int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const void* data,
                           int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                           void* W, int64_t ld, const Reduce* red, unsigned int* progress,
-                          cudaStream_t st, bool* taken) {
+                          cudaStream_t st, bool* taken, int64_t bandwidth) {
   *taken = false;
   const int env_strip = g_strip.load(std::memory_order_relaxed);
   const int env_rows = g_rows.load(std::memory_order_relaxed);
@@ -404,6 +417,7 @@ int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const v
     partial = red->partial;
   }
   SpmmParams prm{(int)ld, (int)R, 0, 0, 0, env_pfd, 0, 0, 0};
+  choose_row_order(&prm, n, avg, bandwidth, ld, dtype);
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;  // timed under the caller's MF_KC_SPMM_CSR scope
 #define MF_STRIP_L(T, VEC, LD, SEGL, DOT, MINB)                                                  \
