@@ -98,7 +98,8 @@ __device__ __forceinline__ void prefetch_row_l1(const int32_t* __restrict__ ptrb
 // LD > 0: the tile width is a compile-time constant (address arithmetic folds into one
 // IMAD.WIDE per gather); LD == 0: any power of two, read from p.ld.
 // PIPE: the gathers of the next row are issued before the current row is multiplied.
-template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT, bool DEFER = false>
+template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT, bool DEFER = false,
+          bool BLOCKED = false>
 __global__ void __launch_bounds__(kBlock, (PIPE || DEFER || SEGL == 7) ? 3 : 4)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
@@ -127,10 +128,21 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   const int64_t nchunks = (n + R - 1) / R;
   const int64_t G = gridDim.x;
 
+  // first row of chunk c: ascending order, or the blocked order of SpmmParams (3-D stencils
+  // whose planes exceed the L2; a separate instantiation so the common path pays nothing for it)
+  auto row0_of = [&](int64_t c) -> int64_t {
+    if constexpr (BLOCKED) return chunk_row0(c, p);
+    else return c * (int64_t)R;
+  };
+  // first row of this CTA's next chunk (>= n if there is none)
+  auto next_row0 = [&](int64_t c, int64_t r0c) -> int64_t {
+    if constexpr (BLOCKED) return c + G < nchunks ? chunk_row0(c + G, p) : n;
+    else return r0c + G * R;
+  };
   // ---- metadata pipeline (all threads): cp.async into multi-buffered shared memory --------
   auto issue_ptr = [&](int64_t c, int buf) {  // row pointers of chunk c -> s_ptr[buf]
     if (c < nchunks) {
-      const int64_t r0 = chunk_row0(c, p);
+      const int64_t r0 = row0_of(c);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       for (int i = threadIdx.x; i <= nr; i += kBlock)
         cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf][i]), indptr + r0 + i);
@@ -138,7 +150,7 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   };
   auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
     if (c < nchunks) {
-      const int64_t r0 = chunk_row0(c, p);
+      const int64_t r0 = row0_of(c);
       const int nr = (int)((n - r0) < R ? (n - r0) : R);
       const int32_t base = s_ptr[pbuf][0];
       const int total = s_ptr[pbuf][nr] - base;
@@ -217,10 +229,10 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     issue_ptr(ch + 2 * G, (int)((t + 2) % 3));
     cp_async_commit();
 
-    const int64_t r0 = chunk_row0(ch, p);
+    const int64_t r0 = row0_of(ch);
     const int nr = (int)((n - r0) < R ? (n - r0) : R);
     if (p.prefetch) {
-      const int64_t pr0 = ch + G < nchunks ? chunk_row0(ch + G, p) : n;
+      const int64_t pr0 = next_row0(ch, r0);
       if (pr0 < n) {
         const int64_t pnr = (n - pr0) < R ? (n - pr0) : R;
         const char* pbase = reinterpret_cast<const char*>(X + pr0 * ld);
@@ -346,8 +358,7 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
             const int lines = (ld * (int)sizeof(T) + 127) / 128;
             if (lane_in_row < lines) {
               const int lp = lr + p.pfd * rps;
-              const int64_t prow = lp < R ? r0 + lp
-                                          : (ch + G < nchunks ? chunk_row0(ch + G, p) + (lp - R) : n);
+              const int64_t prow = lp < R ? r0 + lp : next_row0(ch, r0) + (lp - R);
               if (prow < n)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(
                     reinterpret_cast<const char*>(X + prow * ld) + lane_in_row * 128));
@@ -620,13 +631,25 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   static const int env_pfd = env_int("MF_SPMM_PFD", 3);
   SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd, 0, 0, 0};
   choose_row_order(&prm, n, avg, bandwidth, ld, dtype);
-#define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
+#define MF_SPMM_K(T, VEC, LD, SEGL, PIPE, DOT, BLK)                                            \
   do {                                                                                         \
-    auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT>;                                  \
+    auto kern = spmm_csr_kernel<T, VEC, LD, SEGL, PIPE, DOT, false, BLK>;                      \
     const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);                     \
     prm.window = grid + (env_slack > 0 ? env_slack : (grid / 4 > 8 ? grid / 4 : 8));           \
     kern<<<grid, kBlock, 0, st>>>(indptr, indices, (const T*)data, n, (const T*)X,             \
                                   (const T*)s, (T*)W, prm, progress, partial, fin, LongList{}); \
+  } while (0)
+  // the blocked row order exists for the wide tiles only (compile-time LD): elsewhere a plane of
+  // X is small enough for L2 anyway
+#define MF_SPMM_L(T, VEC, LD, SEGL, PIPE, DOT)                                                 \
+  do {                                                                                         \
+    if constexpr ((LD) > 0 && !(PIPE)) {                                                       \
+      if (prm.block_rows != 0) MF_SPMM_K(T, VEC, LD, SEGL, PIPE, DOT, true);                   \
+      else MF_SPMM_K(T, VEC, LD, SEGL, PIPE, DOT, false);                                      \
+    } else {                                                                                   \
+      prm.block_rows = 0;                                                                      \
+      MF_SPMM_K(T, VEC, LD, SEGL, PIPE, DOT, false);                                           \
+    }                                                                                          \
   } while (0)
 #define MF_SPMM_D(T, VEC, LD, SEGL, PIPE)                     \
   do {                                                        \
@@ -659,6 +682,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
 #undef MF_SPMM_S
 #undef MF_SPMM_D
 #undef MF_SPMM_L
+#undef MF_SPMM_K
   return check_launch("spmm_csr");
 }
 
