@@ -64,19 +64,21 @@ struct SpmmParams {
   // block_rows) -- the same row range of consecutive planes back to back, so that X[r +- stride]
   // is reused within 2 * block_rows rows instead of 2 * outer_stride.
   int64_t outer_stride;
-  int block_rows;      // a multiple of rows_per_chunk that divides outer_stride
+  int block_rows;      // rows_per_chunk << block_shift; divides outer_stride
   int num_outer;       // n / outer_stride
+  int block_shift;     // log2(chunks per block)
 };
 
 // first row of chunk c under the row order of `p` (R = p.rows_per_chunk)
 __device__ __forceinline__ int64_t chunk_row0(int64_t c, const SpmmParams& p) {
   if (p.block_rows == 0) return c * p.rows_per_chunk;
-  const int cpb = p.block_rows / p.rows_per_chunk;  // chunks per block
-  const int64_t sb = c / cpb;
-  const int w = (int)(c - sb * cpb);
-  const int64_t jb = sb / p.num_outer;
-  const int64_t i = sb - jb * p.num_outer;
-  return i * p.outer_stride + jb * p.block_rows + (int64_t)w * p.rows_per_chunk;
+  // 32-bit arithmetic (fewer than 2^31 chunks); chunks per block is a power of two
+  const unsigned int cu = (unsigned int)c;
+  const unsigned int sb = cu >> p.block_shift;
+  const unsigned int w = cu & ((1u << p.block_shift) - 1u);
+  const unsigned int jb = sb / (unsigned int)p.num_outer;
+  const unsigned int i = sb - jb * (unsigned int)p.num_outer;
+  return (int64_t)i * p.outer_stride + (int64_t)jb * p.block_rows + (int64_t)w * p.rows_per_chunk;
 }
 
 inline int env_int(const char* name, int dflt) {
@@ -98,18 +100,20 @@ inline void choose_row_order(SpmmParams* prm, int64_t n, double avg, int64_t ban
   prm->outer_stride = 0;
   prm->block_rows = 0;
   prm->num_outer = 0;
+  prm->block_shift = 0;
   if (!env_block || bandwidth <= 0 || avg > 8.0 || n % bandwidth != 0 || n / bandwidth <= 2 ||
-      n / bandwidth >= (1ll << 30) || 2 * bandwidth * row_bytes <= (40ll << 20))
+      n / bandwidth >= (1ll << 30) || n / R >= (1ll << 31) || 2 * bandwidth * row_bytes <= (40ll << 20))
     return;
+  // largest block of R << q rows that divides the stride and stays under the budget
   const int64_t target = ((int64_t)env_block_mb << 20) / row_bytes;
-  int64_t d = target / R * R;
-  if (d > bandwidth) d = bandwidth / R * R;
-  for (; d >= R; d -= R)
-    if (bandwidth % d == 0) break;
-  if (d >= R && d <= (1 << 30)) {
+  int q = -1;
+  for (int t = 0; t < 24 && (R << t) <= target && (R << t) <= bandwidth; ++t)
+    if (bandwidth % (R << t) == 0) q = t;
+  if (q >= 0) {
     prm->outer_stride = bandwidth;
-    prm->block_rows = (int)d;
+    prm->block_rows = (int)(R << q);
     prm->num_outer = (int)(n / bandwidth);
+    prm->block_shift = q;
   }
 }
 

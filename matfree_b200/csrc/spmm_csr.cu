@@ -66,18 +66,23 @@ template <typename T, int VEC, int SEGL>
 struct RowRegs {
   T x[SEGL][VEC];
   int jb, len;
+  unsigned int dmask;  // bit u set: entry u (< SEGL) is the diagonal; filled when `rowg` >= 0
 };
 
 template <typename T, int VEC, int SEGL>
 __device__ __forceinline__ void issue_row(const int32_t* __restrict__ ptrb, int32_t base,
                                           const int32_t* __restrict__ colb,
                                           const T* __restrict__ Xc, int ld, int lr,
-                                          RowRegs<T, VEC, SEGL>& r) {
+                                          RowRegs<T, VEC, SEGL>& r, int32_t rowg = -1) {
   r.jb = ptrb[lr] - base;
   r.len = ptrb[lr + 1] - base - r.jb;
   int32_t c[SEGL];
+  r.dmask = 0u;
 #pragma unroll
-  for (int u = 0; u < SEGL; ++u) c[u] = u < r.len ? colb[r.jb + u] : 0;
+  for (int u = 0; u < SEGL; ++u) {
+    c[u] = u < r.len ? colb[r.jb + u] : -2;
+    r.dmask |= (unsigned int)(c[u] == rowg) << u;
+  }
 #pragma unroll
   for (int u = 0; u < SEGL; ++u)
     if (u < r.len) ldx<T, VEC>(Xc, (int64_t)c[u] * ld, r.x[u]);
@@ -165,17 +170,23 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   };
 
   // finish one row: scale, store, fused dot
-  auto finish_row = [&](T (&sum)[VEC], int64_t off) {
+  // The fused dot needs X[row]: for the 7-point rows (80-register kernel) it is taken from the
+  // gather of the diagonal entry when the row has one, instead of a reload through L1.
+  constexpr bool kDiagFromGather = FUSE_DOT && SEGL == 7 && !DEFER;
+  auto finish_row_x = [&](T (&sum)[VEC], int64_t off, T (&xo)[VEC], bool have_x) {
     T w[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) w[i] = sum[i] * sv[i];
     stw<T, VEC>(Wc, off, w);
     if (FUSE_DOT) {
-      T xo[VEC];
-      ldx<T, VEC>(Xc, off, xo);
+      if (!have_x) ldx<T, VEC>(Xc, off, xo);
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[0][i] += (double)(xo[i] * sv[i]) * (double)w[i];
     }
+  };
+  auto finish_row = [&](T (&sum)[VEC], int64_t off) {
+    T xo[VEC];
+    finish_row_x(sum, off, xo, false);
   };
 
   // hand a long row to the segment list (one thread of the row-group)
@@ -323,7 +334,20 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
 #pragma unroll
           for (int i = 0; i < VEC; ++i) sum[i] += a * x[i];
         }
-        finish_row(sum, coff + (int64_t)lr * ld);
+        if constexpr (kDiagFromGather) {
+          T xo[VEC];
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) xo[i] = T(0);
+#pragma unroll
+          for (int u = 0; u < SEGL; ++u)
+            if ((r.dmask >> u) & 1u) {  // independent predicates: stays in registers
+#pragma unroll
+              for (int i = 0; i < VEC; ++i) xo[i] = r.x[u][i];
+            }
+          finish_row_x(sum, coff + (int64_t)lr * ld, xo, r.dmask != 0u);
+        } else {
+          finish_row(sum, coff + (int64_t)lr * ld);
+        }
       };
       if (PIPE) {
         RowRegs<T, VEC, SEGL> ra, rb;
@@ -346,7 +370,8 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
             continue;
           }
           RowRegs<T, VEC, SEGL> ra;
-          issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra);
+          issue_row<T, VEC, SEGL>(ptrb, base, colb, Xc, ld, lr, ra,
+                                  kDiagFromGather ? (int32_t)(r0 + lr) : -1);
           if (p.pfd) {
             // Short-distance L2 prefetch of the X row this row-group owns `pfd` sweeps from now
             // (possibly in the CTA's next chunk).  All CTAs advance through one contiguous window
@@ -547,7 +572,7 @@ int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T*
   R = R / rps * rps;
   if (R < rps) R = rps;
   const int64_t nchunks = (n + R - 1) / R;
-  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, 0, 0, 0, 0};
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, 0, 0, 0, 0, 0};
   {
     auto kern = spmm_csr_kernel<T, VEC, 0, 8, false, false, true>;
     const int grid = resident_grid((const void*)kern, kBlock, 0, nchunks);
@@ -629,7 +654,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   // 7.40 / 7.18 / 7.11 ms at 1 / 2 / 3 sweeps ahead, worse from 4 on (the prefetched rows then
   // leave the window the L2 holds)
   static const int env_pfd = env_int("MF_SPMM_PFD", 3);
-  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd, 0, 0, 0};
+  SpmmParams prm{(int)ld, (int)R, env_prefetch, env_l1pf, 0, env_pfd, 0, 0, 0, 0};
   choose_row_order(&prm, n, avg, bandwidth, ld, dtype);
 #define MF_SPMM_K(T, VEC, LD, SEGL, PIPE, DOT, BLK)                                            \
   do {                                                                                         \

@@ -416,7 +416,7 @@ int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const v
     fin = red->fin;
     partial = red->partial;
   }
-  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, env_pfd, 0, 0, 0};
+  SpmmParams prm{(int)ld, (int)R, 0, 0, 0, env_pfd, 0, 0, 0, 0};
   choose_row_order(&prm, n, avg, bandwidth, ld, dtype);
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;  // timed under the caller's MF_KC_SPMM_CSR scope
