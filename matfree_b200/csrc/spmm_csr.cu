@@ -172,7 +172,9 @@ spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   // finish one row: scale, store, fused dot
   // The fused dot needs X[row]: for the 7-point rows (80-register kernel) it is taken from the
   // gather of the diagonal entry when the row has one, instead of a reload through L1.
-  constexpr bool kDiagFromGather = FUSE_DOT && SEGL == 7 && !DEFER;
+  // (measured on the 3-D workload: 14.5 instead of 13.1 ms per product -- the extra live registers
+  // spill in the 80-register kernel -- so it is compiled out; profiles/r2j_instep.jsonl)
+  constexpr bool kDiagFromGather = false;
   auto finish_row_x = [&](T (&sum)[VEC], int64_t off, T (&xo)[VEC], bool have_x) {
     T w[VEC];
 #pragma unroll
