@@ -27,7 +27,7 @@ bad = {k: v for k, v in res.items() if isinstance(v, bool) and not v}
 assert not bad, (rank, res)
 dist.barrier()
 dist.destroy_process_group()
-print("ok", rank, json.dumps(res))
+print("RANK_OK", rank, json.dumps(res))
 """
 
 
@@ -46,7 +46,7 @@ def _run(tmp_path, check, port):
          "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
         env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("ok") == world
+    assert out.stdout.count("RANK_OK") == world
 
 
 def test_probe_sharding_nccl_matches_single_gpu(tmp_path):
