@@ -169,10 +169,12 @@ int64_t mf_operator_split_bytes(const mf_operator_t* op);
 int32_t mf_gemm_config(int32_t variant, int32_t use_tensor_cores);
 int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
 /* Tuning / cross-check knobs of the CSR product (process-wide; negative / zero = keep).
- * use_band_kernel: 1 lets banded / stencil matrices on tiles of at least one warp per row take
- * the band kernel (csrc/spmm_strip.cu: register window over adjacent diagonals, TMA bulk copies
- * of the CSR metadata), 0 (default: it is the faster one on B200, see profiles/) the row-group
- * gather kernel -- both produce the same bits.
+ * use_band_kernel: 0 = the row-group gather kernel; 1 = banded / stencil matrices on tiles of at
+ * least one warp per row take the band kernel (csrc/spmm_strip.cu: register window over adjacent
+ * diagonals, TMA bulk copies of the CSR metadata); 2 = 5-diagonal band matrices on the 256-wide
+ * fp32 tile take the TMA-staged kernel (csrc/spmm_tma.cu: the X rows of a chunk land in shared
+ * memory by cp.async.bulk one chunk ahead).  All three produce the same bits; the default is the
+ * one measured fastest on B200 (profiles/).
  * rows_per_chunk (default 64), prefetch_rows (> 0: L2 prefetch distance, < 0: L1 prefetch
  * distance, 0: off; <= -100 keeps the current value), min_ctas_per_sm (3 or 4: register budget
  * 80 / 64) configure the band kernel. */

@@ -130,15 +130,15 @@ __device__ __forceinline__ double group_sum(double s, int L) {
 // acc[VEC] of thread t belongs to columns col0..col0+VEC-1; the contributions to a column are
 // summed in a fixed order (strided over the lanes of a group, then an xor tree).  Result is
 // written to partial[blockIdx.x * ld + col].
+// `sh`: kBlock * VEC * NACC doubles of shared memory (the caller's, e.g. a dead staging buffer)
 template <int VEC, int NACC = 1>
-__device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int ld,
-                                                   double* __restrict__ partial,
-                                                   int64_t partial_stride) {
-  __shared__ double sh[NACC][kBlock * VEC];
+__device__ __forceinline__ void cta_reduce_columns_smem(double (&acc)[NACC][VEC], int ld,
+                                                        double* __restrict__ partial,
+                                                        int64_t partial_stride, double* sh) {
 #pragma unroll
   for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sh[a][threadIdx.x * VEC + i] = acc[a][i];
+    for (int i = 0; i < VEC; ++i) sh[a * kBlock * VEC + threadIdx.x * VEC + i] = acc[a][i];
   __syncthreads();
   // flat element index e = t*VEC+i maps to column e % ld
   const int npairs = NACC * ld;
@@ -151,11 +151,19 @@ __device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int
     const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     double s = 0.0;
     if (live)
-      for (int e = c + lane * ld; e < kBlock * VEC; e += L * ld) s += sh[a][e];
+      for (int e = c + lane * ld; e < kBlock * VEC; e += L * ld) s += sh[a * kBlock * VEC + e];
     s = group_sum(s, L);
     if (live && lane == 0) partial[a * partial_stride + (int64_t)blockIdx.x * ld + c] = s;
   }
   __syncthreads();
+}
+
+template <int VEC, int NACC = 1>
+__device__ __forceinline__ void cta_reduce_columns(double (&acc)[NACC][VEC], int ld,
+                                                   double* __restrict__ partial,
+                                                   int64_t partial_stride) {
+  __shared__ double sh[NACC * kBlock * VEC];
+  cta_reduce_columns_smem<VEC, NACC>(acc, ld, partial, partial_stride, sh);
 }
 
 // ---------------------------------------------------------------- peer memory (multi-GPU)

@@ -119,6 +119,13 @@ int32_t launch_spmm_strip(const int32_t* indptr, const int32_t* indices, const v
                           cudaStream_t st, bool* taken, int64_t bandwidth = 0);
 
 void spmm_strip_config(int use_strip, int rows, int pfd, int minb);
+// ---- spmm_tma.cu : 5-diagonal band matrices, fp32, ld = 256: X rows staged in shared memory by
+// TMA bulk copies one chunk ahead.  *taken = false: not applicable / switched off.
+int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
+                        int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
+                        int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
+                        bool* taken);
+void spmm_tma_config(int use_tma);
 
 // ---- gemm_simt.cu
 // C[M][ld] = op(A) @ B[K][ld]; A is [M][K] (trans=0, lda>=K) or [K][M] (trans=1, lda>=M)

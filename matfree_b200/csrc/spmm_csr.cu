@@ -623,6 +623,13 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
   const int vec = ld >= nv ? nv : 1;
   const int rps = kBlock / (int)(ld / vec);
   {
+    // 5-diagonal band matrices on the 256-wide fp32 tile: X rows staged by TMA (spmm_tma.cu)
+    bool taken = false;
+    const int32_t rc = launch_spmm_tma(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red, progress,
+                                       st, &taken);
+    if (taken) return rc;
+  }
+  {
     // banded / stencil matrices on wide tiles: the strip kernel (spmm_strip.cu)
     bool taken = false;
     const int32_t rc = launch_spmm_strip(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red,

@@ -1,0 +1,410 @@
+// K2s, TMA route -- CSR times probe block for 5-diagonal band (2-D 5-point stencil) matrices on
+// wide tiles, with the X rows of a chunk staged in shared memory by TMA bulk copies.
+//
+// Why (profiles/r2f_spmm_2d_*.txt): the row-group kernel (spmm_csr.cu) is bound
+// by the L1 data pipe (83.7 % of peak: 6 global-load requests and 12 shared-memory wavefronts per
+// warp-row); the band kernel (spmm_strip.cu) halves that but keeps only 3 gathers per warp in flight,
+// in registers, and becomes latency-bound.  Here the in-flight window lives in SHARED MEMORY instead:
+//   * a CTA takes chunks of R consecutive rows; for a band chunk (every row has 5 entries, the
+//     columns of row i are those of row 0 shifted by i, the middle three adjacent with the diagonal
+//     in the centre) the X rows it needs are three contiguous row ranges -- [c0, c0+R),
+//     [d-1, d+R+1), [c4, c4+R) -- i.e. three contiguous byte ranges of the blocked vector, fetched by
+//     three cp.async.bulk copies (TMA, SASS UBLKCP) issued by ONE thread a whole chunk ahead and
+//     tracked by an mbarrier.  (3R + 2) KB per stage, two stages, two CTAs per SM: ~200 KB of loads
+//     in flight per SM without a single register or stalled warp;
+//   * the consumers read the staged rows with conflict-free LDS.128 (a warp reads 512 contiguous
+//     bytes); a row-group walks consecutive rows, so the -1 / 0 / +1 diagonals slide through
+//     registers (3 LDS.128 per row) and X[row] for the fused alpha dot (matfree/decomp.py:288) is
+//     the diagonal's register;
+//   * band-ness is verified per chunk from the CSR arrays as they are (staged one chunk earlier);
+//     a chunk that is not a band (boundary rows, anything else) takes the gather path row by row.
+//     The FMA order per row is the CSR order either way: W is bit-identical to the other kernels.
+// Chunk scheduling (static chunk -> CTA map, completed-chunk window) is the row-group kernel's.
+#include "internal.h"
+#include "spmm_common.cuh"
+
+namespace mf {
+namespace {
+
+constexpr int kTmaRows = 16;  // R: rows per chunk
+constexpr int kTmaSegl = 5;
+
+__device__ __forceinline__ void tma_mbar_init(uint64_t* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tma_mbar_expect_tx(uint64_t* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU
+__device__ __forceinline__ void tma_mbar_wait(uint64_t* bar, unsigned int parity) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
+    unsigned int done;
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, unsigned int bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          (uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+      "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int VEC>
+struct TmaRowDot {
+  double d[VEC];
+};
+// one row on the gather path, out of line (metadata in shared memory)
+template <typename T, int VEC, int LD, bool FUSE_DOT>
+__device__ __noinline__ TmaRowDot<VEC> tma_gather_row(const int32_t* cols, const T* vals, int len,
+                                                      const T* __restrict__ Xc, T* __restrict__ Wc,
+                                                      int64_t off, const T* sc) {
+  T sum[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) sum[q] = T(0);
+  int u = 0;
+  for (; u + 4 <= len; u += 4) {
+    T x[4][VEC];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) ldx<T, VEC>(Xc, (int64_t)cols[u + v] * LD, x[v]);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const T av = vals[u + v];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) sum[q] += av * x[v][q];
+    }
+  }
+  for (; u < len; ++u) {
+    const T av = vals[u];
+    T x[VEC];
+    ldx<T, VEC>(Xc, (int64_t)cols[u] * LD, x);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) sum[q] += av * x[q];
+  }
+  TmaRowDot<VEC> out;
+  T w[VEC];
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) w[q] = sum[q] * sc[q];
+  stw<T, VEC>(Wc, off, w);
+#pragma unroll
+  for (int q = 0; q < VEC; ++q) out.d[q] = 0.0;
+  if (FUSE_DOT) {
+    T xo[VEC];
+    ldx<T, VEC>(Xc, off, xo);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) out.d[q] = (double)(xo[q] * sc[q]) * (double)w[q];
+  }
+  return out;
+}
+
+// Dynamic shared memory layout (per CTA):
+//   [2 stages][3R + 2 rows][LD] T      X rows: run A (R), run B (R + 2), run C (R)
+//   [4][R + 1] int32                   row pointers of chunks t .. t+3
+//   [3][R * 8] int32, [3][R * 8] T     column indices / values of chunks t .. t+2 (<= 8 per row)
+//   [LD] T                             column scales
+//   [2] uint64 mbarrier, [2] int flags
+template <typename T, int VEC, int LD>
+struct TmaLayout {
+  static constexpr int R = kTmaRows;
+  static constexpr int kStageRows = 3 * R + 2;
+  static constexpr int kEntCap = R * 8;
+  static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
+  static constexpr size_t kPtrOff = 2 * kStageBytes;
+  static constexpr size_t kColOff = kPtrOff + 4 * (R + 1) * sizeof(int32_t) + 12;
+  static constexpr size_t kValOff = kColOff + 3 * kEntCap * sizeof(int32_t);
+  static constexpr size_t kSvOff = kValOff + 3 * kEntCap * sizeof(T);
+  static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
+  static constexpr size_t kFlagOff = kBarOff + 2 * sizeof(uint64_t);
+  static constexpr size_t kBytes = kFlagOff + 4 * sizeof(int);
+};
+
+template <typename T, int VEC, int LD, bool FUSE_DOT>
+__global__ void __launch_bounds__(kBlock, 2)
+spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                const T* __restrict__ data, int64_t n, const T* __restrict__ X,
+                const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
+                unsigned int* __restrict__ progress, double* __restrict__ partial, Finalize fin) {
+  using L = TmaLayout<T, VEC, LD>;
+  constexpr int R = L::R;
+  constexpr int SEGL = kTmaSegl;
+  constexpr int UD = SEGL / 2;
+  constexpr int ld = LD;
+  constexpr int tpr = LD / VEC;
+  constexpr int rps = kBlock / tpr;  // row-groups per CTA
+  constexpr int S = R / rps;         // consecutive rows per row-group
+  static_assert(tpr >= 32 && tpr % 32 == 0 && R % rps == 0 && S >= 1, "tile / chunk geometry");
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* const s_x = reinterpret_cast<T*>(smem);
+  int32_t* const s_ptr = reinterpret_cast<int32_t*>(smem + L::kPtrOff);   // [4][R + 1]
+  int32_t* const s_col = reinterpret_cast<int32_t*>(smem + L::kColOff);   // [3][kEntCap]
+  T* const s_val = reinterpret_cast<T*>(smem + L::kValOff);               // [3][kEntCap]
+  T* const s_sv = reinterpret_cast<T*>(smem + L::kSvOff);
+  uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [2] per stage
+
+  const int grp = threadIdx.x / tpr;
+  const int lane = threadIdx.x & 31;
+  const int c0 = (threadIdx.x % tpr) * VEC;
+  const T* __restrict__ Xc = X + c0;
+  T* __restrict__ Wc = W + c0;
+  T sv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sv[i] = s ? s[c0 + i] : T(1);
+  for (int i = threadIdx.x; i < LD; i += kBlock) s_sv[i] = s ? s[i] : T(1);
+  double acc[1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+
+  const int64_t nchunks = (n + R - 1) / R;
+  const int64_t G = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    tma_mbar_init(&s_bar[0], 1);
+    tma_mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  auto rows_of = [&](int64_t c) -> int { return (int)((n - c * R) < R ? (n - c * R) : R); };
+  auto issue_ptr = [&](int64_t c, int buf) {
+    if (c < nchunks) {
+      const int nr = rows_of(c);
+      for (int i = threadIdx.x; i <= nr; i += kBlock)
+        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf * (R + 1) + i]), indptr + c * R + i);
+    }
+  };
+  auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
+    if (c < nchunks) {
+      const int nr = rows_of(c);
+      const int32_t base = s_ptr[pbuf * (R + 1)];
+      const int total = s_ptr[pbuf * (R + 1) + nr] - base;
+      if (total <= L::kEntCap) {
+        for (int i = threadIdx.x; i < total; i += kBlock) {
+          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_col[ebuf * L::kEntCap + i]), indices + base + i);
+          cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&s_val[ebuf * L::kEntCap + i]),
+                                   data + base + i);
+        }
+      }
+    }
+  };
+  // Warp 0: is chunk c (metadata in s_ptr[pbuf] / s_col[ebuf]) a band?  If so stage its X rows.
+  // Always arms the stage's mbarrier, so its phase parity is a function of the chunk count alone.
+  auto verify_and_stage = [&](int64_t c, int pbuf, int ebuf, int stage) {
+    if (threadIdx.x >= 32) return;
+    bool band = false;
+    int32_t ca = 0, cd = 0, cc = 0;
+    if (c < nchunks) {
+      const int nr = rows_of(c);
+      const int32_t* ptrb = s_ptr + pbuf * (R + 1);
+      const int32_t base = ptrb[0];
+      const int32_t* colb = s_col + ebuf * L::kEntCap;
+      bool ok = nr == R && ptrb[R] - base == R * SEGL;
+      if (ok && lane < R) {
+        const int jb = ptrb[lane] - base;
+        ok = jb == lane * SEGL;
+        if (ok) {
+#pragma unroll
+          for (int u = 0; u < SEGL; ++u) ok = ok && (colb[jb + u] == colb[u] + lane);
+        }
+      }
+      if (ok && lane == 0) {
+        ca = colb[0];
+        cd = colb[UD];
+        cc = colb[SEGL - 1];
+        ok = (int64_t)cd == c * R && colb[UD - 1] == cd - 1 && colb[UD + 1] == cd + 1;
+      }
+      band = __all_sync(0xffffffffu, ok);
+    }
+    if (lane == 0) {
+      s_band[stage] = band ? 1 : 0;
+      T* xs = s_x + (size_t)stage * L::kStageRows * LD;
+      constexpr unsigned int row_bytes = LD * sizeof(T);
+      tma_mbar_expect_tx(&s_bar[stage], band ? (unsigned int)L::kStageRows * row_bytes : 0u);
+      if (band) {
+        tma_bulk_g2s(xs, X + (int64_t)ca * LD, R * row_bytes, &s_bar[stage]);
+        tma_bulk_g2s(xs + (size_t)R * LD, X + (int64_t)(cd - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
+        tma_bulk_g2s(xs + (size_t)(2 * R + 2) * LD, X + (int64_t)cc * LD, R * row_bytes, &s_bar[stage]);
+      }
+    }
+  };
+
+  // ---- prologue: pointers of chunks 0..2, entries of chunks 0..1, X of chunk 0
+  int64_t ch = blockIdx.x;
+  issue_ptr(ch, 0);
+  issue_ptr(ch + G, 1);
+  issue_ptr(ch + 2 * G, 2);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();  // pointers visible; mbarriers initialised; s_sv filled
+  issue_ent(ch, 0, 0);
+  issue_ent(ch + G, 1, 1);
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  verify_and_stage(ch, 0, 0, 0);
+
+  unsigned int seen_done = 0;
+  for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
+    const int pb = (int)(t & 3), eb = (int)(t % 3), stage = (int)(t & 1);
+    if (progress != nullptr && threadIdx.x == 0) {
+      while ((int64_t)seen_done + p.window <= ch) {
+        seen_done = *reinterpret_cast<volatile unsigned int*>(progress);
+        if ((int64_t)seen_done + p.window <= ch) __nanosleep(200);
+      }
+    }
+    __syncthreads();  // metadata of chunks t+1 (entries), t+2 (pointers) visible; stage^1 is free
+    if (progress != nullptr && threadIdx.x == 0 && t > 0) atomicAdd(progress, 1u);
+    // a whole chunk ahead: X rows of chunk t+1; two ahead: its entries; three ahead: its pointers
+    verify_and_stage(ch + G, (int)((t + 1) & 3), (int)((t + 1) % 3), stage ^ 1);
+    issue_ent(ch + 2 * G, (int)((t + 2) & 3), (int)((t + 2) % 3));
+    issue_ptr(ch + 3 * G, (int)((t + 3) & 3));
+    cp_async_commit();
+
+    const int64_t r0 = ch * R;
+    const int nr = rows_of(ch);
+    const int32_t* __restrict__ ptrb = s_ptr + pb * (R + 1);
+    const int32_t base = ptrb[0];
+    const int total = ptrb[nr] - base;
+    const int32_t* __restrict__ colb = s_col + eb * L::kEntCap;
+    const T* __restrict__ valb = s_val + eb * L::kEntCap;
+    const int64_t coff = r0 * ld;
+
+    tma_mbar_wait(&s_bar[stage], (unsigned int)((t >> 1) & 1));  // X rows of chunk t have landed
+    const int lr0 = grp * S;
+    if (s_band[stage]) {
+      const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
+      const T* __restrict__ xa = xs + (size_t)lr0 * LD;                  // run A: row lr
+      const T* __restrict__ xb = xs + (size_t)(R + lr0) * LD;            // run B: rows lr, lr+1, lr+2
+      const T* __restrict__ xc = xs + (size_t)(2 * R + 2 + lr0) * LD;    // run C: row lr
+      T x[SEGL][VEC];
+      vec_load<T>(xb, x[UD - 1]);
+      vec_load<T>(xb + LD, x[UD]);
+      const T* __restrict__ vrow = valb + lr0 * SEGL;
+      int64_t off = coff + (int64_t)lr0 * ld;
+#pragma unroll
+      for (int i = 0; i < S; ++i) {
+        vec_load<T>(xa + (size_t)i * LD, x[0]);
+        vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
+        vec_load<T>(xc + (size_t)i * LD, x[SEGL - 1]);
+        T sum[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) sum[q] = T(0);
+#pragma unroll
+        for (int u = 0; u < SEGL; ++u) {
+          const T av = vrow[i * SEGL + u];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) sum[q] += av * x[u][q];
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) sum[q] *= sv[q];
+        if (FUSE_DOT) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[0][q] += (double)(x[UD][q] * sv[q]) * (double)sum[q];
+        }
+        stw<T, VEC>(Wc, off, sum);
+        off += ld;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+          x[UD - 1][q] = x[UD][q];
+          x[UD][q] = x[UD + 1][q];
+        }
+      }
+    } else {
+      for (int i = 0; i < S; ++i) {
+        const int lr = lr0 + i;
+        if (lr >= nr) break;
+        const int32_t jb = ptrb[lr], len = ptrb[lr + 1] - jb;
+        const int32_t* cols = total <= L::kEntCap ? colb + (jb - base) : indices + jb;
+        const T* vals = total <= L::kEntCap ? valb + (jb - base) : data + jb;
+        const TmaRowDot<VEC> d = tma_gather_row<T, VEC, LD, FUSE_DOT>(
+            cols, vals, len, Xc, Wc, coff + (int64_t)lr * ld, s_sv + c0);
+        if (FUSE_DOT) {
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[0][q] += d.d[q];
+        }
+      }
+    }
+    cp_async_wait<0>();  // entries of chunk t+2 / pointers of chunk t+3 landed (visible after the barrier)
+  }
+  // the stage armed for the chunk after my last one (no copies: c >= nchunks) needs no wait
+  cp_async_wait<0>();
+  if (progress != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (blockIdx.x < nchunks) atomicAdd(progress, 1u);
+      __threadfence();
+      const unsigned int left = atomicAdd(progress + 1, 1u);
+      if (left == gridDim.x - 1) {
+        progress[0] = 0u;
+        progress[1] = 0u;
+      }
+    }
+  }
+  if (FUSE_DOT) {
+    // the X stages are dead: their memory serves the CTA-level reduction (no static array, so two
+    // CTAs of 107 KB fit one SM)
+    __syncthreads();
+    cta_reduce_columns_smem<VEC, 1>(acc, ld, partial, 0, reinterpret_cast<double*>(smem));
+    finalize_if_last<T>(ld, partial, 0, 1, fin);
+  }
+}
+
+std::atomic<int> g_tma{env_int("MF_SPMM_TMA", 0)};
+
+}  // namespace
+
+void spmm_tma_config(int use_tma) {
+  if (use_tma >= 0) g_tma.store(use_tma);
+}
+
+int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
+                        int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
+                        int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
+                        bool* taken) {
+  *taken = false;
+  if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
+  if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
+  const double avg = (double)nnz / (double)n;
+  if (avg > 5.0 || avg <= 4.0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
+  if (((uintptr_t)X & 15) != 0) return MF_OK;
+  static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
+  using L = TmaLayout<float, 4, 256>;
+  const int64_t nchunks = (n + L::R - 1) / L::R;
+  Finalize fin{};
+  double* partial = nullptr;
+  if (red) {
+    fin = red->fin;
+    partial = red->partial;
+  }
+  SpmmParams prm{(int)ld, L::R, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned int* prog = env_throttle ? progress : nullptr;
+  *taken = true;
+#define MF_TMA_L(DOT)                                                                              \
+  do {                                                                                             \
+    auto kern = spmm_tma_kernel<float, 4, 256, DOT>;                                               \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes) != \
+        cudaSuccess) {                                                                             \
+      cudaGetLastError();                                                                          \
+      *taken = false;                                                                              \
+      return MF_OK;                                                                                \
+    }                                                                                              \
+    const int grid = resident_grid((const void*)kern, kBlock, L::kBytes, nchunks);                 \
+    prm.window = grid * 4 + (grid > 8 ? grid : 8);                                                 \
+    kern<<<grid, kBlock, L::kBytes, st>>>(indptr, indices, (const float*)data, n, (const float*)X, \
+                                          (const float*)s, (float*)W, prm, prog, partial, fin);    \
+    return check_launch("spmm_tma");                                                               \
+  } while (0)
+  if (red) MF_TMA_L(true);
+  else MF_TMA_L(false);
+#undef MF_TMA_L
+}
+
+}  // namespace mf

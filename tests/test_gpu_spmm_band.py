@@ -46,7 +46,8 @@ def test_band_kernel_matches_scipy_and_gather_kernel_bitwise(spmm_knobs, dtype, 
     op = m.ops.csr(ip, ix, d)
     X = torch.randn((n, ld), generator=gen, device="cuda", dtype=d.dtype)
     results = {}
-    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, 4, 4)):
+    # 0: row-group gather kernel, 1: band kernel (register window), 2: TMA-staged band kernel
+    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, -2, 4), (2, 64, 2, 3)):
         lib.mf_spmm_config(band, rows, pfd, minb)
         results[(band, rows)] = op.matmat_blocked(X)
     want = scipy_csr(ip, ix, d, n) @ X.cpu().numpy()
@@ -76,11 +77,11 @@ def test_band_kernel_fused_alpha_dot_in_slq(spmm_knobs, dtype):
     integrand = m.funm.monte_carlo_funm_sym_logdet(m.decomp.tridiag_sym(k, reortho="none"))
     est = m.stochtrace.estimator_monte_carlo(integrand, sampler)
     vals = {}
-    for band in (0, 1):
-        lib.mf_spmm_config(band, 64, 2, 4)
-        vals[band] = est.per_probe(op, key, tile=128).cpu().numpy()
     tol = 1e-5 if dtype == np.float32 else 1e-10
-    assert np.allclose(vals[0], vals[1], rtol=tol * 0.1, atol=0)
+    for band, tile in ((0, 128), (1, 128), (0, 256), (2, 256)):
+        lib.mf_spmm_config(band, 64, 2, 4)
+        vals[band] = est.per_probe(op, key, tile=tile).cpu().numpy()
+        assert np.allclose(vals[0], vals[band], rtol=tol * 0.1, atol=0), (band, tile)
     A = scipy_csr(ip, ix, d, n)
     V = oprng.rademacher(oprng.prng_key(1), (P, n), dtype)
     oq, _ = ref.slq_batched(lambda X: (A @ X.T).T, V, k, reortho="none")

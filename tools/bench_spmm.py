@@ -24,7 +24,7 @@ def main():
     ap.add_argument("--ld", type=int, default=256)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--dtype", default="float32")
-    ap.add_argument("--configs", default="0:64:2:4,1:64:2:4,1:64:0:4,1:64:4:4,1:64:2:3,1:128:2:4,1:32:2:4")
+    ap.add_argument("--configs", default="0:64:2:3,1:64:0:3,2:64:0:3")
     a = ap.parse_args()
     shape = tuple(int(x) for x in a.shape.split(","))
     ld = a.ld
