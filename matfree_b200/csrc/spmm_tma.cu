@@ -26,7 +26,6 @@
 namespace mf {
 namespace {
 
-constexpr int kTmaRows = 16;  // R: rows per chunk
 constexpr int kTmaSegl = 5;
 
 __device__ __forceinline__ void tma_mbar_init(uint64_t* bar, unsigned int count) {
@@ -112,9 +111,9 @@ __device__ __noinline__ TmaRowDot<VEC> tma_gather_row(const int32_t* cols, const
 //   [3][R * 8] int32, [3][R * 8] T     column indices / values of chunks t .. t+2 (<= 8 per row)
 //   [LD] T                             column scales
 //   [2] uint64 mbarrier, [2] int flags
-template <typename T, int VEC, int LD>
+template <typename T, int VEC, int LD, int ROWS>
 struct TmaLayout {
-  static constexpr int R = kTmaRows;
+  static constexpr int R = ROWS;  // rows per chunk
   static constexpr int kStageRows = 3 * R + 2;
   static constexpr int kEntCap = R * 8;
   static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
@@ -127,13 +126,13 @@ struct TmaLayout {
   static constexpr size_t kBytes = kFlagOff + 4 * sizeof(int);
 };
 
-template <typename T, int VEC, int LD, bool FUSE_DOT>
-__global__ void __launch_bounds__(kBlock, 2)
+template <typename T, int VEC, int LD, int ROWS, bool FUSE_DOT>
+__global__ void __launch_bounds__(kBlock, ROWS <= 8 ? 3 : (ROWS <= 16 ? 2 : 1))
 spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
                 unsigned int* __restrict__ progress, double* __restrict__ partial, Finalize fin) {
-  using L = TmaLayout<T, VEC, LD>;
+  using L = TmaLayout<T, VEC, LD, ROWS>;
   constexpr int R = L::R;
   constexpr int SEGL = kTmaSegl;
   constexpr int UD = SEGL / 2;
@@ -376,20 +375,21 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   if (avg > 5.0 || avg <= 4.0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
-  using L = TmaLayout<float, 4, 256>;
-  const int64_t nchunks = (n + L::R - 1) / L::R;
+  static const int env_rows = env_int("MF_SPMM_TMA_ROWS", 16);
   Finalize fin{};
   double* partial = nullptr;
   if (red) {
     fin = red->fin;
     partial = red->partial;
   }
-  SpmmParams prm{(int)ld, L::R, 0, 0, 0, 0, 0, 0, 0, 0};
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;
-#define MF_TMA_L(DOT)                                                                              \
+#define MF_TMA_L(ROWS, DOT)                                                                        \
   do {                                                                                             \
-    auto kern = spmm_tma_kernel<float, 4, 256, DOT>;                                               \
+    using L = TmaLayout<float, 4, 256, ROWS>;                                                      \
+    const int64_t nchunks = (n + L::R - 1) / L::R;                                                 \
+    SpmmParams prm{(int)ld, L::R, 0, 0, 0, 0, 0, 0, 0, 0};                                         \
+    auto kern = spmm_tma_kernel<float, 4, 256, ROWS, DOT>;                                         \
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes) != \
         cudaSuccess) {                                                                             \
       cudaGetLastError();                                                                          \
@@ -397,13 +397,21 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
       return MF_OK;                                                                                \
     }                                                                                              \
     const int grid = resident_grid((const void*)kern, kBlock, L::kBytes, nchunks);                 \
-    prm.window = grid * 4 + (grid > 8 ? grid : 8);                                                 \
+    /* the rows in flight stay one contiguous window of about 24 K rows, as in the other kernels */ \
+    prm.window = grid + (int)(24576 / L::R);                                                       \
     kern<<<grid, kBlock, L::kBytes, st>>>(indptr, indices, (const float*)data, n, (const float*)X, \
                                           (const float*)s, (float*)W, prm, prog, partial, fin);    \
     return check_launch("spmm_tma");                                                               \
   } while (0)
-  if (red) MF_TMA_L(true);
-  else MF_TMA_L(false);
+#define MF_TMA_R(ROWS)            \
+  do {                            \
+    if (red) MF_TMA_L(ROWS, true); \
+    else MF_TMA_L(ROWS, false);    \
+  } while (0)
+  if (env_rows <= 8) MF_TMA_R(8);
+  else if (env_rows <= 16) MF_TMA_R(16);
+  else MF_TMA_R(32);
+#undef MF_TMA_R
 #undef MF_TMA_L
 }
 
