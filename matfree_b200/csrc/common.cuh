@@ -135,10 +135,14 @@ template <int VEC, int NACC = 1>
 __device__ __forceinline__ void cta_reduce_columns_smem(double (&acc)[NACC][VEC], int ld,
                                                         double* __restrict__ partial,
                                                         int64_t partial_stride, double* sh) {
+  // threads beyond kBlock (a kernel's extra producer warp) only take part in the barriers
+  const bool part = threadIdx.x < kBlock;
+  if (part) {
 #pragma unroll
-  for (int a = 0; a < NACC; ++a)
+    for (int a = 0; a < NACC; ++a)
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) sh[a * kBlock * VEC + threadIdx.x * VEC + i] = acc[a][i];
+      for (int i = 0; i < VEC; ++i) sh[a * kBlock * VEC + threadIdx.x * VEC + i] = acc[a][i];
+  }
   __syncthreads();
   // flat element index e = t*VEC+i maps to column e % ld
   const int npairs = NACC * ld;
@@ -147,7 +151,7 @@ __device__ __forceinline__ void cta_reduce_columns_smem(double (&acc)[NACC][VEC]
   const int groups = kBlock / L;
   for (int base = 0; base < npairs; base += groups) {
     const int idx = base + threadIdx.x / L;
-    const bool live = idx < npairs;
+    const bool live = part && idx < npairs;
     const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     double s = 0.0;
     if (live)
@@ -281,9 +285,10 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
     seq = *(volatile unsigned int*)&pc->ctl[rank]->red_seq + 1u;
     buf = (int)(seq & 1u);
   }
+  const bool part = threadIdx.x < kBlock;  // see cta_reduce_columns_smem
   for (int base = 0; base < npairs; base += groups) {
     const int idx = base + threadIdx.x / L;
-    const bool live = idx < npairs;
+    const bool live = part && idx < npairs;
     const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     const double* p = partial + a * partial_stride + c;
     double s = 0.0;
@@ -307,7 +312,7 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
     }
     __syncthreads();
     // every rank adds the same numbers in the same (rank) order: identical bits everywhere
-    for (int idx = threadIdx.x; idx < npairs; idx += kBlock) {
+    for (int idx = threadIdx.x; part && idx < npairs; idx += kBlock) {
       double s = 0.0;
       for (int q = 0; q < world; ++q) s += __ldcv(&mine->slots[buf][q][idx]);
       finalize_write<T>(fin, idx, s);
