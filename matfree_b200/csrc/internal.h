@@ -124,7 +124,7 @@ void spmm_strip_config(int use_strip, int rows, int pfd, int minb);
 int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
                         int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
                         int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
-                        bool* taken);
+                        bool* taken, int64_t bandwidth = 0);
 void spmm_tma_config(int use_tma);
 
 // ---- gemm_simt.cu

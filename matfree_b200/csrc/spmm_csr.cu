@@ -626,7 +626,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     // 5-diagonal band matrices on the 256-wide fp32 tile: X rows staged by TMA (spmm_tma.cu)
     bool taken = false;
     const int32_t rc = launch_spmm_tma(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red, progress,
-                                       st, &taken);
+                                       st, &taken, bandwidth);
     if (taken) return rc;
   }
   {

@@ -1,5 +1,5 @@
-// K2s, TMA route -- CSR times probe block for 5-diagonal band (2-D 5-point stencil) matrices on
-// wide tiles, with the X rows of a chunk staged in shared memory by TMA bulk copies.
+// K2s, TMA route -- CSR times probe block for 5- / 7-diagonal band matrices (2-D 5-point and 3-D
+// 7-point stencils) on wide tiles, with the X rows of a chunk staged in shared memory by TMA bulk copies.
 //
 // Why (profiles/r2f_spmm_2d_*.txt): the row-group kernel (spmm_csr.cu) is bound
 // by the L1 data pipe (83.7 % of peak: 6 global-load requests and 12 shared-memory wavefronts per
@@ -26,7 +26,6 @@
 namespace mf {
 namespace {
 
-constexpr int kTmaSegl = 5;
 
 __device__ __forceinline__ void tma_mbar_init(uint64_t* bar, unsigned int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(
@@ -111,10 +110,11 @@ __device__ __noinline__ TmaRowDot<VEC> tma_gather_row(const int32_t* cols, const
 //   [3][R * 8] int32, [3][R * 8] T     column indices / values of chunks t .. t+2 (<= 8 per row)
 //   [LD] T                             column scales
 //   [2] uint64 mbarrier, [2] int flags
-template <typename T, int VEC, int LD, int ROWS>
+template <typename T, int VEC, int LD, int SEGL, int ROWS>
 struct TmaLayout {
   static constexpr int R = ROWS;  // rows per chunk
-  static constexpr int kStageRows = 3 * R + 2;
+  // SEGL - 3 far diagonals (R rows each) + the run of the three adjacent middle ones (R + 2 rows)
+  static constexpr int kStageRows = (SEGL - 3) * R + R + 2;
   static constexpr int kEntCap = R * 8;
   static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
   static constexpr size_t kPtrOff = 2 * kStageBytes;
@@ -126,16 +126,17 @@ struct TmaLayout {
   static constexpr size_t kBytes = kFlagOff + 4 * sizeof(int);
 };
 
-template <typename T, int VEC, int LD, int ROWS, bool FUSE_DOT>
-__global__ void __launch_bounds__(kBlock + 32, ROWS <= 8 ? 3 : (ROWS <= 16 ? 2 : 1))
+template <typename T, int VEC, int LD, int SEGL, int ROWS, bool FUSE_DOT, bool BLOCKED>
+__global__ void __launch_bounds__(kBlock + 32, (SEGL == 5 && ROWS <= 8) ? 3 : (ROWS * (SEGL - 2) <= 48 ? 2 : 1))
 spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
                 unsigned int* __restrict__ progress, double* __restrict__ partial, Finalize fin) {
-  using L = TmaLayout<T, VEC, LD, ROWS>;
+  using L = TmaLayout<T, VEC, LD, SEGL, ROWS>;
   constexpr int R = L::R;
-  constexpr int SEGL = kTmaSegl;
   constexpr int UD = SEGL / 2;
+  constexpr int MID = (UD - 1) * R;  // first stage row of the middle run
+  static_assert(SEGL == 5 || SEGL == 7, "5- or 7-diagonal bands");
   constexpr int ld = LD;
   constexpr int tpr = LD / VEC;
   constexpr int rps = kBlock / tpr;  // row-groups per CTA
@@ -177,12 +178,21 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
 
-  auto rows_of = [&](int64_t c) -> int { return (int)((n - c * R) < R ? (n - c * R) : R); };
+  // first row of chunk c: ascending order, or the blocked order of SpmmParams (3-D stencils)
+  auto row0_of = [&](int64_t c) -> int64_t {
+    if constexpr (BLOCKED) return chunk_row0(c, p);
+    else return c * (int64_t)R;
+  };
+  auto rows_of = [&](int64_t c) -> int {
+    const int64_t r0c = row0_of(c);
+    return (int)((n - r0c) < R ? (n - r0c) : R);
+  };
   auto issue_ptr = [&](int64_t c, int buf) {
     if (c < nchunks && !producer) {
       const int nr = rows_of(c);
+      const int64_t r0c = row0_of(c);
       for (int i = threadIdx.x; i <= nr; i += kBlock)
-        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf * (R + 1) + i]), indptr + c * R + i);
+        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf * (R + 1) + i]), indptr + r0c + i);
     }
   };
   auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
@@ -204,7 +214,9 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   auto verify_and_stage = [&](int64_t c, int pbuf, int ebuf, int stage) {
     if (!producer) return;
     bool band = false;
-    int32_t ca = 0, cd = 0, cc = 0;
+    int32_t cf[SEGL];  // columns of the first row's entries
+#pragma unroll
+    for (int u = 0; u < SEGL; ++u) cf[u] = 0;
     if (c < nchunks) {
       const int nr = rows_of(c);
       const int32_t* ptrb = s_ptr + pbuf * (R + 1);
@@ -220,10 +232,9 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
         }
       }
       if (ok && lane == 0) {
-        ca = colb[0];
-        cd = colb[UD];
-        cc = colb[SEGL - 1];
-        ok = (int64_t)cd == c * R && colb[UD - 1] == cd - 1 && colb[UD + 1] == cd + 1;
+#pragma unroll
+        for (int u = 0; u < SEGL; ++u) cf[u] = colb[u];
+        ok = (int64_t)cf[UD] == row0_of(c) && cf[UD - 1] == cf[UD] - 1 && cf[UD + 1] == cf[UD] + 1;
       }
       band = __all_sync(0xffffffffu, ok);
     }
@@ -233,9 +244,14 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       constexpr unsigned int row_bytes = LD * sizeof(T);
       tma_mbar_expect_tx(&s_bar[stage], band ? (unsigned int)L::kStageRows * row_bytes : 0u);
       if (band) {
-        tma_bulk_g2s(xs, X + (int64_t)ca * LD, R * row_bytes, &s_bar[stage]);
-        tma_bulk_g2s(xs + (size_t)R * LD, X + (int64_t)(cd - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
-        tma_bulk_g2s(xs + (size_t)(2 * R + 2) * LD, X + (int64_t)cc * LD, R * row_bytes, &s_bar[stage]);
+#pragma unroll
+        for (int u = 0; u < UD - 1; ++u)  // far diagonals below the middle run
+          tma_bulk_g2s(xs + (size_t)(u * R) * LD, X + (int64_t)cf[u] * LD, R * row_bytes, &s_bar[stage]);
+        tma_bulk_g2s(xs + (size_t)MID * LD, X + (int64_t)(cf[UD] - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
+#pragma unroll
+        for (int u = UD + 2; u < SEGL; ++u)  // far diagonals above it
+          tma_bulk_g2s(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R) * LD, X + (int64_t)cf[u] * LD,
+                       R * row_bytes, &s_bar[stage]);
       }
     }
   };
@@ -272,7 +288,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     issue_ptr(ch + 3 * G, (int)((t + 3) & 3));
     cp_async_commit();
 
-    const int64_t r0 = ch * R;
+    const int64_t r0 = row0_of(ch);
     const int nr = rows_of(ch);
     const int32_t* __restrict__ ptrb = s_ptr + pb * (R + 1);
     const int32_t base = ptrb[0];
@@ -286,9 +302,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     const int lr0 = grp * S;
     if (s_band[stage]) {
       const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
-      const T* __restrict__ xa = xs + (size_t)lr0 * LD;                  // run A: row lr
-      const T* __restrict__ xb = xs + (size_t)(R + lr0) * LD;            // run B: rows lr, lr+1, lr+2
-      const T* __restrict__ xc = xs + (size_t)(2 * R + 2 + lr0) * LD;    // run C: row lr
+      const T* __restrict__ xb = xs + (size_t)(MID + lr0) * LD;  // middle run: rows lr, lr+1, lr+2
       T x[SEGL][VEC];
       vec_load<T>(xb, x[UD - 1]);
       vec_load<T>(xb + LD, x[UD]);
@@ -296,9 +310,12 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       int64_t off = coff + (int64_t)lr0 * ld;
 #pragma unroll
       for (int i = 0; i < S; ++i) {
-        vec_load<T>(xa + (size_t)i * LD, x[0]);
+#pragma unroll
+        for (int u = 0; u < UD - 1; ++u) vec_load<T>(xs + (size_t)(u * R + lr0 + i) * LD, x[u]);
         vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
-        vec_load<T>(xc + (size_t)i * LD, x[SEGL - 1]);
+#pragma unroll
+        for (int u = UD + 2; u < SEGL; ++u)
+          vec_load<T>(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R + lr0 + i) * LD, x[u]);
         T sum[VEC];
 #pragma unroll
         for (int q = 0; q < VEC; ++q) sum[q] = T(0);
@@ -373,12 +390,13 @@ void spmm_tma_config(int use_tma) {
 int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
                         int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
                         int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
-                        bool* taken) {
+                        bool* taken, int64_t bandwidth) {
   *taken = false;
   if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
   if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
   const double avg = (double)nnz / (double)n;
-  if (avg > 5.0 || avg <= 4.0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
+  const int segl = (avg > 4.0 && avg <= 5.0) ? 5 : ((avg > 6.0 && avg <= 7.0) ? 7 : 0);
+  if (segl == 0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
   static const int env_rows = env_int("MF_SPMM_TMA_ROWS", 16);
@@ -390,12 +408,10 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   }
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;
-#define MF_TMA_L(ROWS, DOT)                                                                        \
+#define MF_TMA_K(SEGL, ROWS, DOT, BLK)                                                             \
   do {                                                                                             \
-    using L = TmaLayout<float, 4, 256, ROWS>;                                                      \
-    const int64_t nchunks = (n + L::R - 1) / L::R;                                                 \
-    SpmmParams prm{(int)ld, L::R, 0, 0, 0, 0, 0, 0, 0, 0};                                         \
-    auto kern = spmm_tma_kernel<float, 4, 256, ROWS, DOT>;                                         \
+    using L = TmaLayout<float, 4, 256, SEGL, ROWS>;                                                \
+    auto kern = spmm_tma_kernel<float, 4, 256, SEGL, ROWS, DOT, BLK>;                              \
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes) != \
         cudaSuccess) {                                                                             \
       cudaGetLastError();                                                                          \
@@ -406,20 +422,33 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
     /* the rows in flight stay one contiguous window of about 24 K rows, as in the other kernels */ \
     prm.window = grid + (int)(24576 / L::R);                                                       \
     kern<<<grid, kBlock + 32, L::kBytes, st>>>(indptr, indices, (const float*)data, n,             \
-                                               (const float*)X,                                    \
-                                          (const float*)s, (float*)W, prm, prog, partial, fin);    \
+                                               (const float*)X, (const float*)s, (float*)W, prm,   \
+                                               prog, partial, fin);                                \
     return check_launch("spmm_tma");                                                               \
   } while (0)
-#define MF_TMA_R(ROWS)            \
-  do {                            \
-    if (red) MF_TMA_L(ROWS, true); \
-    else MF_TMA_L(ROWS, false);    \
+#define MF_TMA_R(SEGL, ROWS)                                                                       \
+  do {                                                                                             \
+    const int64_t nchunks = (n + (ROWS) - 1) / (ROWS);                                             \
+    SpmmParams prm{(int)ld, ROWS, 0, 0, 0, 0, 0, 0, 0, 0};                                         \
+    choose_row_order(&prm, n, avg, bandwidth, ld, dtype);                                          \
+    if (prm.block_rows != 0) {                                                                     \
+      if (red) MF_TMA_K(SEGL, ROWS, true, true);                                                   \
+      else MF_TMA_K(SEGL, ROWS, false, true);                                                      \
+    } else {                                                                                       \
+      if (red) MF_TMA_K(SEGL, ROWS, true, false);                                                  \
+      else MF_TMA_K(SEGL, ROWS, false, false);                                                     \
+    }                                                                                              \
   } while (0)
-  if (env_rows <= 8) MF_TMA_R(8);
-  else if (env_rows <= 16) MF_TMA_R(16);
-  else MF_TMA_R(32);
+  if (segl == 5) {
+    if (env_rows <= 8) MF_TMA_R(5, 8);
+    else if (env_rows <= 16) MF_TMA_R(5, 16);
+    else MF_TMA_R(5, 32);
+  } else {
+    if (env_rows <= 8) MF_TMA_R(7, 8);
+    else MF_TMA_R(7, 16);
+  }
 #undef MF_TMA_R
-#undef MF_TMA_L
+#undef MF_TMA_K
 }
 
 }  // namespace mf

@@ -107,7 +107,7 @@ def test_band_kernel_irregular_matrix_falls_back_row_by_row(spmm_knobs):
     assert np.allclose(W1.cpu().numpy(), A @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
-def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical():
+def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical(spmm_knobs):
     """A 3-D stencil whose planes (bandwidth = 256^2 rows of 1 KB) exceed what L2 keeps between
     their uses is walked in a blocked row order (mf_operator_t::csr_bandwidth, csrc/spmm_csr.cu);
     a narrow tile of the same operator is walked in ascending order.  Row arithmetic is the same,
@@ -127,6 +127,9 @@ def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical():
     Xn = X[:, :32].contiguous()
     Wn = op.matmat_blocked(Xn)                    # 2 * 8 MB planes: ascending order
     assert torch.equal(W[:, :32], Wn)
+    spmm_knobs.mf_spmm_config(2, 64, 2, 3)        # the TMA-staged 7-diagonal kernel, blocked order
+    assert torch.equal(op.matmat_blocked(X), W)
+    spmm_knobs.mf_spmm_config(0, 64, 2, 3)
     rows = torch.tensor([0, 1, 255, 256, 65535, 65536, 65537, n // 2 + 3, n - 65537, n - 1], device="cuda")
     A = scipy_csr(ip, ix, d, n)
     want = A[rows.cpu().numpy()] @ X.cpu().numpy()
