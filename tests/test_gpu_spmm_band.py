@@ -28,7 +28,7 @@ def spmm_knobs():
 
     lib = _lib.load()
     yield lib
-    lib.mf_spmm_config(0, 64, 2, 3)  # the library defaults
+    lib.mf_spmm_config(2, 64, 2, 3)  # the library defaults
 
 
 @pytest.mark.parametrize("dtype,ld", [("float32", 256), ("float32", 128), ("float64", 256), ("float64", 64)])
@@ -127,9 +127,8 @@ def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical(spmm_knobs):
     Xn = X[:, :32].contiguous()
     Wn = op.matmat_blocked(Xn)                    # 2 * 8 MB planes: ascending order
     assert torch.equal(W[:, :32], Wn)
-    spmm_knobs.mf_spmm_config(2, 64, 2, 3)        # the TMA-staged 7-diagonal kernel, blocked order
+    spmm_knobs.mf_spmm_config(0, 64, 2, 3)        # gather kernel forced (7 diagonals take it anyway)
     assert torch.equal(op.matmat_blocked(X), W)
-    spmm_knobs.mf_spmm_config(0, 64, 2, 3)
     rows = torch.tensor([0, 1, 255, 256, 65535, 65536, 65537, n // 2 + 3, n - 65537, n - 1], device="cuda")
     A = scipy_csr(ip, ix, d, n)
     want = A[rows.cpu().numpy()] @ X.cpu().numpy()
