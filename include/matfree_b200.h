@@ -173,7 +173,8 @@ int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
  * least one warp per row take the band kernel (csrc/spmm_strip.cu: register window over adjacent
  * diagonals, TMA bulk copies of the CSR metadata); 2 = 5-diagonal band matrices on the 256-wide
  * fp32 tile take the TMA-staged kernel (csrc/spmm_tma.cu: the X rows of a chunk land in shared
- * memory by cp.async.bulk one chunk ahead).  All three produce the same bits; the default is 2,
+ * memory by cp.async.bulk one chunk ahead); 3 = as 2, plus its 7-diagonal variant (3-D stencils;
+ * measured slower than the gather kernel, opt-in).  All produce the same bits; the default is 2,
  * the one measured fastest on B200 (profiles/); matrices / tiles a kernel does not take fall
  * through to the row-group gather kernel.
  * rows_per_chunk (default 64), prefetch_rows (> 0: L2 prefetch distance, < 0: L1 prefetch

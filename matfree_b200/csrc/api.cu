@@ -659,7 +659,8 @@ int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t 
                        int32_t min_ctas_per_sm) {
   // 0: row-group gather kernel; 1: band kernel (register window); 2 (default): band kernel with
   // the X rows staged in shared memory by TMA
-  if (use_band_kernel >= 0) spmm_tma_config(use_band_kernel == 2 ? 1 : 0);
+  // 3: as 2, and 7-diagonal matrices take the TMA kernel as well (measured slower: opt-in)
+  if (use_band_kernel >= 0) spmm_tma_config(use_band_kernel >= 2 ? use_band_kernel - 1 : 0);
   spmm_strip_config(use_band_kernel < 0 ? -1 : (use_band_kernel == 1 ? 1 : 0), rows_per_chunk,
                     prefetch_rows, min_ctas_per_sm);
   return MF_OK;

@@ -383,7 +383,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
 // On by default for 5-diagonal matrices: 7.0-7.3 ms per product inside the Lanczos step of BASELINE
 // config 2 against 7.8-9.0 ms for the row-group kernel on the same pods, step 0.87-0.89 instead of
 // 0.80-0.86 of the HBM roofline (profiles/r2n_instep.jsonl, r2o_instep.jsonl).  The 7-diagonal variant
-// is opt-in (MF_SPMM_TMA7=1): on the 3-D workload it is slower than the row-group kernel (18.7 vs
+// is opt-in (MF_SPMM_TMA=2, mf_spmm_config(3, ...)): on the 3-D workload it is slower than the row-group kernel (18.7 vs
 // 12.1 ms) -- five staged runs per chunk put 10 KB per row through the shared-memory port, and 1 in
 // 16-32 chunks holds a boundary row and takes the gather path.
 std::atomic<int> g_tma{env_int("MF_SPMM_TMA", 1)};
@@ -402,8 +402,8 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
   if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
   const double avg = (double)nnz / (double)n;
-  static const int env_tma7 = env_int("MF_SPMM_TMA7", 0);
-  const int segl = (avg > 4.0 && avg <= 5.0) ? 5 : ((env_tma7 && avg > 6.0 && avg <= 7.0) ? 7 : 0);
+  const bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;
+  const int segl = (avg > 4.0 && avg <= 5.0) ? 5 : ((tma7 && avg > 6.0 && avg <= 7.0) ? 7 : 0);
   if (segl == 0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);

@@ -47,7 +47,7 @@ def test_band_kernel_matches_scipy_and_gather_kernel_bitwise(spmm_knobs, dtype, 
     X = torch.randn((n, ld), generator=gen, device="cuda", dtype=d.dtype)
     results = {}
     # 0: row-group gather kernel, 1: band kernel (register window), 2: TMA-staged band kernel
-    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, -2, 4), (2, 64, 2, 3)):
+    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, -2, 4), (2, 64, 2, 3), (3, 64, 2, 3)):
         lib.mf_spmm_config(band, rows, pfd, minb)
         results[(band, rows)] = op.matmat_blocked(X)
     want = scipy_csr(ip, ix, d, n) @ X.cpu().numpy()
@@ -127,7 +127,9 @@ def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical(spmm_knobs):
     Xn = X[:, :32].contiguous()
     Wn = op.matmat_blocked(Xn)                    # 2 * 8 MB planes: ascending order
     assert torch.equal(W[:, :32], Wn)
-    spmm_knobs.mf_spmm_config(0, 64, 2, 3)        # gather kernel forced (7 diagonals take it anyway)
+    spmm_knobs.mf_spmm_config(3, 64, 2, 3)        # the TMA-staged 7-diagonal kernel, blocked order
+    assert torch.equal(op.matmat_blocked(X), W)
+    spmm_knobs.mf_spmm_config(0, 64, 2, 3)        # the gather kernel, forced
     assert torch.equal(op.matmat_blocked(X), W)
     rows = torch.tensor([0, 1, 255, 256, 65535, 65536, 65537, n // 2 + 3, n - 65537, n - 1], device="cuda")
     A = scipy_csr(ip, ix, d, n)
