@@ -404,12 +404,14 @@ def run_ours(a, rank, local_rank, world):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
-    # ---- N > 1: multi-GPU parity on the live process group + BASELINE config 4 (collective: all ranks)
-    extras = {}
-    if world > 1 and not a.no_extras and a.workload == "c2":
+    def multi_gpu_extras():
+        """N > 1 (collective: every rank calls it): multi-GPU parity on the live process group +
+        BASELINE config 4.  Never raises."""
+        extras = {}
+        if not (world > 1 and not a.no_extras and a.workload == "c2"):
+            return extras
         from matfree_b200 import _multicheck
 
-        del op
         torch.cuda.empty_cache()
         try:
             extras["multi_gpu_checks"] = {"probe_sharding": _multicheck.probe_sharding(dev),
@@ -424,8 +426,29 @@ def run_ours(a, rank, local_rank, world):
         except Exception as exc:
             extras["c4_rowshard"] = {"parity_ok": False, "error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+        return extras
 
+    # The extras must never cost the headline line: if a rank fails inside them the others would
+    # wait in a collective for ever, so every rank arms a watchdog; on expiry rank 0 prints the line
+    # it already has (with the failure recorded) and all ranks leave.
+    guard = {"line": None, "done": False}
+
+    def watchdog():
+        if guard["done"]:
+            return
+        if rank == 0 and guard["line"] is not None:
+            guard["line"]["multi_gpu_checks"] = {"all_ok": False, "error": "extras timed out after 420 s"}
+            print(json.dumps(guard["line"]), flush=True)
+        os._exit(0)
+
+    del op
     if rank != 0:
+        timer = threading.Timer(420.0, watchdog)
+        timer.daemon = True
+        timer.start()
+        multi_gpu_extras()
+        guard["done"] = True
+        timer.cancel()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -478,7 +501,15 @@ def run_ours(a, rank, local_rank, world):
         "result": {"logdet_estimate": mean, "sem": sem, "closed_form_logdet": truth,
                    "rel_err": abs(mean - truth) / abs(truth)},
     }
-    line.update(extras)
+    if world > 1:
+        guard["line"] = line
+        timer = threading.Timer(420.0, watchdog)
+        timer.daemon = True
+        timer.start()
+        extras = multi_gpu_extras()
+        guard["done"] = True
+        timer.cancel()
+        line.update(extras)
 
     # ---- CPU baseline (rank 0, N = 1 only), bounded sample
     if world == 1 and not a.no_cpu_baseline:
@@ -487,7 +518,6 @@ def run_ours(a, rank, local_rank, world):
 
             port.build()
             port.set_threads()
-            op = None
             del ip, ix, d
             torch.cuda.empty_cache()
             csr = (h_ip.numpy(), h_ix.numpy(), h_d.numpy())
@@ -502,7 +532,6 @@ def run_ours(a, rank, local_rank, world):
                                     "sample": f"failed: {exc}"}
     # ---- N = 1: supplementary workloads (tensor-core evidence for C3, the literal 3-D target)
     if world == 1 and not a.no_extras and a.workload == "c2":
-        op = None
         h_ip = h_ix = h_d = None
         torch.cuda.empty_cache()
         for key_, wl in (("c3", "c3"), ("c2_3d", "c2-3d")):
@@ -522,7 +551,7 @@ def supplementary_line(workload):
            "--no-cpu-baseline", "--no-e2e", "--no-extras"]
     if workload == "c2-3d":
         cmd += ["--tile", "64"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if out.returncode != 0 or not lines:
         raise RuntimeError((out.stderr or out.stdout)[-400:])
