@@ -274,7 +274,7 @@ def run_reference(a, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -438,7 +438,7 @@ def run_ours(a, rank, local_rank, world):
             return
         if rank == 0 and guard["line"] is not None:
             guard["line"]["multi_gpu_checks"] = {"all_ok": False, "error": "extras timed out after 420 s"}
-            print(json.dumps(guard["line"]), flush=True)
+            emit(guard["line"])
         os._exit(0)
 
     del op
@@ -539,7 +539,7 @@ def run_ours(a, rank, local_rank, world):
                 line[key_] = supplementary_line(wl)
             except Exception as exc:
                 line[key_] = {"error": f"{type(exc).__name__}: {exc}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -713,9 +713,29 @@ def run_ours_c3(a, rank, local_rank, world):
                                     "note": "oracle/ref.py slq_batched over NumPy/BLAS sgemm; the JAX reference cannot be installed here"}
         except Exception as exc:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+_JSON_FD = None
+
+
+def claim_stdout():
+    """fd 1 carries exactly the one JSON line: whatever a native library prints there (NCCL's version
+    banner at NCCL_DEBUG >= VERSION, ...) is sent to stderr instead."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -727,14 +747,15 @@ def main():
         a.probes_per_gpu, a.depth = 2048, 20  # C3's own numbers (16384 probes over 8 GPUs)
     if a.grid <= 0:
         a.grid = 256 if a.workload == "c2-3d" else 4096
-    if a.impl == "reference":
-        run_reference(a, rank, world)
-        return
     if world != a.gpus and world == 1 and a.gpus > 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
         raise SystemExit(subprocess.call(cmd))
+    claim_stdout()
+    if a.impl == "reference":
+        run_reference(a, rank, world)
+        return
     if a.workload == "c3":
         run_ours_c3(a, rank, local_rank, world)
     else:
