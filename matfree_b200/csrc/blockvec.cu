@@ -8,6 +8,7 @@
 // thread always owns the same probe columns; per-column sums are accumulated in
 // fp64 registers, reduced deterministically inside the CTA and written as one
 // partial row per CTA; `finalize` adds the partial rows in a fixed order.
+#include <cuda.h>
 #include <cstdlib>
 
 #include "internal.h"
@@ -316,142 +317,191 @@ reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T*
 // Second half of the first Gram-Schmidt pass and first half of the second one in ONE sweep over
 // the basis (matfree/decomp.py:464 and :468):   V <- V - sum_j h_j Q_j ;  h'_j = Q_j . V  (new V).
 // The two need the basis in different shapes -- the update wants, per row, all j; the dots want,
-// per j, all rows -- so the tile Q[0..nq)[R rows] is staged ONCE in shared memory (cp.async,
-// double-buffered, one CTA of R threads per SM, ~100 KB per stage) and read twice from there:
-//   phase A: thread t owns row t of the tile: s = sum_j h_j Qs[j][t]; V' = V - s  -> global + smem
-//   phase B: warp w owns the vectors j = w, w + 8, ... and keeps their fp64 sums in registers for
-//            the whole kernel; lane l covers rows l, l + 32, ... of the tile.
+// per j, all rows -- so the tile Q[0..nq)[R rows] is staged in shared memory and each consumer
+// warp pulls the vectors it owns (j = w, w + 15, ...) into REGISTERS once:
+//   producer: warp 15 issues one TMA bulk copy (cp.async.bulk, 1 KB) per basis vector and tile
+//             into a ring of 2..8 stages, tracked by full / empty mbarriers;
+//   phase A : warp w, lane l: q_j = Qs[j][rows 4l..4l+3 and 128+4l..] for its vectors;
+//             s = sum_j h_j q_j -> sp[w]
+//   middle  : thread t < R adds the 15 warps' sums in warp order; V' = V - s -> global + vs
+//   phase B : the same registers q_j against vs: fp64 sums per vector, kept for the whole kernel.
 // One sweep over Q instead of two: CGS twice costs 3 sweeps of the basis per Arnoldi step, not 4.
-constexpr int kCgsRows = 256;     // rows (flat elements) per tile
-constexpr int kCgsThreads = 512;  // 16 warps (8 left the two shared-memory phases latency-bound; 32 are no faster)
-constexpr int kCgsMaxNq = 104;    // (nq + 1) * kCgsRows * 4 B per stage, two stages <= 227 KB
-constexpr int kCgsJW = (kCgsMaxNq + kCgsThreads / 32 - 1) / (kCgsThreads / 32);
+// History (profiles/r1v_*, r2t_cgs.txt): the first version staged with cp.async from all warps and
+// read the stage twice from shared memory; ncu showed it issue-bound (330 instructions per warp
+// and 128-row tile, a third of them LDGSTS and their address arithmetic) at 0.54-0.69 of HBM.
+constexpr int kCgsRows = 256;         // rows (flat elements) per tile
+constexpr int kCgsConsumers = 480;    // 15 consumer warps (+ the producer = 512 threads: 128 registers each)
+constexpr int kCgsThreads = kCgsConsumers + 32;  // + the producer warp
+constexpr int kCgsMaxNq = 102;        // (nq + 1) KB per stage, two stages + vs + sp <= 225 KB
+constexpr int kCgsJW = (kCgsMaxNq + kCgsConsumers / 32 - 1) / (kCgsConsumers / 32);
+constexpr int kCgsMaxStages = 8;
+constexpr int kCgsSmemMax = 225 * 1024;  // + 1 KB static (alignment) stay below the 227 KB opt-in limit
+constexpr int kCgsFixedBytes = (kCgsRows + (kCgsConsumers / 32) * kCgsRows) * 4 + 2 * kCgsMaxStages * 8;
 
-__device__ __forceinline__ void cgs_cp16(void* smem, const void* gmem, int bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(bytes));
+__device__ __forceinline__ uint32_t cgs_saddr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cgs_mbar_init(uint64_t* bar, unsigned int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cgs_saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cgs_mbar_expect_tx(uint64_t* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cgs_saddr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cgs_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cgs_saddr(bar)) : "memory");
+}
+// bounded wait: a protocol bug must surface as a CUDA error, never as a hung GPU
+__device__ __forceinline__ void cgs_mbar_wait(uint64_t* bar, unsigned int parity) {
+  const uint32_t a = cgs_saddr(bar);
+#pragma unroll 1
+  for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
+    unsigned int done;
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        " selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// one box of a 2-D tensor map (rows c0.., vectors c1..) into shared memory
+__device__ __forceinline__ void cgs_tma_box(void* smem_dst, const CUtensorMap* map, int c0, int c1,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          cgs_saddr(smem_dst)), "l"(map), "r"(cgs_saddr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void cgs_consumer_sync() {  // the 16 consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(kCgsConsumers) : "memory");
 }
 
 __global__ void __launch_bounds__(kCgsThreads, 1)
-cgs_update_dots_kernel(const float* __restrict__ Q, int64_t q_stride, int nq,
-                       const float* __restrict__ h, float* __restrict__ V, int64_t total, int ld,
-                       double* __restrict__ partial, int64_t partial_stride, Finalize fin) {
-  constexpr int R = kCgsRows, NT = kCgsThreads, NW = NT / 32;
-  extern __shared__ __align__(16) float cgs_smem[];
+cgs_update_dots_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmV,
+                       int nq, const float* __restrict__ h, float* __restrict__ V, int64_t total, int ld,
+                       int stages, double* __restrict__ partial, int64_t partial_stride,
+                       Finalize fin) {
+  constexpr int R = kCgsRows, NW = kCgsConsumers / 32;
+  extern __shared__ __align__(1024) float cgs_smem[];
   const int stage_floats = (nq + 1) * R;  // nq basis segments + the segment of V
-  constexpr int G = NT / R;                   // threads per row in phase A
-  const int nqg = (nq + 4 * G - 1) / (4 * G) * (4 * G);  // G parts of whole float4 groups
-  float* vs = cgs_smem + 2 * stage_floats;   // [R] updated V of the current tile
-  float* sp = vs + R;                         // [G - 1][R] partial sums of the other parts of the j range
-  float* hs = sp + (G - 1) * R;               // [nqg]: coefficients, zero-padded (ld == 1)
+  float* vs = cgs_smem + stages * stage_floats;  // [R] updated V of the current tile
+  float* sp = vs + R;                            // [NW][R] the warps' shares of sum_j h_j Q_j
+  uint64_t* full = reinterpret_cast<uint64_t*>(sp + NW * R);  // [stages] data of the stage has landed
+  uint64_t* empty = full + kCgsMaxStages;                     // [stages] the stage may be refilled
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // All of shared memory starts as zeros: phase A reads up to 4 G - 1 segments past the last
-  // basis vector with a zero coefficient, and 0 * (stale bits that happen to be NaN) is NaN.
-  {
-    const int all = 2 * stage_floats + R + (G - 1) * R + nqg + 4 * G * R;  // + read-ahead padding
-    for (int i = tid; i < all; i += NT) cgs_smem[i] = 0.f;
-  }
+  if (tid == 0)
+    for (int s = 0; s < stages; ++s) {
+      cgs_mbar_init(&full[s], 1);
+      cgs_mbar_init(&empty[s], 1);
+    }
+  // the barriers must be visible to the TMA unit (async proxy)
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  for (int i = tid; i < nq; i += NT) hs[i] = h[i];
-
   const int64_t ntiles = (total + R - 1) / R;
-  // A warp copies whole 1 KB segments (segment j = warp, warp + NW, ...: lane l moves the 16-byte
-  // chunks l and l + 32), so the inner loop has no divisions and one pointer per segment.
-  auto issue = [&](int buf, int64_t tile) {
-    float* st = cgs_smem + buf * stage_floats;
-    const int64_t base = tile * R;
-    const int64_t left0 = (total - base - lane * 4) * 4;         // bytes left from chunk `lane`
-    const int64_t left1 = left0 - 32 * 16;                       // ... from chunk `lane + 32`
-    const int b0 = left0 >= 16 ? 16 : (left0 > 0 ? (int)left0 : 0);
-    const int b1 = left1 >= 16 ? 16 : (left1 > 0 ? (int)left1 : 0);
-    for (int j = warp; j <= nq; j += NW) {
-      const float* src = (j < nq ? Q + (int64_t)j * q_stride : V) + base + lane * 4;
-      float* dst = st + j * R + lane * 4;
-      cgs_cp16(dst, b0 ? (const void*)src : (const void*)V, b0);
-      cgs_cp16(dst + 128, b1 ? (const void*)(src + 128) : (const void*)V, b1);
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  };
 
-  double acc[kCgsJW];
-#pragma unroll
-  for (int jj = 0; jj < kCgsJW; ++jj) acc[jj] = 0.0;
-
-  int64_t tile = blockIdx.x;
-  if (tile < ntiles) issue(0, tile);
-  for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
-    const int buf = it & 1;
-    const int64_t next = tile + gridDim.x;
-    if (next < ntiles) {
-      issue(buf ^ 1, next);
-      asm volatile("cp.async.wait_group 1;\n" ::);
-    } else {
-      asm volatile("cp.async.wait_group 0;\n" ::);
-    }
-    __syncthreads();
-    const float* Qs = cgs_smem + buf * stage_floats;
-    // phase A: G threads per row, each over one part of the basis vectors (four coefficients
-    // per shared-memory load); parts 1..G-1 park their sums in sp
-    {
-      const int rowA = tid & (R - 1), half = tid / R;
-      const int jbeg = half * (nqg / G), jend = jbeg + nqg / G;
-      const float4* hc = reinterpret_cast<const float4*>(hs);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int j = jbeg; j < jend; j += 4) {
-        // segments nq .. nqg-1 (the V segment and what follows it in shared memory) meet zero
-        // coefficients; they are finite (user data or the zeros written above)
-        const float4 hv = hc[j >> 2];
-        s0 += hv.x * Qs[(j + 0) * R + rowA];
-        s1 += hv.y * Qs[(j + 1) * R + rowA];
-        s2 += hv.z * Qs[(j + 2) * R + rowA];
-        s3 += hv.w * Qs[(j + 3) * R + rowA];
-      }
-      const float sA = (s0 + s1) + (s2 + s3);
-      if (half > 0) sp[(half - 1) * R + rowA] = sA;
-      __syncthreads();
-      if (half == 0) {
-        const int64_t f = tile * R + rowA;
-        float v = 0.f;
-        if (f < total) {
-          float sall = sA;
-#pragma unroll
-          for (int g = 1; g < G; ++g) sall += sp[(g - 1) * R + rowA];
-          v = Qs[nq * R + rowA] - sall;
-          V[f] = v;
+  if (warp == NW) {
+    // ---- producer: ONE thread, two TMA instructions per tile -- the box [256 rows] x [nq vectors]
+    // of the basis and the 256 rows of V; rows past the end arrive as zeros (and are counted).
+    // (Per-vector bulk copies from the lanes of a warp serialise, ~70 cycles each: r2t_cgs.txt.)
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+      int st = 0;
+      unsigned int round = 0;  // how often the ring has wrapped
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (round > 0) cgs_mbar_wait(&empty[st], (round - 1) & 1u);
+        cgs_mbar_expect_tx(&full[st], (unsigned int)stage_floats * 4u);
+        float* dst = cgs_smem + st * stage_floats;
+        cgs_tma_box(dst, &tmQ, (int)(tile * R), 0, &full[st]);
+        cgs_tma_box(dst + nq * R, &tmV, (int)(tile * R), 0, &full[st]);
+        if (++st == stages) {
+          st = 0;
+          ++round;
         }
-        vs[rowA] = v;
       }
     }
-    __syncthreads();
-    // phase B: this warp's vectors against the whole tile.  Lane l covers rows 4l..4l+3 and
-    // 128+4l..128+4l+3 (two 16-byte loads per vector); the 8 products of a vector are summed in
-    // fp32 and added to the fp64 accumulator once per tile.
-    const float4 va = reinterpret_cast<const float4*>(vs)[lane];
-    const float4 vb = reinterpret_cast<const float4*>(vs)[32 + lane];
+  } else {
+    // ---- consumer warps
+    float hw[kCgsJW];  // coefficients of this warp's vectors (ld == 1)
 #pragma unroll
     for (int jj = 0; jj < kCgsJW; ++jj) {
       const int jv = warp + jj * NW;
-      if (jv < nq) {
-        const float4 qa = reinterpret_cast<const float4*>(Qs + jv * R)[lane];
-        const float4 qb = reinterpret_cast<const float4*>(Qs + jv * R)[32 + lane];
-        float p0 = qa.x * va.x, p1 = qa.y * va.y, p2 = qa.z * va.z, p3 = qa.w * va.w;
-        p0 += qb.x * vb.x;
-        p1 += qb.y * vb.y;
-        p2 += qb.z * vb.z;
-        p3 += qb.w * vb.w;
+      hw[jj] = jv < nq ? h[jv] : 0.f;
+    }
+    double acc[kCgsJW];
+#pragma unroll
+    for (int jj = 0; jj < kCgsJW; ++jj) acc[jj] = 0.0;
+    int st = 0;
+    unsigned int round = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      cgs_mbar_wait(&full[st], round & 1u);
+      const float* Qs = cgs_smem + st * stage_floats;
+      float4 qa[kCgsJW], qb[kCgsJW];
+      float4 sa = make_float4(0.f, 0.f, 0.f, 0.f), sb = sa;
+#pragma unroll
+      for (int jj = 0; jj < kCgsJW; ++jj) {
+        const int jv = warp + jj * NW;
+        qa[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+        qb[jj] = qa[jj];
+        if (jv < nq) {
+          qa[jj] = reinterpret_cast<const float4*>(Qs + jv * R)[lane];
+          qb[jj] = reinterpret_cast<const float4*>(Qs + jv * R)[32 + lane];
+          sa.x += hw[jj] * qa[jj].x;
+          sa.y += hw[jj] * qa[jj].y;
+          sa.z += hw[jj] * qa[jj].z;
+          sa.w += hw[jj] * qa[jj].w;
+          sb.x += hw[jj] * qb[jj].x;
+          sb.y += hw[jj] * qb[jj].y;
+          sb.z += hw[jj] * qb[jj].z;
+          sb.w += hw[jj] * qb[jj].w;
+        }
+      }
+      reinterpret_cast<float4*>(sp + warp * R)[lane] = sa;
+      reinterpret_cast<float4*>(sp + warp * R)[32 + lane] = sb;
+      cgs_consumer_sync();
+      if (tid < R) {
+        const int64_t f = tile * R + tid;
+        float sall = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) sall += sp[w * R + tid];
+        float v = 0.f;
+        if (f < total) {
+          v = Qs[nq * R + tid] - sall;
+          V[f] = v;
+        }
+        vs[tid] = v;
+      }
+      cgs_consumer_sync();
+      // the stage is consumed (the vectors sit in registers, the V segment has been read)
+      if (tid == 0) cgs_mbar_arrive(&empty[st]);
+      // phase B: lane l covers rows 4l..4l+3 and 128+4l..128+4l+3; the 8 products of a vector
+      // are summed in fp32 and added to the fp64 accumulator once per tile
+      const float4 va = reinterpret_cast<const float4*>(vs)[lane];
+      const float4 vb = reinterpret_cast<const float4*>(vs)[32 + lane];
+#pragma unroll
+      for (int jj = 0; jj < kCgsJW; ++jj) {
+        float p0 = qa[jj].x * va.x, p1 = qa[jj].y * va.y, p2 = qa[jj].z * va.z, p3 = qa[jj].w * va.w;
+        p0 += qb[jj].x * vb.x;
+        p1 += qb[jj].y * vb.y;
+        p2 += qb[jj].z * vb.z;
+        p3 += qb[jj].w * vb.w;
         acc[jj] += (double)((p0 + p1) + (p2 + p3));
       }
+      if (++st == stages) {
+        st = 0;
+        ++round;
+      }
     }
-    __syncthreads();  // the stage is refilled by the next iteration's issue
-  }
-  // fold all lanes of the warp (ld == 1: every row belongs to the one column); fixed xor tree
+    // fold all lanes of the warp (ld == 1: every row belongs to the one column); fixed xor tree
 #pragma unroll
-  for (int jj = 0; jj < kCgsJW; ++jj) {
-    const int jv = warp + jj * NW;
-    double sacc = acc[jj];
-    for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
-    if (jv < nq && lane == 0)
-      partial[(int64_t)jv * partial_stride + (int64_t)blockIdx.x] = sacc;
+    for (int jj = 0; jj < kCgsJW; ++jj) {
+      const int jv = warp + jj * NW;
+      double sacc = acc[jj];
+      for (int off = 16; off >= 1; off >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, off);
+      if (jv < nq && lane == 0)
+        partial[(int64_t)jv * partial_stride + (int64_t)blockIdx.x] = sacc;
+    }
   }
   finalize_if_last<float>(ld, partial, partial_stride, nq, fin);
 }
@@ -778,7 +828,8 @@ bool cgs_fused_supported(const void* Q, int64_t q_stride, int64_t nq, const void
   if (!on || dtype != MF_F32 || ld != 1 || nq < 1 || nq > kCgsMaxNq) return false;
   if (partial_rows < nq) return false;  // one partial row per basis vector
   if (q_stride <= 0) q_stride = n * ld;
-  if (q_stride % 4 != 0 || !al16(Q) || !al16(V)) return false;
+  // TMA tensor maps: 16-byte aligned base and vector stride, coordinates in int32
+  if (q_stride % 4 != 0 || !al16(Q) || !al16(V) || n * ld >= (int64_t)1 << 31) return false;
   return n * ld >= 4 * kCgsRows;  // tiny problems: the plain kernels are launch-bound anyway
 }
 
@@ -788,15 +839,21 @@ int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void
   MF_KSCOPE(MF_KC_REORTH_UPDATE, st);
   const int64_t total = n * ld;
   if (q_stride <= 0) q_stride = total;
-  // stages + vs + sp + hs (nq rounded up to 4 G) + 4 G segments of zero padding that phase A may
-  // read past the last stage with zero coefficients
-  constexpr int kG = kCgsThreads / kCgsRows;
-  const size_t smem = (size_t)(2 * (nq + 1) * kCgsRows + kG * kCgsRows + (nq + 4 * kG) + 4 * kG * kCgsRows) * sizeof(float);
+  // as many stages as fit: stages * (nq + 1) segments + vs + sp + the barriers
+  const int64_t stage_bytes = (nq + 1) * kCgsRows * (int64_t)sizeof(float);
+  static const int env_stages = getenv("MF_CGS_STAGES") ? atoi(getenv("MF_CGS_STAGES")) : 0;
+  int stages = (int)((kCgsSmemMax - kCgsFixedBytes) / stage_bytes);
+  if (stages > kCgsMaxStages) stages = kCgsMaxStages;
+  if (env_stages >= 2 && env_stages < stages) stages = env_stages;
+  if (stages < 2) {
+    set_error("cgs_update_dots: nq = %lld does not fit shared memory", (long long)nq);
+    return MF_ERR_INVALID_ARGUMENT;
+  }
+  const size_t smem = (size_t)(stages * stage_bytes) + kCgsFixedBytes;
   static bool configured = false;
   if (!configured) {
-    const size_t max_smem = (size_t)(2 * (kCgsMaxNq + 1) * kCgsRows + kG * kCgsRows + (kCgsMaxNq + 4 * kG) + 4 * kG * kCgsRows) * 4;
     if (cudaFuncSetAttribute(cgs_update_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)max_smem) != cudaSuccess) {
+                             kCgsSmemMax) != cudaSuccess) {
       cudaGetLastError();
       set_error("cgs_update_dots: shared-memory opt-in failed");
       return MF_ERR_CUDA;
@@ -807,9 +864,14 @@ int32_t launch_reorth_update_dots(const void* Q, int64_t nq, const void* h, void
   int grid = num_sms();
   if (grid > ntiles) grid = (int)ntiles;
   Finalize fin{counter, 0, h_out, nullptr, nullptr, peer};
-  cgs_update_dots_kernel<<<grid, kCgsThreads, smem, st>>>((const float*)Q, q_stride, (int)nq,
-                                                       (const float*)h, (float*)V, total, (int)ld,
-                                                       partial, (int64_t)kMaxPartialCtas * ld, fin);
+  // the tile of all nq basis vectors is one TMA box: the map is per launch (its box is nq tall)
+  CUtensorMap tmQ, tmV;
+  MF_TRY(encode_plain_map_2d(&tmQ, Q, (uint64_t)total, (uint64_t)nq, (uint64_t)q_stride * 4, kCgsRows,
+                             (uint32_t)nq));
+  MF_TRY(encode_plain_map_2d(&tmV, V, (uint64_t)total, 1, (uint64_t)q_stride * 4, kCgsRows, 1));
+  cgs_update_dots_kernel<<<grid, kCgsThreads, smem, st>>>(tmQ, tmV, (int)nq, (const float*)h, (float*)V,
+                                                       total, (int)ld, stages, partial,
+                                                       (int64_t)kMaxPartialCtas * ld, fin);
   return check_launch("cgs_update_dots");
 }
 

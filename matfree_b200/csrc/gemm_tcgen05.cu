@@ -546,6 +546,29 @@ int32_t launch_bn(int64_t ld, const float* Aplanes, int64_t lda, int64_t a_rows,
 
 }  // namespace
 
+// A plain (unswizzled) 2-D fp32 tensor map: dim0 contiguous, dim1 `stride1_bytes` apart; boxes
+// that reach past the tensor are zero-filled.  Used by the fused CGS kernel (blockvec.cu) to fetch
+// a tile of ALL basis vectors with one TMA instruction.  `map` points at a CUtensorMap.
+int32_t encode_plain_map_2d(void* map, const void* base, uint64_t dim0, uint64_t dim1,
+                            uint64_t stride1_bytes, uint32_t box0, uint32_t box1) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return MF_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {dim0, dim1};
+  const cuuint64_t gstr[1] = {stride1_bytes};
+  const cuuint32_t bx[2] = {box0, box1}, es[2] = {1, 1};
+  const CUresult rc = fn((CUtensorMap*)map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                         gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (plain 2-D) failed with CUresult %d", (int)rc);
+    return MF_ERR_CUDA;
+  }
+  return MF_OK;
+}
+
 bool tc_gemm_supported(int64_t lda, int64_t M, int64_t K, int64_t ld, int32_t dtype) {
   if (dtype != MF_F32) return false;
   if (ld != 32 && ld != 64 && ld != 128 && ld != 256) return false;

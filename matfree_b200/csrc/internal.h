@@ -154,6 +154,9 @@ bool tc_gemm_supported(int64_t lda, int64_t M, int64_t K, int64_t ld, int32_t dt
 int32_t launch_split_tf32(const void* src, void* planes, int64_t count, cudaStream_t st);
 // C[batch][M][ld] = colscale .* (op(A) @ B) from TF32 planes Aplanes [2][rows][lda] and
 // Bplanes [batch][2][K][ld]; writes C and/or the planes of the result, Csplit [batch][2][M][ld]
+// plain 2-D fp32 tensor map (gemm_tcgen05.cu); `map` points at a CUtensorMap
+int32_t encode_plain_map_2d(void* map, const void* base, uint64_t dim0, uint64_t dim1,
+                            uint64_t stride1_bytes, uint32_t box0, uint32_t box1);
 int32_t launch_gemm_tcgen05(const void* Aplanes, int64_t lda, bool trans, int64_t M, int64_t K,
                             const void* Bplanes, int64_t nbatch, const void* colscale, void* C,
                             void* Csplit, int64_t ld, int variant, cudaStream_t st);

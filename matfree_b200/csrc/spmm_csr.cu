@@ -105,7 +105,7 @@ __device__ __forceinline__ void prefetch_row_l1(const int32_t* __restrict__ ptrb
 // PIPE: the gathers of the next row are issued before the current row is multiplied.
 template <typename T, int VEC, int LD, int SEGL, bool PIPE, bool FUSE_DOT, bool DEFER = false,
           bool BLOCKED = false>
-__global__ void __launch_bounds__(kBlock, (PIPE || DEFER || SEGL == 7) ? 3 : 4)
+__global__ void __launch_bounds__(kBlock, (PIPE || DEFER || (SEGL == 7 && LD >= 128)) ? 3 : 4)
 spmm_csr_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
