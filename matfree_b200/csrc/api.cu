@@ -391,13 +391,11 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
     MF_TRY(launch_scale(i == 0 ? V0 : b.V, length, Qi, 1, dt, n, ld, st));  // :456-457
     bool fused = false;
     MF_TRY(apply_op(op, Qi, nullptr, b.V, ld, b.scr, nullptr, b.counter + 8, &fused, st));  // :460
+    // :463; the same launch files alpha_i = h_i and, for T = (H + H^T)/2 (:133-135), folds h_{i-1}
+    // into the previous off-diagonal
     MF_TRY(launch_reorth_dots(Q, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st, nullptr,
-                              b.partial_rows));  // :463
-    if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
-                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-      set_error("alpha copy failed");
-      return MF_ERR_CUDA;
-    }
+                              b.partial_rows, 0, nullptr, row(alphas, i, ld, dt),
+                              hess == nullptr && i > 0 ? row(betas, i - 1, ld, dt) : nullptr));
     if (hess != nullptr) {
       // H[0..i][i] = h (decomp.py:463,474-475)
       if (cudaMemcpy2DAsync((char*)hess->H + i * ld * es, (size_t)(k * ld * es), b.h,
@@ -419,8 +417,6 @@ int32_t lanczos_full(const mf_operator_t* op, const void* V0, bool have_len, int
         }
         continue;
       }
-    } else if (i > 0) {
-      MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
     }
     if (cgs_fused_supported(Q, 0, i + 1, b.V, dt, n, ld, b.partial_rows)) {
       // :464 and the dots of :468 in one sweep over the basis
@@ -491,13 +487,8 @@ int32_t lanczos_full_sharded(const Shard& sh, const mf_operator_t* op, const voi
     MF_TRY(apply_op(op, sh.ext + i * ext_blk, nullptr, b.V, ld, b.scr, nullptr, b.counter + 8,
                     &fused, st));  // :460
     MF_TRY(launch_reorth_dots(Qmid, i + 1, b.V, dt, n, ld, b.partial, b.counter, b.h, st, nullptr,
-                              b.partial_rows, q_stride, sh.peer));  // :463
-    if (cudaMemcpyAsync(row(alphas, i, ld, dt), row(b.h, i, ld, dt), ld * es,
-                        cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
-      set_error("alpha copy failed");
-      return MF_ERR_CUDA;
-    }
-    if (i > 0) MF_TRY(launch_full_offdiag(row(betas, i - 1, ld, dt), row(b.h, i - 1, ld, dt), dt, ld, st));
+                              b.partial_rows, q_stride, sh.peer, row(alphas, i, ld, dt),
+                              i > 0 ? row(betas, i - 1, ld, dt) : nullptr));  // :463, :133-135
     if (cgs_fused_supported(Qmid, q_stride, i + 1, b.V, dt, n, ld, b.partial_rows)) {
       MF_TRY(launch_reorth_update_dots(Qmid, i + 1, b.h, b.V, n, ld, b.partial, b.counter, b.h2,
                                        st, q_stride, sh.peer));  // :464 + dots of :468

@@ -730,7 +730,7 @@ int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
                            cudaStream_t st, double* dbl_out, int64_t partial_rows,
-                           int64_t q_stride, const PeerCtx* peer) {
+                           int64_t q_stride, const PeerCtx* peer, void* alpha_dst, void* offdiag) {
   MF_KSCOPE(MF_KC_REORTH_DOTS, st);
   const int64_t total = n * ld;
   if (q_stride <= 0) q_stride = total;
@@ -740,6 +740,11 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
   if (nq > JB && ld <= 64 && partial_rows >= (nq + JB - 1) / JB * JB) {
     // one launch for all nq sums
     Finalize fin{counter, 0, h_out, nullptr, dbl_out, peer};
+    if (alpha_dst != nullptr || offdiag != nullptr) {
+      fin.alpha_dst = alpha_dst;
+      fin.offdiag = offdiag;
+      fin.alpha_row = (int)nq - 1;
+    }
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_all_kernel<T, VEC, JB>;
       const int ngroups = (int)((nq + JB - 1) / JB);
@@ -757,6 +762,12 @@ int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dty
     Finalize fin{counter, 0,
                  h_out ? (void*)((char*)h_out + j0 * ld * (int64_t)dtype_size(dtype)) : nullptr,
                  nullptr, dbl_out ? dbl_out + j0 * ld : nullptr, peer};
+    if (alpha_dst != nullptr || offdiag != nullptr) {
+      fin.alpha_dst = alpha_dst;
+      fin.offdiag = offdiag;
+      fin.alpha_row = (int)nq - 1;
+      fin.row0 = (int)j0;
+    }
     MF_DISPATCH_TV(dtype, ld, {
       auto kern = reorth_dots_kernel<T, VEC, JB>;
       const int grid = MF_STREAM_GRID(kern, total, VEC);

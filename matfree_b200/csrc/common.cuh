@@ -238,13 +238,29 @@ struct Finalize {
   double* dbl;            // optional double[nacc][ld]: the fp64 sums
   const PeerCtx* peer;    // optional: the sums are all-reduced over the communicator's ranks
                           // (peer memory, in this kernel) before value / inv / dbl are written
+  // Arnoldi bookkeeping folded into the first Gram-Schmidt reduction (matfree/decomp.py:463 and
+  // :133-135), which saves two tiny launches per step: result row `alpha_row` (counted from
+  // row0, the first row of this launch) is also the diagonal entry; the row before it is the
+  // upper-Hessenberg twin of the previous off-diagonal, off <- (off + h) / 2.
+  void* alpha_dst = nullptr;  // T[ld]
+  void* offdiag = nullptr;    // T[ld]
+  int alpha_row = -1;
+  int row0 = 0;
 };
 
 template <typename T>
-__device__ __forceinline__ void finalize_write(const Finalize& fin, int64_t i, double s) {
+__device__ __forceinline__ void finalize_write(const Finalize& fin, int64_t i, double s, int ld) {
   if (fin.dbl) fin.dbl[i] = s;
   if (fin.mode == 0) {
     if (fin.value) reinterpret_cast<T*>(fin.value)[i] = (T)s;
+    if (fin.alpha_row >= 0) {
+      const int a = (int)(i / ld), c = (int)(i - (int64_t)a * ld);
+      if (fin.alpha_dst && fin.row0 + a == fin.alpha_row) reinterpret_cast<T*>(fin.alpha_dst)[c] = (T)s;
+      if (fin.offdiag && fin.row0 + a == fin.alpha_row - 1) {
+        T* off = reinterpret_cast<T*>(fin.offdiag);
+        off[c] = T(0.5) * ((T)s + off[c]);
+      }
+    }
   } else {
     const T v = (T)sqrt(s);
     if (fin.value) reinterpret_cast<T*>(fin.value)[i] = v;
@@ -291,15 +307,29 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
     const bool live = part && idx < npairs;
     const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     const double* p = partial + a * partial_stride + c;
+    // lane l adds the rows l, l + L, ...: eight loads in flight (a serial chain of L2 round
+    // trips was most of the tail of every reducing kernel on small shards), fixed order
     double s = 0.0;
-    if (live)
-      for (int b = lane; b < grid; b += L) s += __ldcg(p + (int64_t)b * ld);
+    if (live) {
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0, t6 = 0.0, t7 = 0.0;
+      int b = lane;
+      for (; b + 7 * L < grid; b += 8 * L) {
+        const double* pb = p + (int64_t)b * ld;
+        const int64_t sL = (int64_t)L * ld;
+        const double x0 = __ldcg(pb), x1 = __ldcg(pb + sL), x2 = __ldcg(pb + 2 * sL),
+                     x3 = __ldcg(pb + 3 * sL), x4 = __ldcg(pb + 4 * sL), x5 = __ldcg(pb + 5 * sL),
+                     x6 = __ldcg(pb + 6 * sL), x7 = __ldcg(pb + 7 * sL);
+        t0 += x0; t1 += x1; t2 += x2; t3 += x3; t4 += x4; t5 += x5; t6 += x6; t7 += x7;
+      }
+      for (; b < grid; b += L) t0 += __ldcg(p + (int64_t)b * ld);
+      s = ((t0 + t1) + (t2 + t3)) + ((t4 + t5) + (t6 + t7));
+    }
     s = group_sum(s, L);
     if (!live || lane != 0) continue;
     if (xch) {
       for (int q = 0; q < world; ++q) pc->ctl[q]->slots[buf][rank][idx] = s;  // NVLink stores
     } else {
-      finalize_write<T>(fin, (int64_t)a * ld + c, s);
+      finalize_write<T>(fin, (int64_t)a * ld + c, s, ld);
     }
   }
   if (xch) {
@@ -315,7 +345,7 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
     for (int idx = threadIdx.x; part && idx < npairs; idx += kBlock) {
       double s = 0.0;
       for (int q = 0; q < world; ++q) s += __ldcv(&mine->slots[buf][q][idx]);
-      finalize_write<T>(fin, idx, s);
+      finalize_write<T>(fin, idx, s, ld);
     }
     if (threadIdx.x == 0) mine->red_seq = seq;
   }

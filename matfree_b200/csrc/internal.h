@@ -55,7 +55,10 @@ int32_t launch_axpy_cols(const void* X, const void* coef, const void* s1, const 
 int32_t launch_reorth_dots(const void* Q, int64_t nq, const void* V, int32_t dtype, int64_t n,
                            int64_t ld, double* partial, unsigned int* counter, void* h_out,
                            cudaStream_t st, double* dbl_out = nullptr, int64_t partial_rows = 4,
-                           int64_t q_stride = 0, const PeerCtx* peer = nullptr);
+                           int64_t q_stride = 0, const PeerCtx* peer = nullptr,
+                           void* alpha_dst = nullptr, void* offdiag = nullptr);
+// alpha_dst / offdiag (optional, T[ld] each): the Arnoldi bookkeeping of common.cuh's Finalize --
+// h[nq-1] is also written to alpha_dst and offdiag <- (offdiag + h[nq-2]) / 2.
 // Accumulator rows the partial buffer of the CGS dots gets: all k sums in one launch when
 // that costs at most 8 MB (narrow tiles), otherwise 4 (groups of four basis vectors per launch).
 inline int64_t reorth_partial_rows(int64_t ld, int64_t k) {
