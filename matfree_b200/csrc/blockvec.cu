@@ -174,7 +174,7 @@ reorth_dots_kernel(const T* __restrict__ Q, int64_t q_stride, int j0, int nj,
       }
     }
   }
-  cta_reduce_finalize<T, VEC, JB>(acc, ld, partial, partial_stride, nj, fin);
+  cta_reduce_finalize<T, VEC, JB, true>(acc, ld, partial, partial_stride, nj, fin);
 }
 
 // All nq basis vectors in ONE launch (narrow tiles: the per-CTA partial rows of all nq sums fit
@@ -260,7 +260,7 @@ reorth_dots_all_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const 
     for (int w = 0; w < NW; ++w) s += wsum[j][w][c];
     partial[(int64_t)(j0 + j) * partial_stride + (int64_t)r * ld + c] = s;
   }
-  finalize_if_last<T>(ld, partial, partial_stride, nq, fin, R);
+  finalize_if_last<T, true>(ld, partial, partial_stride, nq, fin, R);
 }
 
 template <typename T, int VEC, bool NORM>
@@ -310,7 +310,7 @@ reorth_update_kernel(const T* __restrict__ Q, int64_t q_stride, int nq, const T*
     }
     store_chunk<T, VEC>(V, f, v);
   }
-  if (NORM) cta_reduce_finalize<T, VEC, 1>(acc, ld, partial, 0, 1, fin);
+  if (NORM) cta_reduce_finalize<T, VEC, 1, true>(acc, ld, partial, 0, 1, fin);
 }
 
 // ---------------------------------------------------------------- fused CGS pass (narrow tiles)
@@ -503,7 +503,7 @@ cgs_update_dots_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         partial[(int64_t)jv * partial_stride + (int64_t)blockIdx.x] = sacc;
     }
   }
-  finalize_if_last<float>(ld, partial, partial_stride, nq, fin);
+  finalize_if_last<float, true>(ld, partial, partial_stride, nq, fin);
 }
 
 template <typename T, int VEC>

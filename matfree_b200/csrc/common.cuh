@@ -268,22 +268,14 @@ __device__ __forceinline__ void finalize_write(const Finalize& fin, int64_t i, d
   }
 }
 
-// Second half of a reducing kernel: take a ticket; the CTA drawing the last one adds the
-// partial rows of all CTAs (fixed order) for `nacc_live` accumulators and writes the results.
-template <typename T>
-__device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ partial,
-                                                 int64_t partial_stride, int nacc_live,
-                                                 const Finalize& fin, int nrows = 0) {
-  if (fin.counter == nullptr) return;
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int ticket = atomicAdd(fin.counter, 1u);
-    is_last = ticket == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!is_last) return;
+// The last CTA's share of a reduction.  DEEP: eight loads in flight per lane -- for the kernels of the
+// narrow-tile Arnoldi loop (C4), where the serial chain of L2 round trips was most of each kernel's
+// tail on small shards; elsewhere the plain loop stays (inlined after the CSR kernel's row body the
+// deep variant raised its register pressure and the fused-dot product spilled: 8.1 -> 14.3 ms).
+template <typename T, bool DEEP>
+__device__ __forceinline__ void finalize_last_cta(int ld, double* __restrict__ partial,
+                                               int64_t partial_stride, int nacc_live,
+                                               const Finalize& fin, int nrows) {
   __threadfence();
   const int grid = nrows > 0 ? nrows : (int)gridDim.x;  // partial rows per accumulator
   const int npairs = nacc_live * ld;
@@ -307,22 +299,26 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
     const bool live = part && idx < npairs;
     const int a = live ? idx / ld : 0, c = live ? idx % ld : 0;
     const double* p = partial + a * partial_stride + c;
-    // lane l adds the rows l, l + L, ...: eight loads in flight (a serial chain of L2 round
-    // trips was most of the tail of every reducing kernel on small shards), fixed order
     double s = 0.0;
-    if (live) {
-      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0, t6 = 0.0, t7 = 0.0;
-      int b = lane;
-      for (; b + 7 * L < grid; b += 8 * L) {
-        const double* pb = p + (int64_t)b * ld;
-        const int64_t sL = (int64_t)L * ld;
-        const double x0 = __ldcg(pb), x1 = __ldcg(pb + sL), x2 = __ldcg(pb + 2 * sL),
-                     x3 = __ldcg(pb + 3 * sL), x4 = __ldcg(pb + 4 * sL), x5 = __ldcg(pb + 5 * sL),
-                     x6 = __ldcg(pb + 6 * sL), x7 = __ldcg(pb + 7 * sL);
-        t0 += x0; t1 += x1; t2 += x2; t3 += x3; t4 += x4; t5 += x5; t6 += x6; t7 += x7;
+    if constexpr (DEEP) {
+      // lane l adds the rows l, l + L, ...: eight loads in flight, fixed order
+      if (live) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0, t6 = 0.0, t7 = 0.0;
+        int b = lane;
+        for (; b + 7 * L < grid; b += 8 * L) {
+          const double* pb = p + (int64_t)b * ld;
+          const int64_t sL = (int64_t)L * ld;
+          const double x0 = __ldcg(pb), x1 = __ldcg(pb + sL), x2 = __ldcg(pb + 2 * sL),
+                       x3 = __ldcg(pb + 3 * sL), x4 = __ldcg(pb + 4 * sL), x5 = __ldcg(pb + 5 * sL),
+                       x6 = __ldcg(pb + 6 * sL), x7 = __ldcg(pb + 7 * sL);
+          t0 += x0; t1 += x1; t2 += x2; t3 += x3; t4 += x4; t5 += x5; t6 += x6; t7 += x7;
+        }
+        for (; b < grid; b += L) t0 += __ldcg(p + (int64_t)b * ld);
+        s = ((t0 + t1) + (t2 + t3)) + ((t4 + t5) + (t6 + t7));
       }
-      for (; b < grid; b += L) t0 += __ldcg(p + (int64_t)b * ld);
-      s = ((t0 + t1) + (t2 + t3)) + ((t4 + t5) + (t6 + t7));
+    } else {
+      if (live)
+        for (int b = lane; b < grid; b += L) s += __ldcg(p + (int64_t)b * ld);
     }
     s = group_sum(s, L);
     if (!live || lane != 0) continue;
@@ -352,13 +348,32 @@ __device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ pa
   if (threadIdx.x == 0) *fin.counter = 0u;
 }
 
-template <typename T, int VEC, int NACC = 1>
+// Second half of a reducing kernel: take a ticket; the CTA drawing the last one adds the
+// partial rows of all CTAs (fixed order) for `nacc_live` accumulators and writes the results.
+template <typename T, bool DEEP = false>
+__device__ __forceinline__ void finalize_if_last(int ld, double* __restrict__ partial,
+                                                 int64_t partial_stride, int nacc_live,
+                                                 const Finalize& fin, int nrows = 0) {
+  if (fin.counter == nullptr) return;
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(fin.counter, 1u);
+    is_last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  finalize_last_cta<T, DEEP>(ld, partial, partial_stride, nacc_live, fin, nrows);
+}
+
+template <typename T, int VEC, int NACC = 1, bool DEEP = false>
 __device__ __forceinline__ void cta_reduce_finalize(double (&acc)[NACC][VEC], int ld,
                                                     double* __restrict__ partial,
                                                     int64_t partial_stride, int nacc_live,
                                                     const Finalize& fin) {
   cta_reduce_columns<VEC, NACC>(acc, ld, partial, partial_stride);
-  finalize_if_last<T>(ld, partial, partial_stride, nacc_live, fin);
+  finalize_if_last<T, DEEP>(ld, partial, partial_stride, nacc_live, fin);
 }
 
 }  // namespace mf

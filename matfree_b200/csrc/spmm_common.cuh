@@ -90,11 +90,13 @@ inline int env_int(const char* name, int dflt) {
 // Blocked row order for stencil-like matrices whose far diagonals (`bandwidth` rows away: the
 // planes of a 3-D grid) are too far apart to stay in L2 between their uses.  Measured on the 3-D
 // 7-point Laplacian 256^3 at ld = 256 (profiles/r2f_spmm_3d_t256.txt): 51.5 GB of DRAM reads per
-// product in ascending row order, i.e. X three times; 13.1 instead of 18.2 ms with blocks of 12 MB.
+// product in ascending row order, i.e. X three times; 13.1 instead of 18.2 ms with blocks of 8 MB
+// (budget 12 MB), 11.1-11.8 instead of 11.8-12.3 ms with blocks of 4 MB (budget 6 MB, the default;
+// 2 MB and 16 MB blocks are slower: profiles/r2w_sweep.jsonl, r2w_sweep2.jsonl).
 inline void choose_row_order(SpmmParams* prm, int64_t n, double avg, int64_t bandwidth, int64_t ld,
                              int32_t dtype) {
   static const int env_block = env_int("MF_SPMM_BLOCKED", 1);
-  static const int env_block_mb = env_int("MF_SPMM_BLOCK_MB", 12);
+  static const int env_block_mb = env_int("MF_SPMM_BLOCK_MB", 6);
   const int64_t R = prm->rows_per_chunk;
   const int64_t row_bytes = ld * (int64_t)dtype_size(dtype);
   prm->outer_stride = 0;

@@ -110,12 +110,17 @@ __device__ __noinline__ TmaRowDot<VEC> tma_gather_row(const int32_t* cols, const
 //   [4][R + 1] int32                   row pointers of chunks t .. t+3
 //   [3][R * 8] int32, [3][R * 8] T     column indices / values of chunks t .. t+2 (<= 8 per row)
 //   [LD] T                             column scales
-//   [2] uint64 mbarrier, [2] int flags
+//   [2] uint64 mbarrier, [2] int flags, [2][2] int far offsets, [2][R * SEGL] T dense coefficients
+// 7-diagonal bands (3-D stencils) stage only the five inner diagonals: the two outermost ones
+// (+- one plane) are gathered from global memory / L2 by the consumers, two loads per row issued
+// before the wait on the stage.  Staging all seven costs (5R + 2) KB per stage, which leaves one
+// CTA per SM at R = 16 and was slower than the row-group kernel (profiles/r2o_instep.jsonl).
 template <typename T, int VEC, int LD, int SEGL, int ROWS>
 struct TmaLayout {
   static constexpr int R = ROWS;  // rows per chunk
-  // SEGL - 3 far diagonals (R rows each) + the run of the three adjacent middle ones (R + 2 rows)
-  static constexpr int kStageRows = (SEGL - 3) * R + R + 2;
+  static constexpr int FAR = SEGL == 7 ? 1 : 0;  // outermost diagonals per side that are gathered
+  // the staged far diagonals (R rows each) + the run of the three adjacent middle ones (R + 2 rows)
+  static constexpr int kStageRows = (SEGL - 3 - 2 * FAR) * R + R + 2;
   static constexpr int kEntCap = R * 8;
   static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
   static constexpr size_t kPtrOff = 2 * kStageBytes;
@@ -124,11 +129,13 @@ struct TmaLayout {
   static constexpr size_t kSvOff = kValOff + 3 * kEntCap * sizeof(T);
   static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
   static constexpr size_t kFlagOff = kBarOff + 2 * sizeof(uint64_t);
-  static constexpr size_t kBytes = kFlagOff + 4 * sizeof(int);
+  static constexpr size_t kFarOff = kFlagOff + 4 * sizeof(int);
+  static constexpr size_t kDenseOff = kFarOff + 4 * sizeof(int);
+  static constexpr size_t kBytes = kDenseOff + 2 * (size_t)R * SEGL * sizeof(T);
 };
 
 template <typename T, int VEC, int LD, int SEGL, int ROWS, bool FUSE_DOT, bool BLOCKED>
-__global__ void __launch_bounds__(kBlock + 32, (SEGL == 5 && ROWS <= 8) ? 3 : (ROWS * (SEGL - 2) <= 48 ? 2 : 1))
+__global__ void __launch_bounds__(kBlock + 32, (ROWS <= 8) ? 3 : (ROWS <= 16 ? 2 : 1))
 spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
@@ -136,7 +143,9 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   using L = TmaLayout<T, VEC, LD, SEGL, ROWS>;
   constexpr int R = L::R;
   constexpr int UD = SEGL / 2;
-  constexpr int MID = (UD - 1) * R;  // first stage row of the middle run
+  constexpr int FAR = L::FAR;
+  constexpr int MID = (UD - 1 - FAR) * R;  // first stage row of the middle run
+  static_assert(R < 32, "the producer warp checks one row per lane");
   static_assert(SEGL == 5 || SEGL == 7, "5- or 7-diagonal bands");
   constexpr int ld = LD;
   constexpr int tpr = LD / VEC;
@@ -151,6 +160,8 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   T* const s_sv = reinterpret_cast<T*>(smem + L::kSvOff);
   uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [2] per stage
+  int* const s_far = reinterpret_cast<int*>(smem + L::kFarOff);           // [2][2] offsets of the gathered diagonals
+  T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [2][R][SEGL] coefficients by diagonal
 
   // warps 0..7 (kBlock threads) consume; warp 8 is the producer: it verifies the next chunk, issues
   // its TMA copies and polls the window throttle, so that no consumer warp carries extra work
@@ -210,48 +221,82 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       }
     }
   };
-  // Warp 0: is chunk c (metadata in s_ptr[pbuf] / s_col[ebuf]) a band?  If so stage its X rows.
+  // Producer warp: is chunk c (metadata in s_ptr[pbuf] / s_col[ebuf] / s_val[ebuf]) a band?  A band
+  // chunk has R rows whose columns all lie on the SEGL diagonals row + o[u] (o from any row of the
+  // chunk that has all SEGL entries; o = .., -1, 0, +1, ..); rows may miss entries (the x-boundary
+  // rows of a grid line): lane r files the row's coefficients by diagonal into s_dense, zero where
+  // the entry is absent -- adding 0 * x is exact, so W keeps the bits of the CSR-order sum.
   // Always arms the stage's mbarrier, so its phase parity is a function of the chunk count alone.
   auto verify_and_stage = [&](int64_t c, int pbuf, int ebuf, int stage) {
     if (!producer) return;
     bool band = false;
-    int32_t cf[SEGL];  // columns of the first row's entries
+    int32_t o[SEGL];  // diagonal offsets
 #pragma unroll
-    for (int u = 0; u < SEGL; ++u) cf[u] = 0;
+    for (int u = 0; u < SEGL; ++u) o[u] = 0;
+    int64_t r0c = 0;
     if (c < nchunks) {
       const int nr = rows_of(c);
+      r0c = row0_of(c);
       const int32_t* ptrb = s_ptr + pbuf * (R + 1);
       const int32_t base = ptrb[0];
       const int32_t* colb = s_col + ebuf * L::kEntCap;
-      bool ok = nr == R && ptrb[R] - base == R * SEGL;
+      const T* valb = s_val + ebuf * L::kEntCap;
+      bool ok = nr == R && ptrb[R] - base <= L::kEntCap;
+      int jb = 0, len = 0;
       if (ok && lane < R) {
-        const int jb = ptrb[lane] - base;
-        ok = jb == lane * SEGL;
-        if (ok) {
-#pragma unroll
-          for (int u = 0; u < SEGL; ++u) ok = ok && (colb[jb + u] == colb[u] + lane);
-        }
+        jb = ptrb[lane] - base;
+        len = ptrb[lane + 1] - base - jb;
       }
-      if (ok && lane == 0) {
+      const unsigned int fullm = __ballot_sync(0xffffffffu, ok && lane < R && len == SEGL);
+      ok = ok && fullm != 0u;
+      const int f = fullm ? __ffs((int)fullm) - 1 : 0;
+      const int jbf = __shfl_sync(0xffffffffu, jb, f);
+      if (ok) {
 #pragma unroll
-        for (int u = 0; u < SEGL; ++u) cf[u] = colb[u];
-        ok = (int64_t)cf[UD] == row0_of(c) && cf[UD - 1] == cf[UD] - 1 && cf[UD + 1] == cf[UD] + 1;
+        for (int u = 0; u < SEGL; ++u) o[u] = colb[jbf + u] - (int32_t)(r0c + f);
+        ok = o[UD] == 0 && o[UD - 1] == -1 && o[UD + 1] == 1;
+#pragma unroll
+        for (int u = 1; u < SEGL; ++u) ok = ok && o[u] > o[u - 1];
+        // every X row the chunk touches must exist
+        ok = ok && r0c + o[0] >= 0 && r0c + R - 1 + o[SEGL - 1] < n && r0c >= 1 && r0c + R < n;
+      }
+      if (ok && lane < R) {
+        T* dr = s_dense + (size_t)stage * R * SEGL + lane * SEGL;
+#pragma unroll
+        for (int u = 0; u < SEGL; ++u) dr[u] = T(0);
+        ok = len <= SEGL;
+        int u = 0;
+        for (int e = 0; ok && e < len; ++e) {
+          const int32_t d = colb[jb + e] - (int32_t)(r0c + lane);
+          // next diagonal that matches (columns ascend within a row)
+#pragma unroll
+          for (int w = 0; w < SEGL; ++w)
+            if (w >= u && o[w] != d && w == u) ++u;
+          if (u >= SEGL) {
+            ok = false;
+          } else {
+            dr[u] = valb[jb + e];
+            ++u;
+          }
+        }
       }
       band = __all_sync(0xffffffffu, ok);
     }
     if (lane == 0) {
       s_band[stage] = band ? 1 : 0;
+      s_far[stage * 2 + 0] = o[0];
+      s_far[stage * 2 + 1] = o[SEGL - 1];
       T* xs = s_x + (size_t)stage * L::kStageRows * LD;
       constexpr unsigned int row_bytes = LD * sizeof(T);
       tma_mbar_expect_tx(&s_bar[stage], band ? (unsigned int)L::kStageRows * row_bytes : 0u);
       if (band) {
 #pragma unroll
-        for (int u = 0; u < UD - 1; ++u)  // far diagonals below the middle run
-          tma_bulk_g2s(xs + (size_t)(u * R) * LD, X + (int64_t)cf[u] * LD, R * row_bytes, &s_bar[stage]);
-        tma_bulk_g2s(xs + (size_t)MID * LD, X + (int64_t)(cf[UD] - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
+        for (int u = FAR; u < UD - 1; ++u)  // staged far diagonals below the middle run
+          tma_bulk_g2s(xs + (size_t)((u - FAR) * R) * LD, X + (r0c + o[u]) * LD, R * row_bytes, &s_bar[stage]);
+        tma_bulk_g2s(xs + (size_t)MID * LD, X + (r0c - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
 #pragma unroll
-        for (int u = UD + 2; u < SEGL; ++u)  // far diagonals above it
-          tma_bulk_g2s(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R) * LD, X + (int64_t)cf[u] * LD,
+        for (int u = UD + 2; u < SEGL - FAR; ++u)  // staged far diagonals above it
+          tma_bulk_g2s(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R) * LD, X + (r0c + o[u]) * LD,
                        R * row_bytes, &s_bar[stage]);
       }
     }
@@ -299,23 +344,43 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     const int64_t coff = r0 * ld;
 
     if (producer) continue;  // next barrier
-    tma_mbar_wait(&s_bar[stage], (unsigned int)((t >> 1) & 1));  // X rows of chunk t have landed
     const int lr0 = grp * S;
-    if (s_band[stage]) {
+    const bool band = s_band[stage] != 0;
+    // the two outermost diagonals of a 7-diagonal band: gathered, in flight during the wait
+    T xf[FAR ? 2 : 1][S][VEC];
+    if constexpr (FAR > 0) {
+      if (band) {
+        const int64_t rlo = r0 + lr0 + s_far[stage * 2 + 0], rhi = r0 + lr0 + s_far[stage * 2 + 1];
+#pragma unroll
+        for (int i = 0; i < S; ++i) {
+          ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
+          ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
+        }
+      }
+    }
+    tma_mbar_wait(&s_bar[stage], (unsigned int)((t >> 1) & 1));  // X rows of chunk t have landed
+    if (band) {
       const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
       const T* __restrict__ xb = xs + (size_t)(MID + lr0) * LD;  // middle run: rows lr, lr+1, lr+2
       T x[SEGL][VEC];
       vec_load<T>(xb, x[UD - 1]);
       vec_load<T>(xb + LD, x[UD]);
-      const T* __restrict__ vrow = valb + lr0 * SEGL;
+      const T* __restrict__ vrow = s_dense + (size_t)stage * R * SEGL + lr0 * SEGL;
       int64_t off = coff + (int64_t)lr0 * ld;
 #pragma unroll
       for (int i = 0; i < S; ++i) {
+        if constexpr (FAR > 0) {
 #pragma unroll
-        for (int u = 0; u < UD - 1; ++u) vec_load<T>(xs + (size_t)(u * R + lr0 + i) * LD, x[u]);
+          for (int q = 0; q < VEC; ++q) {
+            x[0][q] = xf[0][i][q];
+            x[SEGL - 1][q] = xf[1][i][q];
+          }
+        }
+#pragma unroll
+        for (int u = FAR; u < UD - 1; ++u) vec_load<T>(xs + (size_t)((u - FAR) * R + lr0 + i) * LD, x[u]);
         vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
 #pragma unroll
-        for (int u = UD + 2; u < SEGL; ++u)
+        for (int u = UD + 2; u < SEGL - FAR; ++u)
           vec_load<T>(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R + lr0 + i) * LD, x[u]);
         T sum[VEC];
 #pragma unroll
@@ -380,12 +445,15 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   }
 }
 
-// On by default for 5-diagonal matrices: 7.0-7.3 ms per product inside the Lanczos step of BASELINE
-// config 2 against 7.8-9.0 ms for the row-group kernel on the same pods, step 0.87-0.89 instead of
-// 0.80-0.86 of the HBM roofline (profiles/r2n_instep.jsonl, r2o_instep.jsonl).  The 7-diagonal variant
-// is opt-in (MF_SPMM_TMA=2, mf_spmm_config(3, ...)): on the 3-D workload it is slower than the row-group kernel (18.7 vs
-// 12.1 ms) -- five staged runs per chunk put 10 KB per row through the shared-memory port, and 1 in
-// 16-32 chunks holds a boundary row and takes the gather path.
+// On by default for 5-diagonal matrices: 6.8-7.6 ms per product inside the Lanczos step of BASELINE
+// config 2 against 7.8-9.0 ms for the row-group kernel on the same pods, step 0.87-0.91 instead of
+// 0.80-0.86 of the HBM roofline (profiles/r2n_instep.jsonl, r2o_instep.jsonl, r2w_sweep.jsonl).  The
+// 7-diagonal variant is opt-in (MF_SPMM_TMA=2, mf_spmm_config(3, ...)): on the 3-D workload it is slower
+// than the row-group kernel -- all seven diagonals staged: 18.7 ms; five staged + two gathered (this
+// version): 15.8 vs 12.3 ms in the step; ncu (profiles/r2v_spmm_3d_tma.txt): L1 pipe 36 % instead of
+// 65 %, but 30 GB of DRAM reads instead of 19 (the staged +-line runs and the gathered +-plane rows
+// miss L2 more often than the row-group kernel's window) and 3.3 cycles per instruction at the
+// per-chunk barrier.
 std::atomic<int> g_tma{env_int("MF_SPMM_TMA", 1)};
 
 }  // namespace
@@ -449,8 +517,7 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   } while (0)
   if (segl == 5) {
     if (env_rows <= 8) MF_TMA_R(5, 8);
-    else if (env_rows <= 16) MF_TMA_R(5, 16);
-    else MF_TMA_R(5, 32);
+    else MF_TMA_R(5, 16);
   } else {
     if (env_rows <= 8) MF_TMA_R(7, 8);
     else MF_TMA_R(7, 16);
