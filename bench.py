@@ -549,8 +549,6 @@ def supplementary_line(workload):
     return the fields of its line that matter as evidence."""
     cmd = [sys.executable, os.path.abspath(__file__), "--workload", workload, "--steps", "2", "--warmup", "3",
            "--no-cpu-baseline", "--no-e2e", "--no-extras"]
-    if workload == "c2-3d":
-        cmd += ["--tile", "64"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     if out.returncode != 0 or not lines:

@@ -13,9 +13,10 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "matfree_b200", "csrc", "build")
-PREFIXES = ["UTCHMMA", "UTCMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UTCBAR", "LDTM", "STTM", "DMMA", "HMMA", "LDGSTS",
+PREFIXES = ["UTCHMMA", "UTCMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "LDTM", "STTM", "DMMA", "HMMA", "LDGSTS",
             "LDG.E.128", "STG.E.128", "LDS.128", "SHFL", "SYNCS", "MEMBAR", "ATOMG", "REDG", "PREFETCH", "CCTL"]
 HOT = ("gemm_tf32x3", "gemm_dmma_kernel<false, 64", "spmm_csr_kernel<float, 4, 256, 5, false, true, false",
+       "spmm_tma_kernel<float, 4, 256, 5, 16, true, false", "spmm_csr_kernel<float, 4, 256, 7, false, true, false, true",
        "lanczos_update_kernel<float, 4, true", "reorth_dots_all_kernel<float, 4", "cgs_update_dots",
        "reorth_update_kernel<float, 4, true", "probe_gen_signs_kernel<float, 4", "halo_push",
        "tridiag_ql_kernel<float, false")
@@ -46,7 +47,7 @@ def short(n):
 def main():
     out = ["# SASS / ptxas evidence: `cuobjdump -sass` of matfree_b200/csrc/build/*.o (nvcc 12.9, -gencode arch=compute_100a,code=sm_100a)",
            "# per kernel, counts of the instructions that identify the hardware path:",
-           "#   UTCHMMA = tcgen05.mma (kind::tf32 here), UTMALDG = TMA tensor load (cp.async.bulk.tensor), LDTM = tcgen05.ld (TMEM -> registers),",
+           "#   UTCHMMA = tcgen05.mma (kind::tf32 here), UTMALDG = TMA tensor load (cp.async.bulk.tensor), UBLKCP = TMA bulk copy (cp.async.bulk), LDTM = tcgen05.ld (TMEM -> registers),",
            "#   UTCBAR = tcgen05.commit, SYNCS = mbarrier ops, DMMA = FP64 tensor-core MMA, LDGSTS = cp.async, MEMBAR/ATOMG = the fused finalize / peer handshakes",
            ""]
     for obj in sorted(glob.glob(os.path.join(BUILD, "*.o"))):
