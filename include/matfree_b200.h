@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 5
+#define MF_ABI_VERSION 6
 
 /* status codes */
 #define MF_OK 0
@@ -105,6 +105,14 @@ typedef struct mf_operator {
                             * `bandwidth` apart (the planes of a 3-D stencil) would not survive
                             * in L2 between their uses, the product walks the rows in a blocked
                             * order (see csrc/spmm_csr.cu) -- same results, fewer DRAM re-reads */
+  int32_t csr_num_diagonals; /* CSR, optional hint: number of distinct diagonals (column - row) the
+                              * entries lie on, 255 = more than 8; 0 = unknown.  The TMA-staged
+                              * band kernel (csrc/spmm_tma.cu) is chosen from the average row
+                              * length when this is 0, and only for matrices with exactly 5 (or 7)
+                              * diagonals when it is known -- an irregular matrix that merely
+                              * averages 5 entries per row then stays on the row-group kernel.
+                              * Either way the kernel verifies every chunk and is correct for
+                              * any CSR matrix. */
 } mf_operator_t;
 
 const char* mf_last_error(void);

@@ -35,6 +35,7 @@ class MfOperator(Structure):
         ("split_planes", c_void_p),
         ("csr_max_row_nnz", c_int32),
         ("csr_bandwidth", c_int64),
+        ("csr_num_diagonals", c_int32),
     ]
 
 

@@ -105,12 +105,17 @@ __device__ __noinline__ TmaRowDot<VEC> tma_gather_row(const int32_t* cols, const
   return out;
 }
 
+__device__ __forceinline__ void tma_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+
 // Dynamic shared memory layout (per CTA):
 //   [2 stages][3R + 2 rows][LD] T      X rows: run A (R), run B (R + 2), run C (R)
-//   [4][R + 1] int32                   row pointers of chunks t .. t+3
-//   [3][R * 8] int32, [3][R * 8] T     column indices / values of chunks t .. t+2 (<= 8 per row)
+//   [6][R + 1] int32                   producer-private: row pointers of chunks t .. t+5
+//   [4][R * 8] int32, [4][R * 8] T     producer-private: column indices / values of chunks t .. t+3
 //   [LD] T                             column scales
-//   [2] uint64 mbarrier, [2] int flags, [2][2] int far offsets, [2][R * SEGL] T dense coefficients
+//   [2] full + [2] empty mbarriers, [2] band flags, [2][2] far offsets, [2][R * SEGL] T dense coefficients
 // 7-diagonal bands (3-D stencils) stage only the five inner diagonals: the two outermost ones
 // (+- one plane) are gathered from global memory / L2 by the consumers, two loads per row issued
 // before the wait on the stage.  Staging all seven costs (5R + 2) KB per stage, which leaves one
@@ -122,18 +127,35 @@ struct TmaLayout {
   // the staged far diagonals (R rows each) + the run of the three adjacent middle ones (R + 2 rows)
   static constexpr int kStageRows = (SEGL - 3 - 2 * FAR) * R + R + 2;
   static constexpr int kEntCap = R * 8;
+  static constexpr int NP = 6, NE = 4;  // ring depths (pointers, entries)
   static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
   static constexpr size_t kPtrOff = 2 * kStageBytes;
-  static constexpr size_t kColOff = kPtrOff + 4 * (R + 1) * sizeof(int32_t) + 12;
-  static constexpr size_t kValOff = kColOff + 3 * kEntCap * sizeof(int32_t);
-  static constexpr size_t kSvOff = kValOff + 3 * kEntCap * sizeof(T);
+  static constexpr size_t kColOff = (kPtrOff + NP * (R + 1) * sizeof(int32_t) + 15) / 16 * 16;
+  static constexpr size_t kValOff = kColOff + NE * kEntCap * sizeof(int32_t);
+  static constexpr size_t kSvOff = kValOff + NE * kEntCap * sizeof(T);
   static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
-  static constexpr size_t kFlagOff = kBarOff + 2 * sizeof(uint64_t);
+  static constexpr size_t kFlagOff = kBarOff + 4 * sizeof(uint64_t);
   static constexpr size_t kFarOff = kFlagOff + 4 * sizeof(int);
   static constexpr size_t kDenseOff = kFarOff + 4 * sizeof(int);
   static constexpr size_t kBytes = kDenseOff + 2 * (size_t)R * SEGL * sizeof(T);
 };
 
+// Producer / consumer pipeline without CTA barriers in the steady state.  Warps 0..7 (kBlock
+// threads) consume; warp 8 produces.
+//   producer, chunk t: its CSR metadata was prefetched into private shared-memory rings by the
+//     producer's own cp.async (entries three chunks ahead, row pointers five), so the verification
+//     below reads shared memory only -- with the metadata loaded on demand the single warp's
+//     dependent global loads were the critical path (7.7 vs 7.1 ms, tools/runs_r2_tma_v3.sh).
+//     Band check (lane r <-> row r): the chunk has R rows whose columns all lie on the SEGL
+//     diagonals row + o[u] (o from any row of the chunk that has all SEGL entries; o = .., -1, 0,
+//     +1, ..); rows may miss entries (the x-boundary rows of a grid line): the lane files the row's
+//     coefficients by diagonal into the stage's dense table, zero where the entry is absent --
+//     adding 0 * x is exact, so W keeps the bits of the CSR-order sum.  Then: wait until the
+//     consumers have released the stage (`empty`), publish table + flags, arm `full` with the
+//     byte count and issue the TMA copies.  Every chunk arms `full` (a chunk that is not a band
+//     with 0 bytes), so the phase parities depend on the chunk count alone.
+//   consumer warp, chunk t: wait on `full`, compute its rows (band: LDS.128 + dense coefficients;
+//     otherwise the gather path with metadata straight from global memory), arrive on `empty`.
 template <typename T, int VEC, int LD, int SEGL, int ROWS, bool FUSE_DOT, bool BLOCKED>
 __global__ void __launch_bounds__(kBlock + 32, (ROWS <= 8) ? 3 : (ROWS <= 16 ? 2 : 1))
 spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
@@ -145,28 +167,27 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   constexpr int UD = SEGL / 2;
   constexpr int FAR = L::FAR;
   constexpr int MID = (UD - 1 - FAR) * R;  // first stage row of the middle run
+  constexpr int NP = L::NP, NE = L::NE;
   static_assert(R < 32, "the producer warp checks one row per lane");
   static_assert(SEGL == 5 || SEGL == 7, "5- or 7-diagonal bands");
   constexpr int ld = LD;
   constexpr int tpr = LD / VEC;
   constexpr int rps = kBlock / tpr;  // row-groups per CTA
   constexpr int S = R / rps;         // consecutive rows per row-group
+  constexpr int kConsumerWarps = kBlock / 32;
   static_assert(tpr >= 32 && tpr % 32 == 0 && R % rps == 0 && S >= 1, "tile / chunk geometry");
   extern __shared__ __align__(128) unsigned char smem[];
   T* const s_x = reinterpret_cast<T*>(smem);
-  int32_t* const s_ptr = reinterpret_cast<int32_t*>(smem + L::kPtrOff);   // [4][R + 1]
-  int32_t* const s_col = reinterpret_cast<int32_t*>(smem + L::kColOff);   // [3][kEntCap]
-  T* const s_val = reinterpret_cast<T*>(smem + L::kValOff);               // [3][kEntCap]
+  int32_t* const s_ptr = reinterpret_cast<int32_t*>(smem + L::kPtrOff);   // [NP][R + 1]
+  int32_t* const s_col = reinterpret_cast<int32_t*>(smem + L::kColOff);   // [NE][kEntCap]
+  T* const s_val = reinterpret_cast<T*>(smem + L::kValOff);               // [NE][kEntCap]
   T* const s_sv = reinterpret_cast<T*>(smem + L::kSvOff);
-  uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* const s_empty = s_full + 2;
   int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [2] per stage
   int* const s_far = reinterpret_cast<int*>(smem + L::kFarOff);           // [2][2] offsets of the gathered diagonals
   T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [2][R][SEGL] coefficients by diagonal
 
-  // warps 0..7 (kBlock threads) consume; warp 8 is the producer: it verifies the next chunk, issues
-  // its TMA copies and polls the window throttle, so that no consumer warp carries extra work
-  // between two CTA barriers (with warp 0 in that role the other warps spent 4.5 cycles per issued
-  // instruction stalled at the barrier, profiles/r2m_spmm_2d_tma.txt)
   const bool producer = threadIdx.x >= kBlock;
   const int grp = threadIdx.x / tpr;
   const int lane = threadIdx.x & 31;
@@ -185,63 +206,90 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   const int64_t G = gridDim.x;
 
   if (threadIdx.x == 0) {
-    tma_mbar_init(&s_bar[0], 1);
-    tma_mbar_init(&s_bar[1], 1);
+    tma_mbar_init(&s_full[0], 1);
+    tma_mbar_init(&s_full[1], 1);
+    tma_mbar_init(&s_empty[0], kConsumerWarps);
+    tma_mbar_init(&s_empty[1], kConsumerWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  __syncthreads();  // mbarriers initialised; s_sv filled
 
   // first row of chunk c: ascending order, or the blocked order of SpmmParams (3-D stencils)
   auto row0_of = [&](int64_t c) -> int64_t {
     if constexpr (BLOCKED) return chunk_row0(c, p);
     else return c * (int64_t)R;
   };
-  auto rows_of = [&](int64_t c) -> int {
-    const int64_t r0c = row0_of(c);
-    return (int)((n - r0c) < R ? (n - r0c) : R);
-  };
-  auto issue_ptr = [&](int64_t c, int buf) {
-    if (c < nchunks && !producer) {
-      const int nr = rows_of(c);
-      const int64_t r0c = row0_of(c);
-      for (int i = threadIdx.x; i <= nr; i += kBlock)
-        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[buf * (R + 1) + i]), indptr + r0c + i);
-    }
-  };
-  auto issue_ent = [&](int64_t c, int pbuf, int ebuf) {  // needs s_ptr[pbuf] visible
-    if (c < nchunks && !producer) {
-      const int nr = rows_of(c);
-      const int32_t base = s_ptr[pbuf * (R + 1)];
-      const int total = s_ptr[pbuf * (R + 1) + nr] - base;
-      if (total <= L::kEntCap) {
-        for (int i = threadIdx.x; i < total; i += kBlock) {
-          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_col[ebuf * L::kEntCap + i]), indices + base + i);
-          cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&s_val[ebuf * L::kEntCap + i]),
-                                   data + base + i);
+  auto rows_of = [&](int64_t r0c) -> int { return (int)((n - r0c) < R ? (n - r0c) : R); };
+
+  if (producer) {
+    // ------------------------------------------------------------------ producer warp
+    // my chunks are c_t = blockIdx.x + t G; ring slots by t
+    auto issue_ptr = [&](int64_t t) {
+      const int64_t c = blockIdx.x + t * G;
+      if (c < nchunks) {
+        const int64_t r0c = row0_of(c);
+        const int nr = rows_of(r0c);
+        if (lane <= nr)
+          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[(int)(t % NP) * (R + 1) + lane]),
+                      indptr + r0c + lane);
+      }
+    };
+    auto issue_ent = [&](int64_t t) {  // needs the pointers of chunk t visible
+      const int64_t c = blockIdx.x + t * G;
+      if (c < nchunks) {
+        const int nr = rows_of(row0_of(c));
+        const int32_t* ptrb = s_ptr + (int)(t % NP) * (R + 1);
+        const int32_t base = ptrb[0];
+        const int total = ptrb[nr] - base;
+        if (total <= L::kEntCap) {
+          int32_t* cb = s_col + (int)(t % NE) * L::kEntCap;
+          T* vb = s_val + (int)(t % NE) * L::kEntCap;
+          for (int i = lane; i < total; i += 32) {
+            cp_async<4>((uint32_t)__cvta_generic_to_shared(&cb[i]), indices + base + i);
+            cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&vb[i]), data + base + i);
+          }
         }
       }
-    }
-  };
-  // Producer warp: is chunk c (metadata in s_ptr[pbuf] / s_col[ebuf] / s_val[ebuf]) a band?  A band
-  // chunk has R rows whose columns all lie on the SEGL diagonals row + o[u] (o from any row of the
-  // chunk that has all SEGL entries; o = .., -1, 0, +1, ..); rows may miss entries (the x-boundary
-  // rows of a grid line): lane r files the row's coefficients by diagonal into s_dense, zero where
-  // the entry is absent -- adding 0 * x is exact, so W keeps the bits of the CSR-order sum.
-  // Always arms the stage's mbarrier, so its phase parity is a function of the chunk count alone.
-  auto verify_and_stage = [&](int64_t c, int pbuf, int ebuf, int stage) {
-    if (!producer) return;
-    bool band = false;
-    int32_t o[SEGL];  // diagonal offsets
-#pragma unroll
-    for (int u = 0; u < SEGL; ++u) o[u] = 0;
-    int64_t r0c = 0;
-    if (c < nchunks) {
-      const int nr = rows_of(c);
-      r0c = row0_of(c);
-      const int32_t* ptrb = s_ptr + pbuf * (R + 1);
+    };
+    for (int64_t t = 0; t < 5; ++t) issue_ptr(t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int64_t t = 0; t < 3; ++t) issue_ent(t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    cp_async_commit();  // an empty group, so that "all but the newest group" below is uniform
+
+    unsigned int seen_done = 0;
+    int64_t ch = blockIdx.x;
+    for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
+      const int stage = (int)(t & 1);
+      // group G_{t-1} = {entries of chunk t+2, pointers of chunk t+4} may still fly; everything
+      // older has landed: entries up to chunk t+1, pointers up to chunk t+3
+      cp_async_wait<1>();
+      __syncwarp();
+      issue_ent(t + 3);
+      issue_ptr(t + 5);
+      cp_async_commit();
+      if (progress != nullptr && lane == 0) {  // window throttle (see spmm_csr.cu)
+        while ((int64_t)seen_done + p.window <= ch) {
+          seen_done = *reinterpret_cast<volatile unsigned int*>(progress);
+          if ((int64_t)seen_done + p.window <= ch) __nanosleep(200);
+        }
+      }
+      __syncwarp();
+      // ---- band check of chunk t
+      const int64_t r0c = row0_of(ch);
+      const int nr = rows_of(r0c);
+      const int32_t* ptrb = s_ptr + (int)(t % NP) * (R + 1);
       const int32_t base = ptrb[0];
-      const int32_t* colb = s_col + ebuf * L::kEntCap;
-      const T* valb = s_val + ebuf * L::kEntCap;
-      bool ok = nr == R && ptrb[R] - base <= L::kEntCap;
+      const int32_t* colb = s_col + (int)(t % NE) * L::kEntCap;
+      const T* valb = s_val + (int)(t % NE) * L::kEntCap;
+      int32_t o[SEGL];  // diagonal offsets
+#pragma unroll
+      for (int u = 0; u < SEGL; ++u) o[u] = 0;
+      bool ok = nr == R && ptrb[nr] - base <= L::kEntCap;
       int jb = 0, len = 0;
       if (ok && lane < R) {
         jb = ptrb[lane] - base;
@@ -260,186 +308,159 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
         // every X row the chunk touches must exist
         ok = ok && r0c + o[0] >= 0 && r0c + R - 1 + o[SEGL - 1] < n && r0c >= 1 && r0c + R < n;
       }
-      if (ok && lane < R) {
-        T* dr = s_dense + (size_t)stage * R * SEGL + lane * SEGL;
+      // the row's coefficients by diagonal, in registers until the stage is free
+      T dv[SEGL];
 #pragma unroll
-        for (int u = 0; u < SEGL; ++u) dr[u] = T(0);
+      for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
+      if (ok && lane < R) {
         ok = len <= SEGL;
         int u = 0;
         for (int e = 0; ok && e < len; ++e) {
           const int32_t d = colb[jb + e] - (int32_t)(r0c + lane);
+          const T a = valb[jb + e];
           // next diagonal that matches (columns ascend within a row)
+          bool hit = false;
 #pragma unroll
           for (int w = 0; w < SEGL; ++w)
-            if (w >= u && o[w] != d && w == u) ++u;
-          if (u >= SEGL) {
-            ok = false;
-          } else {
-            dr[u] = valb[jb + e];
-            ++u;
-          }
+            if (!hit && w >= u && o[w] == d) {
+              dv[w] = a;
+              u = w + 1;
+              hit = true;
+            }
+          ok = hit;
         }
       }
-      band = __all_sync(0xffffffffu, ok);
-    }
-    if (lane == 0) {
-      s_band[stage] = band ? 1 : 0;
-      s_far[stage * 2 + 0] = o[0];
-      s_far[stage * 2 + 1] = o[SEGL - 1];
-      T* xs = s_x + (size_t)stage * L::kStageRows * LD;
-      constexpr unsigned int row_bytes = LD * sizeof(T);
-      tma_mbar_expect_tx(&s_bar[stage], band ? (unsigned int)L::kStageRows * row_bytes : 0u);
-      if (band) {
+      const bool band = __all_sync(0xffffffffu, ok);
+      // the consumers have released this stage (its use two chunks ago)
+      if (t >= 2) tma_mbar_wait(&s_empty[stage], (unsigned int)(((t >> 1) + 1) & 1));
+      if (band && lane < R) {
+        T* dr = s_dense + (size_t)stage * R * SEGL + lane * SEGL;
 #pragma unroll
-        for (int u = FAR; u < UD - 1; ++u)  // staged far diagonals below the middle run
-          tma_bulk_g2s(xs + (size_t)((u - FAR) * R) * LD, X + (r0c + o[u]) * LD, R * row_bytes, &s_bar[stage]);
-        tma_bulk_g2s(xs + (size_t)MID * LD, X + (r0c - 1) * LD, (R + 2) * row_bytes, &s_bar[stage]);
+        for (int u = 0; u < SEGL; ++u) dr[u] = dv[u];
+      }
+      if (lane == 0) {
+        s_band[stage] = band ? 1 : 0;
+        s_far[stage * 2 + 0] = o[0];
+        s_far[stage * 2 + 1] = o[SEGL - 1];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        T* xs = s_x + (size_t)stage * L::kStageRows * LD;
+        constexpr unsigned int row_bytes = LD * sizeof(T);
+        tma_mbar_expect_tx(&s_full[stage], band ? (unsigned int)L::kStageRows * row_bytes : 0u);
+        if (band) {
 #pragma unroll
-        for (int u = UD + 2; u < SEGL - FAR; ++u)  // staged far diagonals above it
-          tma_bulk_g2s(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R) * LD, X + (r0c + o[u]) * LD,
-                       R * row_bytes, &s_bar[stage]);
+          for (int u = FAR; u < UD - 1; ++u)  // staged far diagonals below the middle run
+            tma_bulk_g2s(xs + (size_t)((u - FAR) * R) * LD, X + (r0c + o[u]) * LD, R * row_bytes, &s_full[stage]);
+          tma_bulk_g2s(xs + (size_t)MID * LD, X + (r0c - 1) * LD, (R + 2) * row_bytes, &s_full[stage]);
+#pragma unroll
+          for (int u = UD + 2; u < SEGL - FAR; ++u)  // staged far diagonals above it
+            tma_bulk_g2s(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R) * LD, X + (r0c + o[u]) * LD,
+                         R * row_bytes, &s_full[stage]);
+        }
       }
     }
-  };
-
-  // ---- prologue: pointers of chunks 0..2, entries of chunks 0..1, X of chunk 0
-  int64_t ch = blockIdx.x;
-  issue_ptr(ch, 0);
-  issue_ptr(ch + G, 1);
-  issue_ptr(ch + 2 * G, 2);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();  // pointers visible; mbarriers initialised; s_sv filled
-  issue_ent(ch, 0, 0);
-  issue_ent(ch + G, 1, 1);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
-  verify_and_stage(ch, 0, 0, 0);
-
-  unsigned int seen_done = 0;
-  for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
-    const int pb = (int)(t & 3), eb = (int)(t % 3), stage = (int)(t & 1);
-    if (progress != nullptr && threadIdx.x == kBlock) {
-      while ((int64_t)seen_done + p.window <= ch) {
-        seen_done = *reinterpret_cast<volatile unsigned int*>(progress);
-        if ((int64_t)seen_done + p.window <= ch) __nanosleep(200);
-      }
-    }
-    __syncthreads();  // metadata of chunks t+1 (entries), t+2 (pointers) visible; stage^1 is free
-    if (progress != nullptr && threadIdx.x == kBlock && t > 0) atomicAdd(progress, 1u);
-    // a whole chunk ahead: X rows of chunk t+1; two ahead: its entries; three ahead: its pointers
-    verify_and_stage(ch + G, (int)((t + 1) & 3), (int)((t + 1) % 3), stage ^ 1);
-    issue_ent(ch + 2 * G, (int)((t + 2) & 3), (int)((t + 2) % 3));
-    issue_ptr(ch + 3 * G, (int)((t + 3) & 3));
-    cp_async_commit();
-
-    const int64_t r0 = row0_of(ch);
-    const int nr = rows_of(ch);
-    const int32_t* __restrict__ ptrb = s_ptr + pb * (R + 1);
-    const int32_t base = ptrb[0];
-    const int total = ptrb[nr] - base;
-    const int32_t* __restrict__ colb = s_col + eb * L::kEntCap;
-    const T* __restrict__ valb = s_val + eb * L::kEntCap;
-    const int64_t coff = r0 * ld;
-
-    if (producer) continue;  // next barrier
+    cp_async_wait<0>();
+  } else {
+    // ------------------------------------------------------------------ consumer warps
     const int lr0 = grp * S;
-    const bool band = s_band[stage] != 0;
-    // the two outermost diagonals of a 7-diagonal band: gathered, in flight during the wait
-    T xf[FAR ? 2 : 1][S][VEC];
-    if constexpr (FAR > 0) {
-      if (band) {
-        const int64_t rlo = r0 + lr0 + s_far[stage * 2 + 0], rhi = r0 + lr0 + s_far[stage * 2 + 1];
+    int64_t ch = blockIdx.x;
+    for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
+      const int stage = (int)(t & 1);
+      const int64_t r0 = row0_of(ch);
+      const int64_t coff = r0 * ld;
+      tma_mbar_wait(&s_full[stage], (unsigned int)((t >> 1) & 1));  // X rows / table of chunk t landed
+      if (s_band[stage]) {
+        // the two outermost diagonals of a 7-diagonal band: gathered from global memory / L2
+        T xf[FAR ? 2 : 1][S][VEC];
+        if constexpr (FAR > 0) {
+          const int64_t rlo = r0 + lr0 + s_far[stage * 2 + 0], rhi = r0 + lr0 + s_far[stage * 2 + 1];
+#pragma unroll
+          for (int i = 0; i < S; ++i) {
+            ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
+            ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
+          }
+        }
+        const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
+        const T* __restrict__ xb = xs + (size_t)(MID + lr0) * LD;  // middle run: rows lr, lr+1, lr+2
+        T x[SEGL][VEC];
+        vec_load<T>(xb, x[UD - 1]);
+        vec_load<T>(xb + LD, x[UD]);
+        const T* __restrict__ vrow = s_dense + (size_t)stage * R * SEGL + lr0 * SEGL;
+        int64_t off = coff + (int64_t)lr0 * ld;
 #pragma unroll
         for (int i = 0; i < S; ++i) {
-          ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
-          ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
-        }
-      }
-    }
-    tma_mbar_wait(&s_bar[stage], (unsigned int)((t >> 1) & 1));  // X rows of chunk t have landed
-    if (band) {
-      const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
-      const T* __restrict__ xb = xs + (size_t)(MID + lr0) * LD;  // middle run: rows lr, lr+1, lr+2
-      T x[SEGL][VEC];
-      vec_load<T>(xb, x[UD - 1]);
-      vec_load<T>(xb + LD, x[UD]);
-      const T* __restrict__ vrow = s_dense + (size_t)stage * R * SEGL + lr0 * SEGL;
-      int64_t off = coff + (int64_t)lr0 * ld;
+          if constexpr (FAR > 0) {
 #pragma unroll
-      for (int i = 0; i < S; ++i) {
-        if constexpr (FAR > 0) {
+            for (int q = 0; q < VEC; ++q) {
+              x[0][q] = xf[0][i][q];
+              x[SEGL - 1][q] = xf[1][i][q];
+            }
+          }
+#pragma unroll
+          for (int u = FAR; u < UD - 1; ++u) vec_load<T>(xs + (size_t)((u - FAR) * R + lr0 + i) * LD, x[u]);
+          vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
+#pragma unroll
+          for (int u = UD + 2; u < SEGL - FAR; ++u)
+            vec_load<T>(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R + lr0 + i) * LD, x[u]);
+          T sum[VEC];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) sum[q] = T(0);
+#pragma unroll
+          for (int u = 0; u < SEGL; ++u) {
+            const T av = vrow[i * SEGL + u];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) sum[q] += av * x[u][q];
+          }
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) sum[q] *= sv[q];
+          if (FUSE_DOT) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc[0][q] += (double)(x[UD][q] * sv[q]) * (double)sum[q];
+          }
+          stw<T, VEC>(Wc, off, sum);
+          off += ld;
 #pragma unroll
           for (int q = 0; q < VEC; ++q) {
-            x[0][q] = xf[0][i][q];
-            x[SEGL - 1][q] = xf[1][i][q];
+            x[UD - 1][q] = x[UD][q];
+            x[UD][q] = x[UD + 1][q];
           }
         }
+      } else {
+        // not a band (first / last rows, anything irregular): gather path, metadata from global
+        const int nr = rows_of(r0);
+        for (int i = 0; i < S; ++i) {
+          const int lr = lr0 + i;
+          if (lr >= nr) break;
+          const int32_t jb = __ldg(indptr + r0 + lr), len = __ldg(indptr + r0 + lr + 1) - jb;
+          const TmaRowDot<VEC> d = tma_gather_row<T, VEC, LD, FUSE_DOT>(
+              indices + jb, data + jb, len, Xc, Wc, coff + (int64_t)lr * ld, s_sv + c0);
+          if (FUSE_DOT) {
 #pragma unroll
-        for (int u = FAR; u < UD - 1; ++u) vec_load<T>(xs + (size_t)((u - FAR) * R + lr0 + i) * LD, x[u]);
-        vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
-#pragma unroll
-        for (int u = UD + 2; u < SEGL - FAR; ++u)
-          vec_load<T>(xs + (size_t)(MID + R + 2 + (u - UD - 2) * R + lr0 + i) * LD, x[u]);
-        T sum[VEC];
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) sum[q] = T(0);
-#pragma unroll
-        for (int u = 0; u < SEGL; ++u) {
-          const T av = vrow[i * SEGL + u];
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) sum[q] += av * x[u][q];
-        }
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) sum[q] *= sv[q];
-        if (FUSE_DOT) {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) acc[0][q] += (double)(x[UD][q] * sv[q]) * (double)sum[q];
-        }
-        stw<T, VEC>(Wc, off, sum);
-        off += ld;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) {
-          x[UD - 1][q] = x[UD][q];
-          x[UD][q] = x[UD + 1][q];
+            for (int q = 0; q < VEC; ++q) acc[0][q] += d.d[q];
+          }
         }
       }
-    } else {
-      for (int i = 0; i < S; ++i) {
-        const int lr = lr0 + i;
-        if (lr >= nr) break;
-        const int32_t jb = ptrb[lr], len = ptrb[lr + 1] - jb;
-        const int32_t* cols = total <= L::kEntCap ? colb + (jb - base) : indices + jb;
-        const T* vals = total <= L::kEntCap ? valb + (jb - base) : data + jb;
-        const TmaRowDot<VEC> d = tma_gather_row<T, VEC, LD, FUSE_DOT>(
-            cols, vals, len, Xc, Wc, coff + (int64_t)lr * ld, s_sv + c0);
-        if (FUSE_DOT) {
-#pragma unroll
-          for (int q = 0; q < VEC; ++q) acc[0][q] += d.d[q];
-        }
+      __syncwarp();
+      if (lane == 0) {
+        tma_mbar_arrive(&s_empty[stage]);  // this warp is done with the stage
+        if (progress != nullptr && threadIdx.x == 0) atomicAdd(progress, 1u);
       }
     }
-    cp_async_wait<0>();  // entries of chunk t+2 / pointers of chunk t+3 landed (visible after the barrier)
   }
-  // the stage armed for the chunk after my last one (no copies: c >= nchunks) needs no wait
-  cp_async_wait<0>();
-  if (progress != nullptr) {
-    __syncthreads();
-    if (threadIdx.x == kBlock) {
-      if (blockIdx.x < nchunks) atomicAdd(progress, 1u);
-      __threadfence();
-      const unsigned int left = atomicAdd(progress + 1, 1u);
-      if (left == gridDim.x - 1) {
-        progress[0] = 0u;
-        progress[1] = 0u;
-      }
+  __syncthreads();  // all chunks of this CTA done; no copy is in flight (every armed phase was waited on)
+  if (progress != nullptr && threadIdx.x == 0) {
+    // the last CTA to leave re-arms the counters for the next launch
+    __threadfence();
+    const unsigned int left = atomicAdd(progress + 1, 1u);
+    if (left == gridDim.x - 1) {
+      progress[0] = 0u;
+      progress[1] = 0u;
     }
   }
   if (FUSE_DOT) {
     // the X stages are dead: their memory serves the CTA-level reduction (no static array, so two
-    // CTAs of 107 KB fit one SM)
-    __syncthreads();
+    // CTAs of ~105 KB fit one SM)
     cta_reduce_columns_smem<VEC, 1>(acc, ld, partial, 0, reinterpret_cast<double*>(smem));
     finalize_if_last<T>(ld, partial, 0, 1, fin);
   }
@@ -465,7 +486,7 @@ void spmm_tma_config(int use_tma) {
 int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
                         int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
                         int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
-                        bool* taken, int64_t bandwidth) {
+                        bool* taken, int64_t bandwidth, int32_t num_diagonals) {
   *taken = false;
   if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
   if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
@@ -473,6 +494,9 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   const bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;
   const int segl = (avg > 4.0 && avg <= 5.0) ? 5 : ((tma7 && avg > 6.0 && avg <= 7.0) ? 7 : 0);
   if (segl == 0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
+  // the host knows the diagonal count: only true 5- / 7-diagonal matrices (an irregular matrix that
+  // averages 5 entries per row would run every chunk on the slow gather path of this kernel)
+  if (num_diagonals > 0 && num_diagonals != segl) return MF_OK;
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
   static const int env_rows = env_int("MF_SPMM_TMA_ROWS", 16);

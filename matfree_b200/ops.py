@@ -142,13 +142,38 @@ class CsrOperator(Operator):
             first = self.indices[self.indptr[:-1][ne].long()].long()
             last = self.indices[(self.indptr[1:][ne] - 1).long()].long()
             self.bandwidth = int(torch.maximum((first - rows[ne]).abs(), (last - rows[ne]).abs()).max())
+        self.num_diagonals = self._count_diagonals(counts)
+
+    def _count_diagonals(self, counts):
+        """Number of distinct diagonals (col - row) if every entry lies on the diagonals of the longest
+        row and that row has at most 8 entries, else 255 ("many"); 0 for an empty matrix.  A hint for the
+        kernel choice (`mf_operator_t::csr_num_diagonals`): stencil matrices qualify, irregular ones do not."""
+        import torch
+
+        if self.nnz == 0 or self.n == 0:
+            return 0
+        if self.max_row_nnz > 8 or self.nnz >= 2 ** 31:
+            return 255
+        k = int(torch.argmax(counts))
+        j0 = int(self.indptr[k])
+        offs = (self.indices[j0:j0 + self.max_row_nnz] - k).tolist()
+        if len(set(offs)) != len(offs):
+            return 255
+        row_of = torch.repeat_interleave(torch.arange(self.n, device=self.indices.device, dtype=torch.int32),
+                                         counts.to(torch.int64))
+        d = self.indices - row_of
+        del row_of
+        on = torch.zeros_like(d, dtype=torch.bool)
+        for o in offs:
+            on |= d == o
+        return len(offs) if bool(on.all()) else 255
 
     def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
                                lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz,
-                               csr_bandwidth=self.bandwidth)
+                               csr_bandwidth=self.bandwidth, csr_num_diagonals=self.num_diagonals)
 
 
 class GramOperator(Operator):

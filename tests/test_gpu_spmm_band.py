@@ -142,3 +142,66 @@ def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical(spmm_knobs):
     a = est.per_probe(op, m.prng.prng_key(2), tile=256)
     b = est.per_probe(op, m.prng.prng_key(2), tile=32)
     assert torch.allclose(a, b, rtol=1e-6)
+
+
+def test_tma_kernel_partial_bands_and_diagonal_count_hint(spmm_knobs):
+    """The TMA-staged kernel at ld = 256 on matrices that are only partly bands: chunks whose rows
+    leave the five diagonals take its in-kernel gather path, x-boundary rows (a missing entry) stay
+    on the band path with a zero coefficient.  `ops.csr` counts the diagonals
+    (mf_operator_t::csr_num_diagonals): with the count known the kernel is chosen for true 5-diagonal
+    matrices only; with it forced to "unknown" the average row length decides and an irregular matrix
+    runs through the TMA kernel's fallback.  All routes agree bit for bit with the row-group kernel."""
+    import scipy.sparse as sp
+    from matfree_b200 import workloads
+
+    m = mfb()
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    ld = 256
+    # (a) 2-D Laplacian with non-constant coefficients: 5 diagonals
+    shape = (48, 64)
+    n = int(np.prod(shape))
+    ip, ix, d = workloads.laplacian_csr(shape, shift=0.5, device="cuda")
+    d = d * (1.0 + 0.25 * torch.rand(d.shape, generator=gen, device="cuda"))
+    op = m.ops.csr(ip, ix, d)
+    assert op.num_diagonals == 5 and op.bandwidth == 64
+    X = torch.randn((n, ld), generator=gen, device="cuda")
+    spmm_knobs.mf_spmm_config(0, 64, 2, 3)
+    W0 = op.matmat_blocked(X)
+    spmm_knobs.mf_spmm_config(2, 64, 2, 3)
+    assert torch.equal(op.matmat_blocked(X), W0)
+    assert np.allclose(W0.cpu().numpy(), scipy_csr(ip, ix, d, n) @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # (b) the same matrix with some entries moved off the diagonals (rows 100..139: column + 7)
+    A = scipy_csr(ip, ix, d, n).tolil()
+    for r in range(100, 140):
+        c = (r + 64) % n
+        v = A[r, c]
+        A[r, c] = 0.0
+        A[r, (c + 7) % n] = v if v != 0 else 0.125
+    A = A.tocsr()
+    A.eliminate_zeros()
+    A.sort_indices()
+    op2 = m.ops.csr_from_scipy(A)
+    assert op2.num_diagonals == 255
+    for forced in (255, 0):  # vetoed -> row-group kernel; unknown -> TMA kernel with per-chunk fallback
+        op2.num_diagonals = forced
+        spmm_knobs.mf_spmm_config(2, 64, 2, 3)
+        W2 = op2.matmat_blocked(X)
+        spmm_knobs.mf_spmm_config(0, 64, 2, 3)
+        assert torch.equal(op2.matmat_blocked(X), W2)
+    assert np.allclose(W2.cpu().numpy(), A @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # (c) no band structure at all, 4.5 entries per row on average
+    rng = np.random.default_rng(3)
+    B = sp.random(n, n, density=4.5 / n, random_state=rng, format="csr", dtype=np.float32)
+    B.sort_indices()
+    op3 = m.ops.csr_from_scipy(B)
+    assert op3.num_diagonals == 255
+    for forced in (255, 0):
+        op3.num_diagonals = forced
+        spmm_knobs.mf_spmm_config(2, 64, 2, 3)
+        W3 = op3.matmat_blocked(X)
+        spmm_knobs.mf_spmm_config(0, 64, 2, 3)
+        assert torch.equal(op3.matmat_blocked(X), W3)
+    assert np.allclose(W3.cpu().numpy(), B @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # (d) the 3-D stencil counts 7
+    ip3, ix3, d3 = workloads.laplacian_csr((5, 8, 16), shift=0.5, device="cuda")
+    assert m.ops.csr(ip3, ix3, d3).num_diagonals == 7
