@@ -111,11 +111,11 @@ __device__ __forceinline__ void tma_mbar_arrive(uint64_t* bar) {
 }
 
 // Dynamic shared memory layout (per CTA):
-//   [2 stages][3R + 2 rows][LD] T      X rows: run A (R), run B (R + 2), run C (R)
-//   [6][R + 1] int32                   producer-private: row pointers of chunks t .. t+5
+//   [NS stages][3R + 2 rows][LD] T     X rows: run A (R), run B (R + 2), run C (R)
+//   [8][R + 1] int32                   producer-private: row pointers of chunks t .. t+5
 //   [4][R * 8] int32, [4][R * 8] T     producer-private: column indices / values of chunks t .. t+3
 //   [LD] T                             column scales
-//   [2] full + [2] empty mbarriers, [2] band flags, [2][2] far offsets, [2][R * SEGL] T dense coefficients
+//   [NS] full + [NS] empty mbarriers, [NS] band flags, [NS][2] far offsets, [NS][R * SEGL] T dense coefficients
 // 7-diagonal bands (3-D stencils) stage only the five inner diagonals: the two outermost ones
 // (+- one plane) are gathered from global memory / L2 by the consumers, two loads per row issued
 // before the wait on the stage.  Staging all seven costs (5R + 2) KB per stage, which leaves one
@@ -127,17 +127,19 @@ struct TmaLayout {
   // the staged far diagonals (R rows each) + the run of the three adjacent middle ones (R + 2 rows)
   static constexpr int kStageRows = (SEGL - 3 - 2 * FAR) * R + R + 2;
   static constexpr int kEntCap = R * 8;
-  static constexpr int NP = 6, NE = 4;  // ring depths (pointers, entries)
+  static constexpr int NP = 8, NE = 4;  // ring depths (pointers: chunks t .. t+5, entries: t .. t+3), powers of two
+  // stages of the X ring: two of 50 KB at R = 16, four of 26 KB at R = 8 (the same ~100 KB per CTA)
+  static constexpr int NS = R <= 8 ? 4 : 2;
   static constexpr size_t kStageBytes = (size_t)kStageRows * LD * sizeof(T);
-  static constexpr size_t kPtrOff = 2 * kStageBytes;
+  static constexpr size_t kPtrOff = NS * kStageBytes;
   static constexpr size_t kColOff = (kPtrOff + NP * (R + 1) * sizeof(int32_t) + 15) / 16 * 16;
   static constexpr size_t kValOff = kColOff + NE * kEntCap * sizeof(int32_t);
   static constexpr size_t kSvOff = kValOff + NE * kEntCap * sizeof(T);
   static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
-  static constexpr size_t kFlagOff = kBarOff + 4 * sizeof(uint64_t);
-  static constexpr size_t kFarOff = kFlagOff + 4 * sizeof(int);
-  static constexpr size_t kDenseOff = kFarOff + 4 * sizeof(int);
-  static constexpr size_t kBytes = kDenseOff + 2 * (size_t)R * SEGL * sizeof(T);
+  static constexpr size_t kFlagOff = kBarOff + 2 * NS * sizeof(uint64_t);
+  static constexpr size_t kFarOff = kFlagOff + NS * sizeof(int);
+  static constexpr size_t kDenseOff = kFarOff + 2 * NS * sizeof(int);
+  static constexpr size_t kBytes = kDenseOff + NS * (size_t)R * SEGL * sizeof(T);
 };
 
 // Producer / consumer pipeline without CTA barriers in the steady state.  Warps 0..7 (kBlock
@@ -157,7 +159,7 @@ struct TmaLayout {
 //   consumer warp, chunk t: wait on `full`, compute its rows (band: LDS.128 + dense coefficients;
 //     otherwise the gather path with metadata straight from global memory), arrive on `empty`.
 template <typename T, int VEC, int LD, int SEGL, int ROWS, bool FUSE_DOT, bool BLOCKED>
-__global__ void __launch_bounds__(kBlock + 32, (ROWS <= 8) ? 3 : (ROWS <= 16 ? 2 : 1))
+__global__ void __launch_bounds__(kBlock + 32, ROWS <= 16 ? 2 : 1)
 spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
                 const T* __restrict__ s, T* __restrict__ W, SpmmParams p,
@@ -167,7 +169,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   constexpr int UD = SEGL / 2;
   constexpr int FAR = L::FAR;
   constexpr int MID = (UD - 1 - FAR) * R;  // first stage row of the middle run
-  constexpr int NP = L::NP, NE = L::NE;
+  constexpr int NP = L::NP, NE = L::NE, NS = L::NS;
   static_assert(R < 32, "the producer warp checks one row per lane");
   static_assert(SEGL == 5 || SEGL == 7, "5- or 7-diagonal bands");
   constexpr int ld = LD;
@@ -183,7 +185,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   T* const s_val = reinterpret_cast<T*>(smem + L::kValOff);               // [NE][kEntCap]
   T* const s_sv = reinterpret_cast<T*>(smem + L::kSvOff);
   uint64_t* const s_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* const s_empty = s_full + 2;
+  uint64_t* const s_empty = s_full + NS;
   int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [2] per stage
   int* const s_far = reinterpret_cast<int*>(smem + L::kFarOff);           // [2][2] offsets of the gathered diagonals
   T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [2][R][SEGL] coefficients by diagonal
@@ -206,10 +208,10 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   const int64_t G = gridDim.x;
 
   if (threadIdx.x == 0) {
-    tma_mbar_init(&s_full[0], 1);
-    tma_mbar_init(&s_full[1], 1);
-    tma_mbar_init(&s_empty[0], kConsumerWarps);
-    tma_mbar_init(&s_empty[1], kConsumerWarps);
+    for (int i = 0; i < NS; ++i) {
+      tma_mbar_init(&s_full[i], 1);
+      tma_mbar_init(&s_empty[i], kConsumerWarps);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();  // mbarriers initialised; s_sv filled
@@ -230,7 +232,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
         const int64_t r0c = row0_of(c);
         const int nr = rows_of(r0c);
         if (lane <= nr)
-          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[(int)(t % NP) * (R + 1) + lane]),
+          cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[(int)(t & (NP - 1)) * (R + 1) + lane]),
                       indptr + r0c + lane);
       }
     };
@@ -238,12 +240,12 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       const int64_t c = blockIdx.x + t * G;
       if (c < nchunks) {
         const int nr = rows_of(row0_of(c));
-        const int32_t* ptrb = s_ptr + (int)(t % NP) * (R + 1);
+        const int32_t* ptrb = s_ptr + (int)(t & (NP - 1)) * (R + 1);
         const int32_t base = ptrb[0];
         const int total = ptrb[nr] - base;
         if (total <= L::kEntCap) {
-          int32_t* cb = s_col + (int)(t % NE) * L::kEntCap;
-          T* vb = s_val + (int)(t % NE) * L::kEntCap;
+          int32_t* cb = s_col + (int)(t & (NE - 1)) * L::kEntCap;
+          T* vb = s_val + (int)(t & (NE - 1)) * L::kEntCap;
           for (int i = lane; i < total; i += 32) {
             cp_async<4>((uint32_t)__cvta_generic_to_shared(&cb[i]), indices + base + i);
             cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&vb[i]), data + base + i);
@@ -264,7 +266,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     unsigned int seen_done = 0;
     int64_t ch = blockIdx.x;
     for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
-      const int stage = (int)(t & 1);
+      const int stage = (int)(t & (NS - 1));
       // group G_{t-1} = {entries of chunk t+2, pointers of chunk t+4} may still fly; everything
       // older has landed: entries up to chunk t+1, pointers up to chunk t+3
       cp_async_wait<1>();
@@ -282,10 +284,10 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       // ---- band check of chunk t
       const int64_t r0c = row0_of(ch);
       const int nr = rows_of(r0c);
-      const int32_t* ptrb = s_ptr + (int)(t % NP) * (R + 1);
+      const int32_t* ptrb = s_ptr + (int)(t & (NP - 1)) * (R + 1);
       const int32_t base = ptrb[0];
-      const int32_t* colb = s_col + (int)(t % NE) * L::kEntCap;
-      const T* valb = s_val + (int)(t % NE) * L::kEntCap;
+      const int32_t* colb = s_col + (int)(t & (NE - 1)) * L::kEntCap;
+      const T* valb = s_val + (int)(t & (NE - 1)) * L::kEntCap;
       int32_t o[SEGL];  // diagonal offsets
 #pragma unroll
       for (int u = 0; u < SEGL; ++u) o[u] = 0;
@@ -312,7 +314,16 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       T dv[SEGL];
 #pragma unroll
       for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
-      if (ok && lane < R) {
+      if (fullm == (1u << R) - 1u) {
+        // every row has all SEGL entries (the common case): entry u must sit on diagonal u
+        if (ok && lane < R) {
+#pragma unroll
+          for (int u = 0; u < SEGL; ++u) {
+            ok = ok && colb[jb + u] - (int32_t)(r0c + lane) == o[u];
+            dv[u] = valb[jb + u];
+          }
+        }
+      } else if (ok && lane < R) {
         ok = len <= SEGL;
         int u = 0;
         for (int e = 0; ok && e < len; ++e) {
@@ -331,8 +342,8 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
         }
       }
       const bool band = __all_sync(0xffffffffu, ok);
-      // the consumers have released this stage (its use two chunks ago)
-      if (t >= 2) tma_mbar_wait(&s_empty[stage], (unsigned int)(((t >> 1) + 1) & 1));
+      // the consumers have released this stage (its use NS chunks ago)
+      if (t >= NS) tma_mbar_wait(&s_empty[stage], (unsigned int)(((t / NS) + 1) & 1));
       if (band && lane < R) {
         T* dr = s_dense + (size_t)stage * R * SEGL + lane * SEGL;
 #pragma unroll
@@ -366,10 +377,10 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
     const int lr0 = grp * S;
     int64_t ch = blockIdx.x;
     for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
-      const int stage = (int)(t & 1);
+      const int stage = (int)(t & (NS - 1));
       const int64_t r0 = row0_of(ch);
       const int64_t coff = r0 * ld;
-      tma_mbar_wait(&s_full[stage], (unsigned int)((t >> 1) & 1));  // X rows / table of chunk t landed
+      tma_mbar_wait(&s_full[stage], (unsigned int)((t / NS) & 1));  // X rows / table of chunk t landed
       if (s_band[stage]) {
         // the two outermost diagonals of a 7-diagonal band: gathered from global memory / L2
         T xf[FAR ? 2 : 1][S][VEC];
