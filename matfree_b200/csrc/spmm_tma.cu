@@ -502,7 +502,16 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
   if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
   const double avg = (double)nnz / (double)n;
-  const bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;
+  static const int env_rows = env_int("MF_SPMM_TMA_ROWS", 16);
+  // 7 diagonals: on by default where it was measured faster than the row-group kernel -- 3-D
+  // stencils walked in the blocked row order (11.1 vs 11.8 ms per product on the 256^3 target,
+  // profiles/r2zc_window.jsonl); elsewhere opt-in (MF_SPMM_TMA=2, mf_spmm_config(3, ...))
+  bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;
+  if (!tma7 && avg > 6.0 && avg <= 7.0) {
+    SpmmParams probe{(int)ld, env_rows <= 8 ? 8 : 16, 0, 0, 0, 0, 0, 0, 0, 0};
+    choose_row_order(&probe, n, avg, bandwidth, ld, dtype);
+    tma7 = probe.block_rows != 0;
+  }
   const int segl = (avg > 4.0 && avg <= 5.0) ? 5 : ((tma7 && avg > 6.0 && avg <= 7.0) ? 7 : 0);
   if (segl == 0 || n >= (1ll << 31) - 1 || nnz >= (1ll << 31) - 1) return MF_OK;
   // the host knows the diagonal count: only true 5- / 7-diagonal matrices (an irregular matrix that
@@ -510,7 +519,10 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   if (num_diagonals > 0 && num_diagonals != segl) return MF_OK;
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
-  static const int env_rows = env_int("MF_SPMM_TMA_ROWS", 16);
+  // completed-chunk window beyond the resident grid, in rows: wide in ascending order (C2: 6.6 ms at
+  // 24576 rows, 7.6 at 8192, 10.8 at 0), one block in the blocked order (3-D target: 11.1 ms at 4096
+  // rows, 11.7 at 24576 -- a wider window spreads the CTAs over more planes than L2 keeps)
+  static const int env_window_rows = env_int("MF_SPMM_TMA_WINDOW", 0);
   Finalize fin{};
   double* partial = nullptr;
   if (red) {
@@ -530,8 +542,10 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
       return MF_OK;                                                                                \
     }                                                                                              \
     const int grid = resident_grid((const void*)kern, kBlock + 32, L::kBytes, nchunks);            \
-    /* the rows in flight stay one contiguous window of about 24 K rows, as in the other kernels */ \
-    prm.window = grid + (int)(24576 / L::R);                                                       \
+    /* the rows in flight stay one contiguous window (see env_window_rows above) */              \
+    const int wrows = env_window_rows > 0 ? env_window_rows                                        \
+                                          : (prm.block_rows != 0 ? prm.block_rows : 24576);        \
+    prm.window = grid + wrows / L::R;                                                              \
     kern<<<grid, kBlock + 32, L::kBytes, st>>>(indptr, indices, (const float*)data, n,             \
                                                (const float*)X, (const float*)s, (float*)W, prm,   \
                                                prog, partial, fin);                                \
