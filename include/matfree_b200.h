@@ -180,9 +180,12 @@ int32_t mf_operator_split(const mf_operator_t* op, void* planes, void* stream);
  * use_band_kernel: 0 = the row-group gather kernel; 1 = banded / stencil matrices on tiles of at
  * least one warp per row take the band kernel (csrc/spmm_strip.cu: register window over adjacent
  * diagonals, TMA bulk copies of the CSR metadata); 2 = 5-diagonal band matrices on the 256-wide
- * fp32 tile take the TMA-staged kernel (csrc/spmm_tma.cu: the X rows of a chunk land in shared
- * memory by cp.async.bulk one chunk ahead); 3 = as 2, plus its 7-diagonal variant (3-D stencils;
- * measured slower than the gather kernel, opt-in).  All produce the same bits; the default is 2,
+ * fp32 tile take the TMA-staged kernels (csrc/spmm_tma.cu: the X rows of a chunk land in shared
+ * memory by cp.async.bulk ahead of their use; 2-D stencils whose line length is known from
+ * csr_bandwidth are walked down strips of the grid so that every X row is staged once; 3-D
+ * stencils in the blocked row order take the 7-diagonal variant); 3 = as 2, every 7-diagonal
+ * matrix takes the TMA kernel; 4 = as 3, and the strip walk whatever the problem size; 5 = as 3
+ * without the strip walk (3-5: tests and A/B runs).  All produce the same bits; the default is 2,
  * the one measured fastest on B200 (profiles/); matrices / tiles a kernel does not take fall
  * through to the row-group gather kernel.
  * rows_per_chunk (default 64), prefetch_rows (> 0: L2 prefetch distance, < 0: L1 prefetch

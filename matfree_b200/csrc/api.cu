@@ -650,7 +650,9 @@ int32_t mf_spmm_config(int32_t use_band_kernel, int32_t rows_per_chunk, int32_t 
                        int32_t min_ctas_per_sm) {
   // 0: row-group gather kernel; 1: band kernel (register window); 2 (default): band kernel with
   // the X rows staged in shared memory by TMA
-  // 3: as 2, and 7-diagonal matrices take the TMA kernel as well (measured slower: opt-in)
+  // 3: as 2, and every 7-diagonal matrix takes the TMA kernel (by default only 3-D stencils in the
+  //    blocked row order); 4: as 3, and the column-walk kernel whatever the problem size (tests);
+  // 5: as 3 without the column walk (the chunked TMA kernel on 2-D stencils: A/B runs, tests)
   if (use_band_kernel >= 0) spmm_tma_config(use_band_kernel >= 2 ? use_band_kernel - 1 : 0);
   spmm_strip_config(use_band_kernel < 0 ? -1 : (use_band_kernel == 1 ? 1 : 0), rows_per_chunk,
                     prefetch_rows, min_ctas_per_sm);

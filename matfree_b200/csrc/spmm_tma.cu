@@ -477,6 +477,320 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------- column walk (2-D 5-point bands)
+// The kernel above moves every X row from L2 into shared memory three times (as part of the -line
+// run, the middle run and the +line run of three different chunks): 54.6 GB of L2 -> SM traffic for
+// 17.2 GB of X (profiles/r2zb_spmm_2d_tma.txt), and its consumers spend 43 % of their time waiting
+// for a stage.  Here a CTA walks DOWN a strip of the grid instead: chunk (line l, strip s) = rows
+// l L + s R .. + R (L = the line length = the operator's bandwidth hint), then (l + 1, s), ... for
+// SEG lines.  Shared memory holds a ring of line segments X[l' L + s R - 1 .. + R + 2): the chunk
+// of line l needs the segments l - 1, l, l + 1, two of which the previous chunk already used, so
+// ONE TMA copy of R + 2 rows per chunk replaces three runs: 1.125 instead of 3.1 KB of L2 -> SM
+// traffic per row.  Work items = (segment of SEG lines, strip), item i -> CTA i mod grid, strips
+// of one segment adjacent in i, so the CTAs resident at any time read adjacent strips of the same
+// lines and X comes from DRAM once.  Everything else (producer warp with private metadata rings,
+// band check per chunk, dense coefficients, gather path for chunks that are not bands or touch
+// the first / last line, FMA order) is the kernel above; no completed-chunk window is needed.
+template <typename T, int LD, int ROWS>
+struct WalkLayout {
+  static constexpr int R = ROWS;
+  static constexpr int NSL = 5;  // line-segment slots: the chunk's three + two in flight
+  static constexpr int kSlotRows = R + 2;
+  static constexpr int kEntCap = R * 8;
+  static constexpr int NP = 8, NE = 4;
+  static constexpr size_t kSlotBytes = (size_t)kSlotRows * LD * sizeof(T);
+  static constexpr size_t kPtrOff = NSL * kSlotBytes;
+  static constexpr size_t kColOff = (kPtrOff + NP * (R + 1) * sizeof(int32_t) + 15) / 16 * 16;
+  static constexpr size_t kValOff = kColOff + NE * kEntCap * sizeof(int32_t);
+  static constexpr size_t kSvOff = kValOff + NE * kEntCap * sizeof(T);
+  static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
+  static constexpr size_t kFlagOff = kBarOff + 2 * NSL * sizeof(uint64_t);
+  static constexpr size_t kDenseOff = kFlagOff + 8 * sizeof(int);
+  static constexpr size_t kBytes = kDenseOff + NSL * (size_t)R * 5 * sizeof(T);
+};
+
+template <typename T, int VEC, int LD, int ROWS, bool FUSE_DOT>
+__global__ void __launch_bounds__(kBlock + 32, 2)
+spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                 const T* __restrict__ data, int64_t n, const T* __restrict__ X,
+                 const T* __restrict__ s, T* __restrict__ W, int64_t line, int seg,
+                 double* __restrict__ partial, Finalize fin) {
+  using L = WalkLayout<T, LD, ROWS>;
+  constexpr int R = L::R, SEGL = 5, UD = 2;
+  constexpr int NP = L::NP, NE = L::NE, NSL = L::NSL;
+  static_assert(R < 32, "the producer warp checks one row per lane");
+  constexpr int ld = LD;
+  constexpr int tpr = LD / VEC;
+  constexpr int rps = kBlock / tpr;
+  constexpr int S = R / rps;
+  constexpr int kConsumerWarps = kBlock / 32;
+  static_assert(tpr >= 32 && tpr % 32 == 0 && R % rps == 0 && S >= 1, "tile / chunk geometry");
+  extern __shared__ __align__(128) unsigned char smem[];
+  T* const s_x = reinterpret_cast<T*>(smem);                              // [NSL][R + 2][LD]
+  int32_t* const s_ptr = reinterpret_cast<int32_t*>(smem + L::kPtrOff);   // [NP][R + 1]
+  int32_t* const s_col = reinterpret_cast<int32_t*>(smem + L::kColOff);   // [NE][kEntCap]
+  T* const s_val = reinterpret_cast<T*>(smem + L::kValOff);               // [NE][kEntCap]
+  T* const s_sv = reinterpret_cast<T*>(smem + L::kSvOff);
+  uint64_t* const s_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* const s_empty = s_full + NSL;
+  int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [NSL] by the slot of the newest segment
+  T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [NSL][R][5]
+
+  const bool producer = threadIdx.x >= kBlock;
+  const int grp = threadIdx.x / tpr;
+  const int lane = threadIdx.x & 31;
+  const int c0 = (threadIdx.x % tpr) * VEC;
+  const T* __restrict__ Xc = X + c0;
+  T* __restrict__ Wc = W + c0;
+  T sv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) sv[i] = (s && !producer) ? s[c0 + i] : T(1);
+  for (int i = threadIdx.x; i < LD; i += kBlock + 32) s_sv[i] = s ? s[i] : T(1);
+  double acc[1][VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[0][i] = 0.0;
+
+  const int64_t lines = n / line;
+  const int strips = (int)(line / R);
+  const int64_t items = (lines / seg) * strips;
+  const int64_t G = gridDim.x;
+  const int64_t my_items = (int64_t)blockIdx.x < items ? (items - blockIdx.x + G - 1) / G : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSL; ++i) {
+      tma_mbar_init(&s_full[i], 1);
+      tma_mbar_init(&s_empty[i], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // first row of this CTA's chunk (item k, line y of its segment)
+  auto chunk_row = [&](int64_t k, int y) -> int64_t {
+    const int64_t item = blockIdx.x + k * G;
+    const int64_t g = item / strips;
+    const int sidx = (int)(item - g * strips);
+    return (g * seg + y) * line + (int64_t)sidx * R;
+  };
+
+  if (producer) {
+    // ------------------------------------------------------------------ producer warp
+    const int64_t my_chunks = my_items * seg;
+    auto row_of_t = [&](int64_t t) -> int64_t { return chunk_row(t / seg, (int)(t % seg)); };
+    auto issue_ptr = [&](int64_t t) {
+      if (t < my_chunks && lane <= R)
+        cp_async<4>((uint32_t)__cvta_generic_to_shared(&s_ptr[(int)(t & (NP - 1)) * (R + 1) + lane]),
+                    indptr + row_of_t(t) + lane);
+    };
+    auto issue_ent = [&](int64_t t) {  // needs the pointers of chunk t visible
+      if (t < my_chunks) {
+        const int32_t* ptrb = s_ptr + (int)(t & (NP - 1)) * (R + 1);
+        const int32_t base = ptrb[0];
+        const int total = ptrb[R] - base;
+        if (total <= L::kEntCap) {
+          int32_t* cb = s_col + (int)(t & (NE - 1)) * L::kEntCap;
+          T* vb = s_val + (int)(t & (NE - 1)) * L::kEntCap;
+          for (int i = lane; i < total; i += 32) {
+            cp_async<4>((uint32_t)__cvta_generic_to_shared(&cb[i]), indices + base + i);
+            cp_async<(int)sizeof(T)>((uint32_t)__cvta_generic_to_shared(&vb[i]), data + base + i);
+          }
+        }
+      }
+    };
+    for (int64_t t = 0; t < 5; ++t) issue_ptr(t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    for (int64_t t = 0; t < 3; ++t) issue_ent(t);
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    cp_async_commit();  // an empty group, so that "all but the newest group" below is uniform
+
+    int slot = 0;
+    unsigned int wraps = 0;  // how often the slot ring has wrapped
+    int64_t t = 0;           // chunk counter of this CTA
+    for (int64_t k = 0; k < my_items; ++k) {
+      const int64_t item = blockIdx.x + k * G;
+      const int64_t g = item / strips;
+      const int sidx = (int)(item - g * strips);
+      for (int j = 0; j < seg + 2; ++j) {
+        // line segment j of the item: line g seg - 1 + j, rows first .. first + R + 2
+        const int64_t lj = g * seg - 1 + j;
+        const int64_t first = lj * line + (int64_t)sidx * R - 1;
+        const bool valid = lj >= 0 && lj < lines && first >= 0 && first + R + 2 <= n;
+        bool band = false;
+        T dv[SEGL];
+#pragma unroll
+        for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
+        if (j >= 2) {
+          // ---- chunk t = (k, y = j - 2): metadata pipeline + band check
+          cp_async_wait<1>();
+          __syncwarp();
+          issue_ent(t + 3);
+          issue_ptr(t + 5);
+          cp_async_commit();
+          const int y = j - 2;
+          const int64_t ly = g * seg + y;
+          const int64_t r0c = ly * line + (int64_t)sidx * R;
+          const int32_t* ptrb = s_ptr + (int)(t & (NP - 1)) * (R + 1);
+          const int32_t base = ptrb[0];
+          const int32_t* colb = s_col + (int)(t & (NE - 1)) * L::kEntCap;
+          const T* valb = s_val + (int)(t & (NE - 1)) * L::kEntCap;
+          // the three line segments of the chunk must exist (not the first / last line; the last
+          // strip of the last but one line reaches one row past the matrix)
+          bool ok = ly >= 1 && ly + 1 < lines && r0c - line - 1 >= 0 && r0c + line + R + 1 <= n &&
+                    ptrb[R] - base <= L::kEntCap;
+          int jb = 0, len = 0;
+          if (ok && lane < R) {
+            jb = ptrb[lane] - base;
+            len = ptrb[lane + 1] - base - jb;
+          }
+          const int32_t o[SEGL] = {(int32_t)-line, -1, 0, 1, (int32_t)line};
+          const unsigned int fullm = __ballot_sync(0xffffffffu, ok && lane < R && len == SEGL);
+          if (fullm == (1u << R) - 1u) {
+            if (ok && lane < R) {
+#pragma unroll
+              for (int u = 0; u < SEGL; ++u) {
+                ok = ok && colb[jb + u] - (int32_t)(r0c + lane) == o[u];
+                dv[u] = valb[jb + u];
+              }
+            }
+          } else if (ok && lane < R) {
+            ok = len <= SEGL;
+            int u = 0;
+            for (int e = 0; ok && e < len; ++e) {
+              const int32_t d = colb[jb + e] - (int32_t)(r0c + lane);
+              const T a = valb[jb + e];
+              bool hit = false;
+#pragma unroll
+              for (int w = 0; w < SEGL; ++w)
+                if (!hit && w >= u && o[w] == d) {
+                  dv[w] = a;
+                  u = w + 1;
+                  hit = true;
+                }
+              ok = hit;
+            }
+          }
+          band = __all_sync(0xffffffffu, ok);
+          ++t;
+        }
+        // the consumers have released this slot (the segment NSL loads ago)
+        if (wraps > 0) tma_mbar_wait(&s_empty[slot], (wraps - 1) & 1u);
+        if (j >= 2) {
+          if (band && lane < R) {
+            T* dr = s_dense + (size_t)slot * R * SEGL + lane * SEGL;
+#pragma unroll
+            for (int u = 0; u < SEGL; ++u) dr[u] = dv[u];
+          }
+          if (lane == 0) s_band[slot] = band ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          constexpr unsigned int seg_bytes = (unsigned int)L::kSlotBytes;
+          tma_mbar_expect_tx(&s_full[slot], valid ? seg_bytes : 0u);
+          if (valid) tma_bulk_g2s(s_x + (size_t)slot * L::kSlotRows * LD, X + first * LD, seg_bytes, &s_full[slot]);
+        }
+        if (++slot == NSL) {
+          slot = 0;
+          ++wraps;
+        }
+      }
+    }
+    cp_async_wait<0>();
+  } else {
+    // ------------------------------------------------------------------ consumer warps
+    const int lr0 = grp * S;
+    int sl0 = 0;             // slot of the chunk's oldest segment (line l - 1)
+    unsigned int w0 = 0;     // ring wraps at sl0
+    for (int64_t k = 0; k < my_items; ++k) {
+      for (int y = 0; y < seg; ++y) {
+        const int64_t r0 = chunk_row(k, y);
+        const int64_t coff = r0 * ld;
+        int sl1 = sl0 + 1, sl2 = sl0 + 2;
+        unsigned int w1 = w0, w2 = w0;
+        if (sl1 >= NSL) { sl1 -= NSL; ++w1; }
+        if (sl2 >= NSL) { sl2 -= NSL; ++w2; }
+        tma_mbar_wait(&s_full[sl0], w0 & 1u);
+        tma_mbar_wait(&s_full[sl1], w1 & 1u);
+        tma_mbar_wait(&s_full[sl2], w2 & 1u);  // also publishes the chunk's table
+        if (s_band[sl2]) {
+          const T* __restrict__ xa = s_x + ((size_t)sl0 * L::kSlotRows + 1 + lr0) * LD + c0;  // line l - 1
+          const T* __restrict__ xb = s_x + ((size_t)sl1 * L::kSlotRows + lr0) * LD + c0;      // rows lr - 1 ..
+          const T* __restrict__ xc = s_x + ((size_t)sl2 * L::kSlotRows + 1 + lr0) * LD + c0;  // line l + 1
+          T x[SEGL][VEC];
+          vec_load<T>(xb, x[UD - 1]);
+          vec_load<T>(xb + LD, x[UD]);
+          const T* __restrict__ vrow = s_dense + (size_t)sl2 * R * SEGL + lr0 * SEGL;
+          int64_t off = coff + (int64_t)lr0 * ld;
+#pragma unroll
+          for (int i = 0; i < S; ++i) {
+            vec_load<T>(xa + (size_t)i * LD, x[0]);
+            vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
+            vec_load<T>(xc + (size_t)i * LD, x[SEGL - 1]);
+            T sum[VEC];
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) sum[q] = T(0);
+#pragma unroll
+            for (int u = 0; u < SEGL; ++u) {
+              const T av = vrow[i * SEGL + u];
+#pragma unroll
+              for (int q = 0; q < VEC; ++q) sum[q] += av * x[u][q];
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) sum[q] *= sv[q];
+            if (FUSE_DOT) {
+#pragma unroll
+              for (int q = 0; q < VEC; ++q) acc[0][q] += (double)(x[UD][q] * sv[q]) * (double)sum[q];
+            }
+            stw<T, VEC>(Wc, off, sum);
+            off += ld;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+              x[UD - 1][q] = x[UD][q];
+              x[UD][q] = x[UD + 1][q];
+            }
+          }
+        } else {
+          // not a band, or a chunk of the first / last line: gather path, metadata from global
+          for (int i = 0; i < S; ++i) {
+            const int lr = lr0 + i;
+            const int32_t jb = __ldg(indptr + r0 + lr), len = __ldg(indptr + r0 + lr + 1) - jb;
+            const TmaRowDot<VEC> d = tma_gather_row<T, VEC, LD, FUSE_DOT>(
+                indices + jb, data + jb, len, Xc, Wc, coff + (int64_t)lr * ld, s_sv + c0);
+            if (FUSE_DOT) {
+#pragma unroll
+              for (int q = 0; q < VEC; ++q) acc[0][q] += d.d[q];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tma_mbar_arrive(&s_empty[sl0]);  // the segment of line l - 1 has had its last use
+          if (y == seg - 1) {              // end of the item: so have the other two
+            tma_mbar_arrive(&s_empty[sl1]);
+            tma_mbar_arrive(&s_empty[sl2]);
+          }
+        }
+        if (y == seg - 1) {
+          // the next item starts three segments further
+          sl0 += 3;
+          if (sl0 >= NSL) { sl0 -= NSL; ++w0; }
+        } else {
+          sl0 = sl1;
+          w0 = w1;
+        }
+      }
+    }
+  }
+  __syncthreads();  // all chunks of this CTA done; every armed phase was waited on
+  if (FUSE_DOT) {
+    cta_reduce_columns_smem<VEC, 1>(acc, ld, partial, 0, reinterpret_cast<double*>(smem));
+    finalize_if_last<T>(ld, partial, 0, 1, fin);
+  }
+}
+
 // On by default for 5-diagonal matrices: 6.8-7.6 ms per product inside the Lanczos step of BASELINE
 // config 2 against 7.8-9.0 ms for the row-group kernel on the same pods, step 0.87-0.91 instead of
 // 0.80-0.86 of the HBM roofline (profiles/r2n_instep.jsonl, r2o_instep.jsonl, r2w_sweep.jsonl).  The
@@ -506,7 +820,7 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   // 7 diagonals: on by default where it was measured faster than the row-group kernel -- 3-D
   // stencils walked in the blocked row order (11.1 vs 11.8 ms per product on the 256^3 target,
   // profiles/r2zc_window.jsonl); elsewhere opt-in (MF_SPMM_TMA=2, mf_spmm_config(3, ...))
-  bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;
+  bool tma7 = g_tma.load(std::memory_order_relaxed) >= 2;  // modes 2, 3, 4
   if (!tma7 && avg > 6.0 && avg <= 7.0) {
     SpmmParams probe{(int)ld, env_rows <= 8 ? 8 : 16, 0, 0, 0, 0, 0, 0, 0, 0};
     choose_row_order(&probe, n, avg, bandwidth, ld, dtype);
@@ -531,6 +845,43 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   }
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;
+  // 2-D 5-point bands whose line length is known (the bandwidth hint): the column walk
+  static const int env_walk = env_int("MF_SPMM_WALK", 1);
+  const int mode = g_tma.load(std::memory_order_relaxed);  // 3: walk whatever the size; 4: never
+  if (segl == 5 && env_walk && mode != 4 && bandwidth >= 64 && bandwidth % 16 == 0 && n % bandwidth == 0 &&
+      bandwidth < (1ll << 30)) {
+    const int64_t lines = n / bandwidth;
+    const int64_t strips = bandwidth / 16;
+    // lines per work item: the longest segment (a divisor of the line count, 16 .. 512) that still
+    // leaves four items per resident CTA; else the shortest one
+    int seg = 0;
+    for (int d = 512; d >= 16 && seg == 0; --d)
+      if (lines % d == 0 && (lines / d) * strips >= 8 * (int64_t)num_sms()) seg = d;
+    for (int d = 16; d <= 512 && seg == 0; ++d)
+      if (lines % d == 0) seg = d;
+    const int64_t items = seg > 0 ? (lines / seg) * (bandwidth / 16) : 0;
+    if (seg > 0 && (items >= 2 * num_sms() || mode == 3)) {
+      using WL = WalkLayout<float, 256, 16>;
+#define MF_WALK_K(DOT)                                                                              \
+  do {                                                                                              \
+    auto kern = spmm_walk_kernel<float, 4, 256, 16, DOT>;                                           \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WL::kBytes) != \
+        cudaSuccess) {                                                                              \
+      cudaGetLastError();                                                                           \
+      *taken = false;                                                                               \
+      return MF_OK;                                                                                 \
+    }                                                                                               \
+    const int grid = resident_grid((const void*)kern, kBlock + 32, WL::kBytes, items);              \
+    kern<<<grid, kBlock + 32, WL::kBytes, st>>>(indptr, indices, (const float*)data, n,             \
+                                                (const float*)X, (const float*)s, (float*)W,        \
+                                                bandwidth, seg, partial, fin);                      \
+    return check_launch("spmm_walk");                                                               \
+  } while (0)
+      if (red) MF_WALK_K(true);
+      else MF_WALK_K(false);
+#undef MF_WALK_K
+    }
+  }
 #define MF_TMA_K(SEGL, ROWS, DOT, BLK)                                                             \
   do {                                                                                             \
     using L = TmaLayout<float, 4, 256, SEGL, ROWS>;                                                \

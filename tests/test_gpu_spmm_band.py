@@ -32,7 +32,7 @@ def spmm_knobs():
 
 
 @pytest.mark.parametrize("dtype,ld", [("float32", 256), ("float32", 128), ("float64", 256), ("float64", 64)])
-@pytest.mark.parametrize("shape", [(37, 70), (5, 103), (64, 256), (9, 10, 33), (3, 40, 64), (700,)])
+@pytest.mark.parametrize("shape", [(37, 70), (5, 103), (64, 256), (48, 64), (96, 128), (9, 10, 33), (3, 40, 64), (700,)])
 def test_band_kernel_matches_scipy_and_gather_kernel_bitwise(spmm_knobs, dtype, ld, shape):
     from matfree_b200 import workloads
 
@@ -46,8 +46,10 @@ def test_band_kernel_matches_scipy_and_gather_kernel_bitwise(spmm_knobs, dtype, 
     op = m.ops.csr(ip, ix, d)
     X = torch.randn((n, ld), generator=gen, device="cuda", dtype=d.dtype)
     results = {}
-    # 0: row-group gather kernel, 1: band kernel (register window), 2: TMA-staged band kernel
-    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, -2, 4), (2, 64, 2, 3), (3, 64, 2, 3)):
+    # 0: row-group gather kernel, 1: band kernel (register window), 2: TMA-staged band kernels,
+    # 3: + every 7-diagonal matrix, 4: + the strip walk whatever the size, 5: without the strip walk
+    for band, rows, pfd, minb in ((0, 64, 2, 4), (1, 64, 2, 4), (1, 32, 0, 3), (1, 128, -2, 4), (2, 64, 2, 3), (3, 64, 2, 3),
+                                  (4, 64, 2, 3), (5, 64, 2, 3)):
         lib.mf_spmm_config(band, rows, pfd, minb)
         results[(band, rows)] = op.matmat_blocked(X)
     want = scipy_csr(ip, ix, d, n) @ X.cpu().numpy()
@@ -78,7 +80,7 @@ def test_band_kernel_fused_alpha_dot_in_slq(spmm_knobs, dtype):
     est = m.stochtrace.estimator_monte_carlo(integrand, sampler)
     vals = {}
     tol = 1e-5 if dtype == np.float32 else 1e-10
-    for band, tile in ((0, 128), (1, 128), (0, 256), (2, 256)):
+    for band, tile in ((0, 128), (1, 128), (0, 256), (2, 256), (4, 256), (5, 256)):  # 4: strip walk (40 lines of 64)
         lib.mf_spmm_config(band, 64, 2, 4)
         vals[band] = est.per_probe(op, key, tile=tile).cpu().numpy()
         assert np.allclose(vals[0], vals[band], rtol=tol * 0.1, atol=0), (band, tile)
@@ -167,8 +169,9 @@ def test_tma_kernel_partial_bands_and_diagonal_count_hint(spmm_knobs):
     X = torch.randn((n, ld), generator=gen, device="cuda")
     spmm_knobs.mf_spmm_config(0, 64, 2, 3)
     W0 = op.matmat_blocked(X)
-    spmm_knobs.mf_spmm_config(2, 64, 2, 3)
-    assert torch.equal(op.matmat_blocked(X), W0)
+    for cfg in (2, 4):  # 4: the strip walk (48 lines of 64 rows)
+        spmm_knobs.mf_spmm_config(cfg, 64, 2, 3)
+        assert torch.equal(op.matmat_blocked(X), W0)
     assert np.allclose(W0.cpu().numpy(), scipy_csr(ip, ix, d, n) @ X.cpu().numpy(), rtol=1e-5, atol=1e-5)
     # (b) the same matrix with some entries moved off the diagonals (rows 100..139: column + 7)
     A = scipy_csr(ip, ix, d, n).tolil()
@@ -182,9 +185,9 @@ def test_tma_kernel_partial_bands_and_diagonal_count_hint(spmm_knobs):
     A.sort_indices()
     op2 = m.ops.csr_from_scipy(A)
     assert op2.num_diagonals == 255
-    for forced in (255, 0):  # vetoed -> row-group kernel; unknown -> TMA kernel with per-chunk fallback
+    for forced, cfg in ((255, 2), (0, 2), (0, 4)):  # vetoed -> row-group kernel; unknown -> TMA kernels with per-chunk fallback
         op2.num_diagonals = forced
-        spmm_knobs.mf_spmm_config(2, 64, 2, 3)
+        spmm_knobs.mf_spmm_config(cfg, 64, 2, 3)
         W2 = op2.matmat_blocked(X)
         spmm_knobs.mf_spmm_config(0, 64, 2, 3)
         assert torch.equal(op2.matmat_blocked(X), W2)
