@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MF_ABI_VERSION 6
+#define MF_ABI_VERSION 7
 
 /* status codes */
 #define MF_OK 0
@@ -113,6 +113,10 @@ typedef struct mf_operator {
                               * averages 5 entries per row then stays on the row-group kernel.
                               * Either way the kernel verifies every chunk and is correct for
                               * any CSR matrix. */
+  int64_t csr_line_stride;   /* CSR stencils, optional hint: the smallest diagonal offset above 1,
+                              * i.e. the length of a grid line (2-D: = csr_bandwidth; 3-D: the
+                              * +-line neighbour); 0 = unknown.  With it the TMA kernels walk
+                              * down strips of the grid (csrc/spmm_tma.cu) */
 } mf_operator_t;
 
 const char* mf_last_error(void);

@@ -36,6 +36,7 @@ class MfOperator(Structure):
         ("csr_max_row_nnz", c_int32),
         ("csr_bandwidth", c_int64),
         ("csr_num_diagonals", c_int32),
+        ("csr_line_stride", c_int64),
     ]
 
 

@@ -209,7 +209,8 @@ int32_t apply_op(const mf_operator_t* op, const void* X, const void* s, void* W,
                              W, ld, nullptr, nullptr, st, scr.spmm);
     }
     MF_TRY(launch_spmm_csr(op->indptr, op->indices, op->values, op->n, op->nnz, op->dtype, X, s, W,
-                           ld, red, tickets, st, nullptr, op->csr_bandwidth, op->csr_num_diagonals));
+                           ld, red, tickets, st, nullptr, op->csr_bandwidth, op->csr_num_diagonals,
+                           op->csr_line_stride));
     *fused = red != nullptr;
     return MF_OK;
   }

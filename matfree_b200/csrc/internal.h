@@ -113,7 +113,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* tickets,
                         cudaStream_t st, void* irregular_scratch = nullptr, int64_t bandwidth = 0,
-                        int32_t num_diagonals = 0);
+                        int32_t num_diagonals = 0, int64_t line_stride = 0);
 
 // ---- spmm_strip.cu : the band route of launch_spmm_csr (stencil / banded matrices, tiles wide
 // enough that a row is at least one warp).  *taken = false: not applicable, nothing launched.
@@ -128,7 +128,8 @@ void spmm_strip_config(int use_strip, int rows, int pfd, int minb);
 int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
                         int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
                         int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
-                        bool* taken, int64_t bandwidth = 0, int32_t num_diagonals = 0);
+                        bool* taken, int64_t bandwidth = 0, int32_t num_diagonals = 0,
+                        int64_t line_stride = 0);
 void spmm_tma_config(int use_tma);
 
 // ---- gemm_simt.cu

@@ -595,7 +595,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
                         int64_t n, int64_t nnz, int32_t dtype, const void* X, const void* s,
                         void* W, int64_t ld, const Reduce* red, unsigned int* progress,
                         cudaStream_t st, void* irregular_scratch, int64_t bandwidth,
-                        int32_t num_diagonals) {
+                        int32_t num_diagonals, int64_t line_stride) {
   MF_KSCOPE(MF_KC_SPMM_CSR, st);
   if (n <= 0) return MF_OK;
   if (irregular_scratch != nullptr) {
@@ -627,7 +627,7 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     // 5-diagonal band matrices on the 256-wide fp32 tile: X rows staged by TMA (spmm_tma.cu)
     bool taken = false;
     const int32_t rc = launch_spmm_tma(indptr, indices, data, n, nnz, dtype, X, s, W, ld, red, progress,
-                                       st, &taken, bandwidth, num_diagonals);
+                                       st, &taken, bandwidth, num_diagonals, line_stride);
     if (taken) return rc;
   }
   {

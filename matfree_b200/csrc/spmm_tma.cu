@@ -491,7 +491,7 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
 // lines and X comes from DRAM once.  Everything else (producer warp with private metadata rings,
 // band check per chunk, dense coefficients, gather path for chunks that are not bands or touch
 // the first / last line, FMA order) is the kernel above; no completed-chunk window is needed.
-template <typename T, int LD, int ROWS>
+template <typename T, int LD, int SEGL, int ROWS>
 struct WalkLayout {
   static constexpr int R = ROWS;
   static constexpr int NSL = 5;  // line-segment slots: the chunk's three + two in flight
@@ -506,17 +506,24 @@ struct WalkLayout {
   static constexpr size_t kBarOff = (kSvOff + LD * sizeof(T) + 15) / 16 * 16;
   static constexpr size_t kFlagOff = kBarOff + 2 * NSL * sizeof(uint64_t);
   static constexpr size_t kDenseOff = kFlagOff + 8 * sizeof(int);
-  static constexpr size_t kBytes = kDenseOff + NSL * (size_t)R * 5 * sizeof(T);
+  static constexpr size_t kBytes = kDenseOff + NSL * (size_t)R * SEGL * sizeof(T);
 };
 
-template <typename T, int VEC, int LD, int ROWS, bool FUSE_DOT>
+// SEGL = 7 (3-D stencils: offsets -plane, -line, -1, 0, 1, line, plane): the five inner diagonals
+// as above; the +-plane rows are gathered from global memory / L2 by the consumers, issued before
+// the waits on the segments.  One work item = one plane's strip (seg = lines per plane), so the
+// CTAs resident at a time walk the same lines of ~18 consecutive planes and the +-plane rows a
+// CTA gathers are the rows its neighbours in z stage at about the same time.
+template <typename T, int VEC, int LD, int SEGL, int ROWS, bool FUSE_DOT>
 __global__ void __launch_bounds__(kBlock + 32, 2)
 spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
                  const T* __restrict__ data, int64_t n, const T* __restrict__ X,
-                 const T* __restrict__ s, T* __restrict__ W, int64_t line, int seg,
-                 double* __restrict__ partial, Finalize fin) {
-  using L = WalkLayout<T, LD, ROWS>;
-  constexpr int R = L::R, SEGL = 5, UD = 2;
+                 const T* __restrict__ s, T* __restrict__ W, int64_t line, int64_t plane, int seg,
+                 unsigned int* __restrict__ progress, int window, double* __restrict__ partial,
+                 Finalize fin) {
+  using L = WalkLayout<T, LD, SEGL, ROWS>;
+  constexpr int R = L::R, UD = SEGL / 2, FAR = SEGL == 7 ? 1 : 0;
+  static_assert(SEGL == 5 || SEGL == 7, "5- or 7-diagonal bands");
   constexpr int NP = L::NP, NE = L::NE, NSL = L::NSL;
   static_assert(R < 32, "the producer warp checks one row per lane");
   constexpr int ld = LD;
@@ -534,7 +541,7 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
   uint64_t* const s_full = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* const s_empty = s_full + NSL;
   int* const s_band = reinterpret_cast<int*>(smem + L::kFlagOff);         // [NSL] by the slot of the newest segment
-  T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [NSL][R][5]
+  T* const s_dense = reinterpret_cast<T*>(smem + L::kDenseOff);           // [NSL][R][SEGL]
 
   const bool producer = threadIdx.x >= kBlock;
   const int grp = threadIdx.x / tpr;
@@ -610,6 +617,7 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
     int slot = 0;
     unsigned int wraps = 0;  // how often the slot ring has wrapped
     int64_t t = 0;           // chunk counter of this CTA
+    unsigned int seen_done = 0;
     for (int64_t k = 0; k < my_items; ++k) {
       const int64_t item = blockIdx.x + k * G;
       const int64_t g = item / strips;
@@ -624,7 +632,24 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
 #pragma unroll
         for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
         if (j >= 2) {
-          // ---- chunk t = (k, y = j - 2): metadata pipeline + band check
+          // ---- chunk t = (k, y = j - 2).  Step throttle (3-D): the +-plane rows a CTA gathers are
+          // in L2 only while its neighbours in z walk the same lines, so no CTA may run more than
+          // `window` chunks (counted over the whole grid) ahead of the completed ones
+          // (only over the steps every CTA has: in the last, partial wave of items the completed
+          // count no longer grows by the whole grid per step)
+          if (progress != nullptr && lane == 0 && t < (items / G) * seg) {
+            const int64_t vch = t * G + blockIdx.x;
+            unsigned int spins = 0;
+            while ((int64_t)seen_done + window <= vch) {
+              seen_done = *reinterpret_cast<volatile unsigned int*>(progress);
+              if ((int64_t)seen_done + window <= vch) {
+                __nanosleep(200);
+                if (++spins > (1u << 26)) __trap();  // a protocol bug must not hang the GPU
+              }
+            }
+          }
+          __syncwarp();
+          // metadata pipeline + band check
           cp_async_wait<1>();
           __syncwarp();
           issue_ent(t + 3);
@@ -641,12 +666,22 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
           // strip of the last but one line reaches one row past the matrix)
           bool ok = ly >= 1 && ly + 1 < lines && r0c - line - 1 >= 0 && r0c + line + R + 1 <= n &&
                     ptrb[R] - base <= L::kEntCap;
+          if (FAR) ok = ok && r0c - plane >= 0 && r0c + R - 1 + plane < n;  // the gathered rows exist
           int jb = 0, len = 0;
           if (ok && lane < R) {
             jb = ptrb[lane] - base;
             len = ptrb[lane + 1] - base - jb;
           }
-          const int32_t o[SEGL] = {(int32_t)-line, -1, 0, 1, (int32_t)line};
+          int32_t o[SEGL];
+          o[UD] = 0;
+          o[UD - 1] = -1;
+          o[UD + 1] = 1;
+          o[UD - 2] = (int32_t)-line;
+          o[UD + 2] = (int32_t)line;
+          if constexpr (FAR > 0) {
+            o[0] = (int32_t)-plane;
+            o[SEGL - 1] = (int32_t)plane;
+          }
           const unsigned int fullm = __ballot_sync(0xffffffffu, ok && lane < R && len == SEGL);
           if (fullm == (1u << R) - 1u) {
             if (ok && lane < R) {
@@ -712,6 +747,21 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
         unsigned int w1 = w0, w2 = w0;
         if (sl1 >= NSL) { sl1 -= NSL; ++w1; }
         if (sl2 >= NSL) { sl2 -= NSL; ++w2; }
+        // the +-plane rows of a 7-diagonal band: gathered, in flight during the waits below
+        // (two rows ahead: all S rows at once cost 32 registers and spilled)
+        constexpr int FD = S < 2 ? S : 2;
+        T xf[FAR ? 2 : 1][FD][VEC];
+        const bool far_ok = FAR > 0 && r0 - plane >= 0 && r0 + R - 1 + plane < n;
+        const int64_t rlo = r0 + lr0 - plane, rhi = r0 + lr0 + plane;
+        if constexpr (FAR > 0) {
+          if (far_ok) {
+#pragma unroll
+            for (int i = 0; i < FD; ++i) {
+              ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
+              ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
+            }
+          }
+        }
         tma_mbar_wait(&s_full[sl0], w0 & 1u);
         tma_mbar_wait(&s_full[sl1], w1 & 1u);
         tma_mbar_wait(&s_full[sl2], w2 & 1u);  // also publishes the chunk's table
@@ -726,9 +776,20 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
           int64_t off = coff + (int64_t)lr0 * ld;
 #pragma unroll
           for (int i = 0; i < S; ++i) {
-            vec_load<T>(xa + (size_t)i * LD, x[0]);
+            if constexpr (FAR > 0) {
+#pragma unroll
+              for (int q = 0; q < VEC; ++q) {
+                x[0][q] = xf[0][i % FD][q];
+                x[SEGL - 1][q] = xf[1][i % FD][q];
+              }
+              if (i + FD < S) {  // the band flag implies far_ok
+                ldx<T, VEC>(Xc, (rlo + i + FD) * LD, xf[0][i % FD]);
+                ldx<T, VEC>(Xc, (rhi + i + FD) * LD, xf[1][i % FD]);
+              }
+            }
+            vec_load<T>(xa + (size_t)i * LD, x[UD - 2]);
             vec_load<T>(xb + (size_t)(i + 2) * LD, x[UD + 1]);
-            vec_load<T>(xc + (size_t)i * LD, x[SEGL - 1]);
+            vec_load<T>(xc + (size_t)i * LD, x[UD + 2]);
             T sum[VEC];
 #pragma unroll
             for (int q = 0; q < VEC; ++q) sum[q] = T(0);
@@ -767,6 +828,7 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
         }
         __syncwarp();
         if (lane == 0) {
+          if (progress != nullptr && threadIdx.x == 0) atomicAdd(progress, 1u);
           tma_mbar_arrive(&s_empty[sl0]);  // the segment of line l - 1 has had its last use
           if (y == seg - 1) {              // end of the item: so have the other two
             tma_mbar_arrive(&s_empty[sl1]);
@@ -785,6 +847,15 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
     }
   }
   __syncthreads();  // all chunks of this CTA done; every armed phase was waited on
+  if (progress != nullptr && threadIdx.x == 0) {
+    // the last CTA to leave re-arms the counters for the next launch
+    __threadfence();
+    const unsigned int left = atomicAdd(progress + 1, 1u);
+    if (left == gridDim.x - 1) {
+      progress[0] = 0u;
+      progress[1] = 0u;
+    }
+  }
   if (FUSE_DOT) {
     cta_reduce_columns_smem<VEC, 1>(acc, ld, partial, 0, reinterpret_cast<double*>(smem));
     finalize_if_last<T>(ld, partial, 0, 1, fin);
@@ -811,7 +882,7 @@ void spmm_tma_config(int use_tma) {
 int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const void* data, int64_t n,
                         int64_t nnz, int32_t dtype, const void* X, const void* s, void* W,
                         int64_t ld, const Reduce* red, unsigned int* progress, cudaStream_t st,
-                        bool* taken, int64_t bandwidth, int32_t num_diagonals) {
+                        bool* taken, int64_t bandwidth, int32_t num_diagonals, int64_t line_stride) {
   *taken = false;
   if (!g_tma.load(std::memory_order_relaxed) || n <= 0) return MF_OK;
   if (dtype != MF_F32 || ld != 256) return MF_OK;  // fp32, one 1 KB row per probe-tile row
@@ -845,40 +916,61 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   }
   unsigned int* prog = env_throttle ? progress : nullptr;
   *taken = true;
-  // 2-D 5-point bands whose line length is known (the bandwidth hint): the column walk
+  // stencils whose line length is known (2-D: the bandwidth hint; 3-D: csr_line_stride): the strip walk
   static const int env_walk = env_int("MF_SPMM_WALK", 1);
+  static const int env_walk_slack = env_int("MF_SPMM_WALK_SLACK", 3);  // line steps a CTA may run ahead (3-D)
   const int mode = g_tma.load(std::memory_order_relaxed);  // 3: walk whatever the size; 4: never
-  if (segl == 5 && env_walk && mode != 4 && bandwidth >= 64 && bandwidth % 16 == 0 && n % bandwidth == 0 &&
-      bandwidth < (1ll << 30)) {
-    const int64_t lines = n / bandwidth;
-    const int64_t strips = bandwidth / 16;
-    // lines per work item: the longest segment (a divisor of the line count, 16 .. 512) that still
-    // leaves four items per resident CTA; else the shortest one
+  const int64_t wline = segl == 5 ? bandwidth : line_stride;
+  const int64_t wplane = segl == 5 ? 0 : bandwidth;
+  // (3-D: measured slower than the chunked kernel, 13.1 vs 10.7 ms on the 256^3 target whatever the
+  // step throttle -- the +-plane gathers sit in the consumers' critical path and shared memory has no
+  // room to stage them as well; profiles/r2zg_walk.jsonl, r2zh_walk.jsonl -- so only on request)
+  if (env_walk && mode != 4 && (segl == 5 || mode == 3) && wline >= 64 && wline % 16 == 0 && n % wline == 0 &&
+      bandwidth < (1ll << 30) &&
+      (segl == 5 ? (line_stride == 0 || line_stride == bandwidth)
+                 : (wplane > wline && wplane % wline == 0 && n % wplane == 0))) {
+    const int64_t lines = n / wline;
+    const int64_t strips = wline / 16;
+    // lines per work item.  2-D: the longest segment (a divisor of the line count, 16 .. 512) that
+    // still leaves four items per resident CTA, else the shortest one; 3-D: one plane
     int seg = 0;
-    for (int d = 512; d >= 16 && seg == 0; --d)
-      if (lines % d == 0 && (lines / d) * strips >= 8 * (int64_t)num_sms()) seg = d;
-    for (int d = 16; d <= 512 && seg == 0; ++d)
-      if (lines % d == 0) seg = d;
-    const int64_t items = seg > 0 ? (lines / seg) * (bandwidth / 16) : 0;
+    if (segl == 7) {
+      const int64_t lpp = wplane / wline;
+      if (lpp >= 16 && lpp <= 4096) seg = (int)lpp;
+    } else {
+      for (int d = 512; d >= 16 && seg == 0; --d)
+        if (lines % d == 0 && (lines / d) * strips >= 8 * (int64_t)num_sms()) seg = d;
+      for (int d = 16; d <= 512 && seg == 0; ++d)
+        if (lines % d == 0) seg = d;
+    }
+    const int64_t items = seg > 0 ? (lines / seg) * strips : 0;
     if (seg > 0 && (items >= 2 * num_sms() || mode == 3)) {
-      using WL = WalkLayout<float, 256, 16>;
-#define MF_WALK_K(DOT)                                                                              \
+#define MF_WALK_K(SEGL, DOT)                                                                        \
   do {                                                                                              \
-    auto kern = spmm_walk_kernel<float, 4, 256, 16, DOT>;                                           \
+    using WL = WalkLayout<float, 256, SEGL, 16>;                                                    \
+    auto kern = spmm_walk_kernel<float, 4, 256, SEGL, 16, DOT>;                                     \
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WL::kBytes) != \
         cudaSuccess) {                                                                              \
       cudaGetLastError();                                                                           \
       *taken = false;                                                                               \
       return MF_OK;                                                                                 \
     }                                                                                               \
-    const int grid = resident_grid((const void*)kern, kBlock + 32, WL::kBytes, items);              \
+    int grid = resident_grid((const void*)kern, kBlock + 32, WL::kBytes, items);                    \
+    /* 3-D: whole planes per wave of CTAs, and the step throttle (see the kernel) */                \
+    if ((SEGL) == 7 && grid > strips) grid = (int)(grid / strips * strips);                         \
     kern<<<grid, kBlock + 32, WL::kBytes, st>>>(indptr, indices, (const float*)data, n,             \
                                                 (const float*)X, (const float*)s, (float*)W,        \
-                                                bandwidth, seg, partial, fin);                      \
+                                                wline, wplane, seg, (SEGL) == 7 ? prog : nullptr,   \
+                                                grid * (1 + env_walk_slack), partial, fin);         \
     return check_launch("spmm_walk");                                                               \
   } while (0)
-      if (red) MF_WALK_K(true);
-      else MF_WALK_K(false);
+      if (segl == 5) {
+        if (red) MF_WALK_K(5, true);
+        else MF_WALK_K(5, false);
+      } else {
+        if (red) MF_WALK_K(7, true);
+        else MF_WALK_K(7, false);
+      }
 #undef MF_WALK_K
     }
   }

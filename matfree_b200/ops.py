@@ -150,6 +150,7 @@ class CsrOperator(Operator):
         kernel choice (`mf_operator_t::csr_num_diagonals`): stencil matrices qualify, irregular ones do not."""
         import torch
 
+        self.line_stride = 0
         if self.nnz == 0 or self.n == 0:
             return 0
         if self.max_row_nnz > 8 or self.nnz >= 2 ** 31:
@@ -166,14 +167,19 @@ class CsrOperator(Operator):
         on = torch.zeros_like(d, dtype=torch.bool)
         for o in offs:
             on |= d == o
-        return len(offs) if bool(on.all()) else 255
+        if not bool(on.all()):
+            return 255
+        above = [o for o in offs if o > 1]
+        self.line_stride = min(above) if above else 0  # `mf_operator_t::csr_line_stride`
+        return len(offs)
 
     def _struct(self):
         return _lib.MfOperator(kind=self.kind, dtype=_device.mf_dtype(self.dtype), n=self.n, m=self.n,
                                nnz=self.nnz, values=self.data.data_ptr(),
                                indptr=self.indptr.data_ptr(), indices=self.indices.data_ptr(),
                                lda=0, split_planes=None, csr_max_row_nnz=self.max_row_nnz,
-                               csr_bandwidth=self.bandwidth, csr_num_diagonals=self.num_diagonals)
+                               csr_bandwidth=self.bandwidth, csr_num_diagonals=self.num_diagonals,
+                               csr_line_stride=self.line_stride)
 
 
 class GramOperator(Operator):

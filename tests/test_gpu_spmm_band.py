@@ -129,7 +129,10 @@ def test_blocked_row_order_for_wide_3d_stencils_is_bit_identical(spmm_knobs):
     Xn = X[:, :32].contiguous()
     Wn = op.matmat_blocked(Xn)                    # 2 * 8 MB planes: ascending order
     assert torch.equal(W[:, :32], Wn)
-    spmm_knobs.mf_spmm_config(3, 64, 2, 3)        # the TMA-staged 7-diagonal kernel, blocked order
+    assert op.num_diagonals == 7 and op.line_stride == 256
+    spmm_knobs.mf_spmm_config(5, 64, 2, 3)        # the TMA-staged 7-diagonal kernel, blocked order
+    assert torch.equal(op.matmat_blocked(X), W)
+    spmm_knobs.mf_spmm_config(4, 64, 2, 3)        # the strip walk (one item = one plane's strip)
     assert torch.equal(op.matmat_blocked(X), W)
     spmm_knobs.mf_spmm_config(0, 64, 2, 3)        # the gather kernel, forced
     assert torch.equal(op.matmat_blocked(X), W)

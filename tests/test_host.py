@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
-    assert lib.mf_abi_version() == 6
+    assert lib.mf_abi_version() == 7
     assert lib.mf_launch_count() == 0
 
 
