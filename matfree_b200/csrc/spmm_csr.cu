@@ -589,6 +589,47 @@ int32_t launch_irregular(const int32_t* indptr, const int32_t* indices, const T*
   }
   return check_launch("spmm_long_rows");
 }
+// One thread per row, metadata straight from global memory, no staging and no barriers: the route
+// for a single vector (ld = 1: BASELINE config 4, where the product is bound by streaming the
+// matrix).  The staged row-group kernel above moves 14 KB of metadata per 256-row chunk between
+// two CTA barriers and is latency-bound there (2.5-3.1 TB/s of matrix stream on the 256^3 7-point
+// Laplacian); here every thread keeps its row's (column, value) pairs and X gathers in flight at
+// once, 2048 threads per SM.  Rows of up to 8 entries are fully unrolled; the FMA order is the CSR
+// order, so the results are those of the other kernels bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+spmm_row_thread_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                       const T* __restrict__ data, int64_t n, const T* __restrict__ X,
+                       const T* __restrict__ s, T* __restrict__ W) {
+  const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n) return;
+  const T sc = s ? s[0] : T(1);
+  const int32_t jb = __ldg(indptr + r), je = __ldg(indptr + r + 1);
+  const int len = je - jb;
+  T sum = T(0);
+  if (len <= 8) {
+    int32_t c[8];
+    T a[8], x[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      c[u] = 0;
+      a[u] = T(0);
+      if (u < len) {
+        c[u] = __ldg(indices + jb + u);
+        a[u] = __ldg(data + jb + u);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] = u < len ? __ldg(X + c[u]) : T(0);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (u < len) sum += a[u] * x[u];
+  } else {
+    for (int32_t j = jb; j < je; ++j) sum += __ldg(data + j) * __ldg(X + __ldg(indices + j));
+  }
+  W[r] = sum * sc;
+}
+
 }  // namespace
 
 int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const void* data,
@@ -619,6 +660,20 @@ int32_t launch_spmm_csr(const int32_t* indptr, const int32_t* indices, const voi
     return launch_irregular<double, 1>(indptr, indices, (const double*)data, n, nnz,
                                        (const double*)X, (const double*)s, (double*)W, ld,
                                        irregular_scratch, st);
+  }
+  if (ld == 1 && red == nullptr && n < (1ll << 31) * 256) {
+    // a single vector without the fused dot: one thread per row (see the kernel)
+    static const int env_row_thread = env_int("MF_SPMM_ROW_THREAD", 1);
+    if (env_row_thread) {
+      const unsigned int grid = (unsigned int)((n + 255) / 256);
+      if (dtype == MF_F32)
+        spmm_row_thread_kernel<float><<<grid, 256, 0, st>>>(indptr, indices, (const float*)data, n,
+                                                           (const float*)X, (const float*)s, (float*)W);
+      else
+        spmm_row_thread_kernel<double><<<grid, 256, 0, st>>>(indptr, indices, (const double*)data, n,
+                                                            (const double*)X, (const double*)s, (double*)W);
+      return check_launch("spmm_row_thread");
+    }
   }
   const int nv = dtype == MF_F64 ? 2 : 4;
   const int vec = ld >= nv ? nv : 1;

@@ -211,3 +211,30 @@ def test_tma_kernel_partial_bands_and_diagonal_count_hint(spmm_knobs):
     # (d) the 3-D stencil counts 7
     ip3, ix3, d3 = workloads.laplacian_csr((5, 8, 16), shift=0.5, device="cuda")
     assert m.ops.csr(ip3, ix3, d3).num_diagonals == 7
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_single_vector_row_thread_kernel_matches_wider_tiles_bitwise(dtype):
+    """ld = 1 (a single vector, BASELINE config 4) takes the one-thread-per-row kernel: the same
+    CSR-order FMAs as the tiled kernels, so column 0 of a wider tile has the same bits."""
+    import scipy.sparse as sp
+    from matfree_b200 import workloads
+
+    m = mfb()
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    tdt = torch.float32 if dtype == "float32" else torch.float64
+    ip, ix, d = workloads.laplacian_csr((9, 10, 33), shift=0.5, dtype=dtype, device="cuda")
+    d = d * (1.0 + 0.25 * torch.rand(d.shape, generator=gen, device="cuda", dtype=tdt))
+    ops_ = [m.ops.csr(ip, ix, d)]
+    rng = np.random.default_rng(4)
+    B = sp.random(3000, 3000, density=20.0 / 3000, random_state=rng, format="csr", dtype=np.dtype(dtype))
+    B.sort_indices()  # rows of 5 .. 40 entries: the loop path
+    ops_.append(m.ops.csr_from_scipy(B))
+    for op in ops_:
+        X = torch.randn((op.n, 4), generator=gen, device="cuda", dtype=tdt)
+        W4 = op.matmat_blocked(X)
+        W1 = op.matmat_blocked(X[:, :1].contiguous())
+        assert torch.equal(W1[:, 0], W4[:, 0])
+    want = B @ X[:, :1].cpu().numpy()
+    tol = 1e-5 if dtype == "float32" else 1e-12
+    assert np.allclose(W1.cpu().numpy(), want, rtol=tol, atol=tol)
