@@ -1,25 +1,26 @@
 // K2s, TMA route -- CSR times probe block for 5- / 7-diagonal band matrices (2-D 5-point and 3-D
-// 7-point stencils) on wide tiles, with the X rows of a chunk staged in shared memory by TMA bulk copies.
+// 7-point stencils) on the 256-wide fp32 tile, with the X rows staged in shared memory by TMA bulk copies.
 //
 // Why (profiles/r2f_spmm_2d_*.txt): the row-group kernel (spmm_csr.cu) is bound
 // by the L1 data pipe (83.7 % of peak: 6 global-load requests and 12 shared-memory wavefronts per
 // warp-row); the band kernel (spmm_strip.cu) halves that but keeps only 3 gathers per warp in flight,
-// in registers, and becomes latency-bound.  Here the in-flight window lives in SHARED MEMORY instead:
-//   * a CTA takes chunks of R consecutive rows; for a band chunk (every row has 5 entries, the
-//     columns of row i are those of row 0 shifted by i, the middle three adjacent with the diagonal
-//     in the centre) the X rows it needs are three contiguous row ranges -- [c0, c0+R),
-//     [d-1, d+R+1), [c4, c4+R) -- i.e. three contiguous byte ranges of the blocked vector, fetched by
-//     three cp.async.bulk copies (TMA, SASS UBLKCP) issued by ONE thread a whole chunk ahead and
-//     tracked by an mbarrier.  (3R + 2) KB per stage, two stages, two CTAs per SM: ~200 KB of loads
-//     in flight per SM without a single register or stalled warp;
+// in registers, and becomes latency-bound.  Here the in-flight window lives in SHARED MEMORY instead.
+// Two kernels, both producer / consumer pipelines (warp 8 produces, warps 0..7 consume, full / empty
+// mbarriers, no CTA barrier in the steady state), both verifying band-ness per chunk of 16 rows
+// from the CSR arrays as they are and falling back to a row-by-row gather path otherwise; the FMA
+// order per row is the CSR order on every path, so W is bit-identical to the other kernels:
+//   * spmm_tma_kernel ("chunked"): a CTA takes chunks of 16 consecutive rows in the row-group
+//     kernel's order (static chunk -> CTA map, completed-chunk window; blocked order for 3-D); the
+//     X rows a band chunk needs are three contiguous runs -- fetched by three cp.async.bulk copies
+//     (SASS UBLKCP) a whole chunk ahead; (3R + 2) KB per stage, two stages, two CTAs per SM.  For 7
+//     diagonals the two +-plane diagonals are gathered by the consumers instead of staged.
+//   * spmm_walk_kernel ("strip walk", the default for 2-D stencils whose line length is known): a
+//     CTA walks down a strip of the grid, so two of the three runs of a chunk are already in its
+//     ring of line segments: ONE copy of R + 2 rows per chunk, 1.1 instead of 3.1 KB of L2 -> SM
+//     traffic per row.
 //   * the consumers read the staged rows with conflict-free LDS.128 (a warp reads 512 contiguous
 //     bytes); a row-group walks consecutive rows, so the -1 / 0 / +1 diagonals slide through
-//     registers (3 LDS.128 per row) and X[row] for the fused alpha dot (matfree/decomp.py:288) is
-//     the diagonal's register;
-//   * band-ness is verified per chunk from the CSR arrays as they are (staged one chunk earlier);
-//     a chunk that is not a band (boundary rows, anything else) takes the gather path row by row.
-//     The FMA order per row is the CSR order either way: W is bit-identical to the other kernels.
-// Chunk scheduling (static chunk -> CTA map, completed-chunk window) is the row-group kernel's.
+//     registers and X[row] for the fused alpha dot (matfree/decomp.py:288) is the diagonal's register.
 #include "internal.h"
 #include "spmm_common.cuh"
 
