@@ -16,7 +16,8 @@ BUILD = os.path.join(ROOT, "matfree_b200", "csrc", "build")
 PREFIXES = ["UTCHMMA", "UTCMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "LDTM", "STTM", "DMMA", "HMMA", "LDGSTS",
             "LDG.E.128", "STG.E.128", "LDS.128", "SHFL", "SYNCS", "MEMBAR", "ATOMG", "REDG", "PREFETCH", "CCTL"]
 HOT = ("gemm_tf32x3", "gemm_dmma_kernel<false, 64", "spmm_csr_kernel<float, 4, 256, 5, false, true, false",
-       "spmm_tma_kernel<float, 4, 256, 5, 16, true, false", "spmm_csr_kernel<float, 4, 256, 7, false, true, false, true",
+       "spmm_tma_kernel<float, 4, 256, 5, 16, true, false", "spmm_walk_kernel<float, 4, 256, 5, 16, true", "spmm_row_thread_kernel<float",
+       "spmm_tma_kernel<float, 4, 256, 7, 16, true, true", "spmm_csr_kernel<float, 4, 256, 7, false, true, false, true",
        "lanczos_update_kernel<float, 4, true", "reorth_dots_all_kernel<float, 4", "cgs_update_dots",
        "reorth_update_kernel<float, 4, true", "probe_gen_signs_kernel<float, 4", "halo_push",
        "tridiag_ql_kernel<float, false")
