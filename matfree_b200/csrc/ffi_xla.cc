@@ -63,9 +63,15 @@ void batch_shape(const ffi::AnyBuffer& v, int64_t* B, int64_t* n) {
   *B = *n ? (int64_t)v.element_count() / *n : 0;
 }
 
+// bandwidth / num_diagonals / line_stride: the structure hints of the operator struct, 0 = unknown, computed
+// once per operator by the binding; they select the TMA-staged kernels for stencils
 mf_operator_t csr_op(const ffi::Buffer<ffi::S32>& indptr, const ffi::Buffer<ffi::S32>& indices,
-                     const ffi::AnyBuffer& data) {
+                     const ffi::AnyBuffer& data, int64_t bandwidth, int64_t num_diagonals,
+                     int64_t line_stride) {
   mf_operator_t op{};
+  op.csr_bandwidth = bandwidth;
+  op.csr_num_diagonals = (int32_t)num_diagonals;
+  op.csr_line_stride = line_stride;
   op.kind = MF_OP_CSR;
   op.dtype = mf_dtype_of(data.element_type());
   op.n = (int64_t)indptr.element_count() - 1;
@@ -171,10 +177,11 @@ ffi::Error LanczosCommon(cudaStream_t stream, ffi::ScratchAllocator& scratch, co
 ffi::Error LanczosCsrImpl(cudaStream_t stream, ffi::ScratchAllocator scratch,
                           ffi::Buffer<ffi::S32> indptr, ffi::Buffer<ffi::S32> indices,
                           ffi::AnyBuffer data, ffi::AnyBuffer vec, int64_t num_matvecs,
-                          int32_t reortho, ffi::Result<ffi::AnyBuffer> Q,
+                          int32_t reortho, int64_t csr_bandwidth, int64_t csr_num_diagonals,
+                          int64_t csr_line_stride, ffi::Result<ffi::AnyBuffer> Q,
                           ffi::Result<ffi::AnyBuffer> alphas, ffi::Result<ffi::AnyBuffer> betas,
                           ffi::Result<ffi::AnyBuffer> residual, ffi::Result<ffi::AnyBuffer> init_len) {
-  const mf_operator_t op = csr_op(indptr, indices, data);
+  const mf_operator_t op = csr_op(indptr, indices, data, csr_bandwidth, csr_num_diagonals, csr_line_stride);
   return LanczosCommon(stream, scratch, op, vec, num_matvecs, reortho, Q, alphas, betas, residual,
                        init_len);
 }
@@ -250,8 +257,9 @@ ffi::Error SlqEstimateCsrImpl(cudaStream_t stream, ffi::ScratchAllocator scratch
                               ffi::AnyBuffer data, int64_t num_probes, int64_t p0,
                               int64_t num_matvecs, int32_t reortho, int32_t sampler, int32_t x64_bits,
                               int32_t fn, double fn_param, int64_t tile, uint32_t key0, uint32_t key1,
+                              int64_t csr_bandwidth, int64_t csr_num_diagonals, int64_t csr_line_stride,
                               ffi::Result<ffi::AnyBuffer> quad) {
-  const mf_operator_t op = csr_op(indptr, indices, data);
+  const mf_operator_t op = csr_op(indptr, indices, data, csr_bandwidth, csr_num_diagonals, csr_line_stride);
   return EstimateCommon(stream, scratch, op, num_probes, p0, num_matvecs, reortho, sampler, x64_bits,
                         fn, fn_param, tile, key0, key1, quad);
 }
@@ -304,11 +312,17 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Attr<int32_t>("kind")
         .Ret<ffi::AnyBuffer>());
 
-#define MF_LANCZOS_TAIL                \
+#define MF_CSR_HINTS                         \
+  .Attr<int64_t>("csr_bandwidth")            \
+      .Attr<int64_t>("csr_num_diagonals")    \
+      .Attr<int64_t>("csr_line_stride")
+#define MF_LANCZOS_ATTRS               \
   .Arg<ffi::AnyBuffer>()               \
       .Attr<int64_t>("num_matvecs")    \
-      .Attr<int32_t>("reortho")        \
-      .Ret<ffi::AnyBuffer>()           \
+      .Attr<int32_t>("reortho")
+#define MF_LANCZOS_TAIL MF_LANCZOS_ATTRS MF_LANCZOS_RETS
+#define MF_LANCZOS_RETS                \
+  .Ret<ffi::AnyBuffer>()               \
       .Ret<ffi::AnyBuffer>()           \
       .Ret<ffi::AnyBuffer>()           \
       .Ret<ffi::AnyBuffer>()           \
@@ -321,7 +335,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Ctx<ffi::ScratchAllocator>()
         .Arg<ffi::Buffer<ffi::S32>>()
         .Arg<ffi::Buffer<ffi::S32>>()
-        .Arg<ffi::AnyBuffer>() MF_LANCZOS_TAIL);
+        .Arg<ffi::AnyBuffer>() MF_LANCZOS_ATTRS MF_CSR_HINTS MF_LANCZOS_RETS);
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
     mf_lanczos_dense_ffi, LanczosDenseImpl,
@@ -351,7 +365,8 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Attr<double>("fn_param")
         .Ret<ffi::AnyBuffer>());
 
-#define MF_ESTIMATE_TAIL               \
+#define MF_ESTIMATE_TAIL MF_ESTIMATE_ATTRS.Ret<ffi::AnyBuffer>()
+#define MF_ESTIMATE_ATTRS              \
   .Attr<int64_t>("num_probes")         \
       .Attr<int64_t>("p0")             \
       .Attr<int64_t>("num_matvecs")    \
@@ -362,8 +377,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
       .Attr<double>("fn_param")        \
       .Attr<int64_t>("tile")           \
       .Attr<uint32_t>("key0")          \
-      .Attr<uint32_t>("key1")          \
-      .Ret<ffi::AnyBuffer>()
+      .Attr<uint32_t>("key1")
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
     mf_slq_estimate_csr_ffi, SlqEstimateCsrImpl,
@@ -372,7 +386,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(
         .Ctx<ffi::ScratchAllocator>()
         .Arg<ffi::Buffer<ffi::S32>>()
         .Arg<ffi::Buffer<ffi::S32>>()
-        .Arg<ffi::AnyBuffer>() MF_ESTIMATE_TAIL);
+        .Arg<ffi::AnyBuffer>() MF_ESTIMATE_ATTRS MF_CSR_HINTS.Ret<ffi::AnyBuffer>());
 
 XLA_FFI_DEFINE_HANDLER_SYMBOL(
     mf_slq_estimate_dense_ffi, SlqEstimateDenseImpl,
