@@ -146,7 +146,8 @@ class CsrOperator(Operator):
 
     def _count_diagonals(self, counts):
         """Number of distinct diagonals (col - row) if every entry lies on the diagonals of the longest
-        row and that row has at most 8 entries, else 255 ("many"); 0 for an empty matrix.  A hint for the
+        row, that row has at most 8 entries and its offsets look like a grid stencil's (symmetric, with
+        -1 / 0 / +1), else 255 ("many / not a stencil"); 0 for an empty matrix.  A hint for the
         kernel choice (`mf_operator_t::csr_num_diagonals`): stencil matrices qualify, irregular ones do not."""
         import torch
 
@@ -158,7 +159,8 @@ class CsrOperator(Operator):
         k = int(torch.argmax(counts))
         j0 = int(self.indptr[k])
         offs = (self.indices[j0:j0 + self.max_row_nnz] - k).tolist()
-        if len(set(offs)) != len(offs):
+        # a grid stencil: distinct, symmetric offsets around the three adjacent middle diagonals
+        if len(set(offs)) != len(offs) or sorted(offs) != sorted(-o for o in offs) or not {-1, 0, 1} <= set(offs):
             return 255
         row_of = torch.repeat_interleave(torch.arange(self.n, device=self.indices.device, dtype=torch.int32),
                                          counts.to(torch.int64))
