@@ -376,22 +376,48 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
   } else {
     // ------------------------------------------------------------------ consumer warps
     const int lr0 = grp * S;
+    int far_lo = 0, far_hi = 0;  // offsets of the gathered diagonals in the last band chunk
+    bool far_known = false;
     int64_t ch = blockIdx.x;
     for (int64_t t = 0; ch < nchunks; ++t, ch += G) {
       const int stage = (int)(t & (NS - 1));
       const int64_t r0 = row0_of(ch);
       const int64_t coff = r0 * ld;
-      tma_mbar_wait(&s_full[stage], (unsigned int)((t / NS) & 1));  // X rows / table of chunk t landed
-      if (s_band[stage]) {
-        // the two outermost diagonals of a 7-diagonal band: gathered from global memory / L2
-        T xf[FAR ? 2 : 1][S][VEC];
-        if constexpr (FAR > 0) {
-          const int64_t rlo = r0 + lr0 + s_far[stage * 2 + 0], rhi = r0 + lr0 + s_far[stage * 2 + 1];
+      // The two outermost diagonals of a 7-diagonal band are gathered from global memory / L2, two
+      // rows ahead of their use.  Their offsets come with the stage, but a stencil has the same ones
+      // in every chunk: the first two rows are requested BEFORE the wait with the offsets of the last
+      // band chunk (in flight while the stage lands) and again after it only if the offsets differ.
+      constexpr int FD = S < 2 ? S : 2;
+      T xf[FAR ? 2 : 1][FD][VEC];
+      bool spec = false;
+      if constexpr (FAR > 0) {
+        const int64_t rlo = r0 + lr0 + far_lo, rhi = r0 + lr0 + far_hi;
+        if (far_known && rlo >= 0 && rhi + S <= n) {
+          spec = true;
 #pragma unroll
-          for (int i = 0; i < S; ++i) {
+          for (int i = 0; i < FD; ++i) {
             ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
             ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
           }
+        }
+      }
+      tma_mbar_wait(&s_full[stage], (unsigned int)((t / NS) & 1));  // X rows / table of chunk t landed
+      if (s_band[stage]) {
+        int64_t rlo = 0, rhi = 0;
+        if constexpr (FAR > 0) {
+          const int flo = s_far[stage * 2 + 0], fhi = s_far[stage * 2 + 1];
+          rlo = r0 + lr0 + flo;
+          rhi = r0 + lr0 + fhi;
+          if (!spec || flo != far_lo || fhi != far_hi) {
+#pragma unroll
+            for (int i = 0; i < FD; ++i) {
+              ldx<T, VEC>(Xc, (rlo + i) * LD, xf[0][i]);
+              ldx<T, VEC>(Xc, (rhi + i) * LD, xf[1][i]);
+            }
+          }
+          far_lo = flo;
+          far_hi = fhi;
+          far_known = true;
         }
         const T* __restrict__ xs = s_x + (size_t)stage * L::kStageRows * LD + c0;
         const T* __restrict__ xb = xs + (size_t)(MID + lr0) * LD;  // middle run: rows lr, lr+1, lr+2
@@ -405,8 +431,12 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
           if constexpr (FAR > 0) {
 #pragma unroll
             for (int q = 0; q < VEC; ++q) {
-              x[0][q] = xf[0][i][q];
-              x[SEGL - 1][q] = xf[1][i][q];
+              x[0][q] = xf[0][i % FD][q];
+              x[SEGL - 1][q] = xf[1][i % FD][q];
+            }
+            if (i + FD < S) {
+              ldx<T, VEC>(Xc, (rlo + i + FD) * LD, xf[0][i % FD]);
+              ldx<T, VEC>(Xc, (rhi + i + FD) * LD, xf[1][i % FD]);
             }
           }
 #pragma unroll
