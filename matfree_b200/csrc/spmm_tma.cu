@@ -325,22 +325,28 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
           }
         }
       } else if (ok && lane < R) {
+        // rows that miss entries (the x-boundary rows of a grid line): every entry must sit on one
+        // of the diagonals and the columns must ascend strictly.  Branch-free, all candidate
+        // entries in flight at once: this path runs for one chunk in eight on a 256^3 grid and a
+        // serial match per entry made the producer late for the chunks behind it.
         ok = len <= SEGL;
-        int u = 0;
-        for (int e = 0; ok && e < len; ++e) {
-          const int32_t d = colb[jb + e] - (int32_t)(r0c + lane);
-          const T a = valb[jb + e];
-          // next diagonal that matches (columns ascend within a row)
-          bool hit = false;
+        int matched = 0;
+        int32_t dprev = 0;
 #pragma unroll
-          for (int w = 0; w < SEGL; ++w)
-            if (!hit && w >= u && o[w] == d) {
-              dv[w] = a;
-              u = w + 1;
-              hit = true;
-            }
-          ok = hit;
+        for (int e = 0; e < SEGL; ++e) {
+          const bool live = e < len;
+          const int32_t d = live ? colb[jb + e] - (int32_t)(r0c + lane) : 0;
+          const T a = live ? valb[jb + e] : T(0);
+          ok = ok && (e == 0 || !live || d > dprev);
+          dprev = d;
+#pragma unroll
+          for (int w = 0; w < SEGL; ++w) {
+            const bool hit = live && o[w] == d;
+            dv[w] = hit ? a : dv[w];
+            matched += hit ? 1 : 0;
+          }
         }
+        ok = ok && matched == len;
       }
       const bool band = __all_sync(0xffffffffu, ok);
       // the consumers have released this stage (its use NS chunks ago)
@@ -723,21 +729,26 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
               }
             }
           } else if (ok && lane < R) {
+            // rows that miss entries: branch-free match of every entry against the diagonals (see
+            // spmm_tma_kernel)
             ok = len <= SEGL;
-            int u = 0;
-            for (int e = 0; ok && e < len; ++e) {
-              const int32_t d = colb[jb + e] - (int32_t)(r0c + lane);
-              const T a = valb[jb + e];
-              bool hit = false;
+            int matched = 0;
+            int32_t dprev = 0;
 #pragma unroll
-              for (int w = 0; w < SEGL; ++w)
-                if (!hit && w >= u && o[w] == d) {
-                  dv[w] = a;
-                  u = w + 1;
-                  hit = true;
-                }
-              ok = hit;
+            for (int e = 0; e < SEGL; ++e) {
+              const bool live = e < len;
+              const int32_t d = live ? colb[jb + e] - (int32_t)(r0c + lane) : 0;
+              const T a = live ? valb[jb + e] : T(0);
+              ok = ok && (e == 0 || !live || d > dprev);
+              dprev = d;
+#pragma unroll
+              for (int w = 0; w < SEGL; ++w) {
+                const bool hit = live && o[w] == d;
+                dv[w] = hit ? a : dv[w];
+                matched += hit ? 1 : 0;
+              }
             }
+            ok = ok && matched == len;
           }
           band = __all_sync(0xffffffffu, ok);
           ++t;
