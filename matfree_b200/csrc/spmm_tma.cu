@@ -947,8 +947,9 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
   if (((uintptr_t)X & 15) != 0) return MF_OK;
   static const int env_throttle = env_int("MF_SPMM_THROTTLE", 1);
   // completed-chunk window beyond the resident grid, in rows: wide in ascending order (C2: 6.6 ms at
-  // 24576 rows, 7.6 at 8192, 10.8 at 0), one block in the blocked order (3-D target: 11.1 ms at 4096
-  // rows, 11.7 at 24576 -- a wider window spreads the CTAs over more planes than L2 keeps)
+  // 24576 rows, 7.6 at 8192, 10.8 at 0), two blocks in the blocked order (3-D target: 9.9 ms at 8192
+  // or 12288 rows, 10.1 at 6144, 10.4 at 4096, 11.3 at 16384 -- a wider window spreads the CTAs over
+  // more planes than L2 keeps; profiles/r2zc_window.jsonl, r2zp_sweep.jsonl, r2zq_sweep.jsonl)
   static const int env_window_rows = env_int("MF_SPMM_TMA_WINDOW", 0);
   Finalize fin{};
   double* partial = nullptr;
@@ -1029,7 +1030,7 @@ int32_t launch_spmm_tma(const int32_t* indptr, const int32_t* indices, const voi
     const int grid = resident_grid((const void*)kern, kBlock + 32, L::kBytes, nchunks);            \
     /* the rows in flight stay one contiguous window (see env_window_rows above) */              \
     const int wrows = env_window_rows > 0 ? env_window_rows                                        \
-                                          : (prm.block_rows != 0 ? prm.block_rows : 24576);        \
+                                          : (prm.block_rows != 0 ? 2 * prm.block_rows : 24576);    \
     prm.window = grid + wrows / L::R;                                                              \
     kern<<<grid, kBlock + 32, L::kBytes, st>>>(indptr, indices, (const float*)data, n,             \
                                                (const float*)X, (const float*)s, (float*)W, prm,   \
