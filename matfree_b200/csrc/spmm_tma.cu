@@ -111,6 +111,48 @@ __device__ __forceinline__ void tma_mbar_arrive(uint64_t* bar) {
                : "memory");
 }
 
+// The producer warp's match of a chunk's rows against the diagonals `o` (lane r <-> row r): fills
+// the row's coefficients by diagonal (zero where the entry is absent) and returns whether the row is
+// on the band.  `full_rows`: every row of the chunk has all SEGL entries (the common case), then
+// entry u must sit on diagonal u.  Otherwise (the x-boundary rows of a grid line miss an entry)
+// every entry must sit on one of the diagonals and the columns must ascend strictly -- branch-free,
+// all candidate entries in flight at once: that path runs for one chunk in eight on a 256^3 grid,
+// and a serial match per entry made the producer late for the chunks behind it.
+template <typename T, int SEGL>
+__device__ __forceinline__ bool tma_match_row(bool ok, bool full_rows, const int32_t* colb,
+                                              const T* valb, int jb, int len, int32_t row,
+                                              const int32_t (&o)[SEGL], T (&dv)[SEGL]) {
+#pragma unroll
+  for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
+  if (!ok) return false;
+  if (full_rows) {
+#pragma unroll
+    for (int u = 0; u < SEGL; ++u) {
+      ok = ok && colb[jb + u] - row == o[u];
+      dv[u] = valb[jb + u];
+    }
+    return ok;
+  }
+  ok = len <= SEGL;
+  int matched = 0;
+  int32_t dprev = 0;
+#pragma unroll
+  for (int e = 0; e < SEGL; ++e) {
+    const bool live = e < len;
+    const int32_t d = live ? colb[jb + e] - row : 0;
+    const T a = live ? valb[jb + e] : T(0);
+    ok = ok && (e == 0 || !live || d > dprev);
+    dprev = d;
+#pragma unroll
+    for (int w = 0; w < SEGL; ++w) {
+      const bool hit = live && o[w] == d;
+      dv[w] = hit ? a : dv[w];
+      matched += hit ? 1 : 0;
+    }
+  }
+  return ok && matched == len;
+}
+
 // Dynamic shared memory layout (per CTA):
 //   [NS stages][3R + 2 rows][LD] T     X rows: run A (R), run B (R + 2), run C (R)
 //   [8][R + 1] int32                   producer-private: row pointers of chunks t .. t+5
@@ -313,41 +355,8 @@ spmm_tma_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ 
       }
       // the row's coefficients by diagonal, in registers until the stage is free
       T dv[SEGL];
-#pragma unroll
-      for (int u = 0; u < SEGL; ++u) dv[u] = T(0);
-      if (fullm == (1u << R) - 1u) {
-        // every row has all SEGL entries (the common case): entry u must sit on diagonal u
-        if (ok && lane < R) {
-#pragma unroll
-          for (int u = 0; u < SEGL; ++u) {
-            ok = ok && colb[jb + u] - (int32_t)(r0c + lane) == o[u];
-            dv[u] = valb[jb + u];
-          }
-        }
-      } else if (ok && lane < R) {
-        // rows that miss entries (the x-boundary rows of a grid line): every entry must sit on one
-        // of the diagonals and the columns must ascend strictly.  Branch-free, all candidate
-        // entries in flight at once: this path runs for one chunk in eight on a 256^3 grid and a
-        // serial match per entry made the producer late for the chunks behind it.
-        ok = len <= SEGL;
-        int matched = 0;
-        int32_t dprev = 0;
-#pragma unroll
-        for (int e = 0; e < SEGL; ++e) {
-          const bool live = e < len;
-          const int32_t d = live ? colb[jb + e] - (int32_t)(r0c + lane) : 0;
-          const T a = live ? valb[jb + e] : T(0);
-          ok = ok && (e == 0 || !live || d > dprev);
-          dprev = d;
-#pragma unroll
-          for (int w = 0; w < SEGL; ++w) {
-            const bool hit = live && o[w] == d;
-            dv[w] = hit ? a : dv[w];
-            matched += hit ? 1 : 0;
-          }
-        }
-        ok = ok && matched == len;
-      }
+      ok = tma_match_row<T, SEGL>(ok && lane < R, fullm == (1u << R) - 1u, colb, valb, jb, len,
+                                  (int32_t)(r0c + lane), o, dv) || (ok && lane >= R);
       const bool band = __all_sync(0xffffffffu, ok);
       // the consumers have released this stage (its use NS chunks ago)
       if (t >= NS) tma_mbar_wait(&s_empty[stage], (unsigned int)(((t / NS) + 1) & 1));
@@ -720,36 +729,8 @@ spmm_walk_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__
             o[SEGL - 1] = (int32_t)plane;
           }
           const unsigned int fullm = __ballot_sync(0xffffffffu, ok && lane < R && len == SEGL);
-          if (fullm == (1u << R) - 1u) {
-            if (ok && lane < R) {
-#pragma unroll
-              for (int u = 0; u < SEGL; ++u) {
-                ok = ok && colb[jb + u] - (int32_t)(r0c + lane) == o[u];
-                dv[u] = valb[jb + u];
-              }
-            }
-          } else if (ok && lane < R) {
-            // rows that miss entries: branch-free match of every entry against the diagonals (see
-            // spmm_tma_kernel)
-            ok = len <= SEGL;
-            int matched = 0;
-            int32_t dprev = 0;
-#pragma unroll
-            for (int e = 0; e < SEGL; ++e) {
-              const bool live = e < len;
-              const int32_t d = live ? colb[jb + e] - (int32_t)(r0c + lane) : 0;
-              const T a = live ? valb[jb + e] : T(0);
-              ok = ok && (e == 0 || !live || d > dprev);
-              dprev = d;
-#pragma unroll
-              for (int w = 0; w < SEGL; ++w) {
-                const bool hit = live && o[w] == d;
-                dv[w] = hit ? a : dv[w];
-                matched += hit ? 1 : 0;
-              }
-            }
-            ok = ok && matched == len;
-          }
+          ok = tma_match_row<T, SEGL>(ok && lane < R, fullm == (1u << R) - 1u, colb, valb, jb, len,
+                                      (int32_t)(r0c + lane), o, dv) || (ok && lane >= R);
           band = __all_sync(0xffffffffu, ok);
           ++t;
         }
