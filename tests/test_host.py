@@ -256,3 +256,45 @@ def test_ffi_shim_compiles_and_matches_integration_doc(tmp_path):
     lib = _lib.load()
     for name in called:
         assert hasattr(lib, name) and name in _lib.SIGNATURES, name
+
+
+def test_integration_doc_csr_hints_on_known_stencils():
+    """The `csr_hints` helper INTEGRATION.md gives the reference-side binding (NumPy, run once per
+    operator) must produce the structure hints of include/matfree_b200.h that `matfree_b200.ops.csr`
+    computes on the device: bandwidth, number of diagonals, line stride of 2-D / 3-D grid stencils,
+    and "not a stencil" for an irregular matrix."""
+    import re
+
+    import numpy as np
+    import scipy.sparse as sp
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"^def csr_hints\(.*?(?=^def )", doc, re.S | re.M)
+    assert m, "INTEGRATION.md no longer defines csr_hints"
+    ns = {"np": np}
+    exec(m.group(0), ns)
+    csr_hints = ns["csr_hints"]
+
+    def lap(shape):
+        mats = [sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(k, k)) for k in shape]
+        out = None
+        for i, T in enumerate(mats):
+            term = None
+            for j, k in enumerate(shape):
+                f = T if i == j else sp.identity(k)
+                term = f if term is None else sp.kron(term, f)
+            out = term if out is None else out + term
+        A = sp.csr_matrix(out)
+        A.sort_indices()
+        return A
+
+    A2 = lap((6, 32))
+    h = csr_hints(A2.indptr, A2.indices)
+    assert (int(h["csr_bandwidth"]), int(h["csr_num_diagonals"]), int(h["csr_line_stride"])) == (32, 5, 32)
+    A3 = lap((3, 4, 16))
+    h = csr_hints(A3.indptr, A3.indices)
+    assert (int(h["csr_bandwidth"]), int(h["csr_num_diagonals"]), int(h["csr_line_stride"])) == (64, 7, 16)
+    B = sp.random(200, 200, density=0.02, random_state=np.random.default_rng(0), format="csr")
+    B.sort_indices()
+    h = csr_hints(B.indptr, B.indices)
+    assert int(h["csr_num_diagonals"]) == 255 and int(h["csr_line_stride"]) == 0
