@@ -466,17 +466,20 @@ def run_ours(a, rank, local_rank, world):
         kernels[cls] = ent
     top = next(iter(kernels))
     # dram__bytes_read.sum + dram__bytes_write.sum per launch: NOT measured in this run (ncu cannot
-    # run inside a timed bench) -- a static number from the committed ncu --set full capture of this
-    # very configuration (grid 4096, tile 256; these two kernels are unchanged since): it equals the
-    # algorithmic bytes to 0.2 % (lanczos_update) / 2 % (spmm_csr), i.e. no wasted re-reads
-    ncu_traffic = {"lanczos_update": 51.686667e9 + 17.160440e9, "spmm_csr": 18.537456e9 + 17.154800e9,
+    # run inside a timed bench) -- static numbers from the committed ncu captures of this very
+    # configuration (grid 4096, tile 256) on the final code of round 2: lanczos_update
+    # profiles/r2zx_update_dram.txt, the strip-walk CSR product profiles/r2zf_spmm_2d_walk.txt, probe_gen
+    # profiles/r1o_full.txt (unchanged kernel).  They equal the algorithmic bytes to 0.1 % / 0.2 %, i.e. no
+    # wasted re-reads
+    ncu_traffic = {"lanczos_update": 51.54e9 + 17.15e9, "spmm_csr": 17.918636e9 + 17.137428e9,
                    "probe_gen": 0.003344e9 + 17.124462e9}
     traffic = ncu_traffic.get(top) if (a.workload == "c2" and a.grid == 4096 and tile == 256) else None
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top].get("achieved_gbs"),
                 "peak": peak, "unit": "GB/s", "frac": kernels[top].get("frac_of_peak"),
                 "traffic": traffic,
-                "traffic_source": ("static: ncu --set full capture profiles/r1o_full.txt of this configuration "
-                                   "(not measured in this run)") if traffic else None,
+                "traffic_source": ("static: ncu capture of this configuration on the final round-2 code, "
+                                   "profiles/r2zx_update_dram.txt / r2zf_spmm_2d_walk.txt (not measured in this run)")
+                if traffic else None,
                 "peak_source": peak_kind, "share_of_step": kernels[top]["share"],
                 "note": ("the peak is the driver's copy benchmark (1 read : 1 write); this kernel streams "
                          "3 reads : 1 write, which HBM serves slightly faster, so frac can exceed 1"
