@@ -1,6 +1,9 @@
 #!/bin/bash
-# producer with the branch-free match for rows that miss entries (in-tree library) against the serial match (ab/lib_head.so)
-# library) against all of them after it (ab/lib_head.so), interleaved on the 3-D target
+# A/B of a kernel change on the 3-D target: the in-tree library against ab/lib_head.so, the library built from the
+# commit before the change (git stash; python -c 'import __graft_entry__ as g; g.build()'; cp matfree_b200/_lib/libmatfree_b200.so ab/lib_head.so;
+# git stash pop; rebuild) and selected with MF_LIB_PATH; interleaved because the pods differ by a few percent.
+# Used for: the +-plane gathers issued before the stage wait (profiles/r2zn_farspec.jsonl) and the producer's
+# branch-free match for rows that miss entries (profiles/r2zo_match.jsonl).
 timeout 600 python -m pytest tests/test_gpu_spmm_band.py tests/test_gpu_parity.py -q 2>&1 | tail -2
 out=gpurun_out/r2zo_farspec.jsonl
 : > $out
