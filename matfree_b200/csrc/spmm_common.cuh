@@ -70,7 +70,7 @@ struct SpmmParams {
 };
 
 // first row of chunk c under the row order of `p` (R = p.rows_per_chunk)
-__device__ __forceinline__ int64_t chunk_row0(int64_t c, const SpmmParams& p) {
+__host__ __device__ __forceinline__ int64_t chunk_row0(int64_t c, const SpmmParams& p) {
   if (p.block_rows == 0) return c * p.rows_per_chunk;
   // 32-bit arithmetic (fewer than 2^31 chunks); chunks per block is a power of two
   const unsigned int cu = (unsigned int)c;

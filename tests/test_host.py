@@ -298,3 +298,22 @@ def test_integration_doc_csr_hints_on_known_stencils():
     B.sort_indices()
     h = csr_hints(B.indptr, B.indices)
     assert int(h["csr_num_diagonals"]) == 255 and int(h["csr_line_stride"]) == 0
+
+
+def test_blocked_row_order_is_a_permutation_of_the_chunks(tmp_path):
+    """`chunk_row0` / `choose_row_order` (csrc/spmm_common.cuh: the blocked row order of the CSR product
+    for 3-D stencils) checked on the host: every chunk start is visited exactly once and consecutive
+    blocks are the same row range of consecutive planes (tests/csrc/row_order_check.cu, compiled with
+    nvcc; no CUDA call is made, so no GPU is needed)."""
+    import shutil
+
+    if shutil.which("nvcc") is None:
+        pytest.skip("nvcc not on PATH")
+    exe = str(tmp_path / "row_order_check")
+    r = subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17",
+                        "-I", os.path.join(ROOT, "matfree_b200", "csrc"), "-I", os.path.join(ROOT, "include"),
+                        "-o", exe, os.path.join(ROOT, "tests", "csrc", "row_order_check.cu")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "row order: ok" in r.stdout, r.stdout + r.stderr
