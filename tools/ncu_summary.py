@@ -3,6 +3,9 @@
 
   python tools/ncu_summary.py launches gpurun_out/launches.csv            > profiles/<name>_launches.txt
   python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [regex]        > profiles/<name>_full.txt
+  python tools/ncu_summary.py wide gpurun_out/prof.ncu-rep [regex]        > profiles/<name>.txt   (all memory-hierarchy counters)
+  python tools/ncu_summary.py hotspots gpurun_out/prof.ncu-rep [top]      > profiles/<name>_hotspots.txt
+      (needs a capture made with --import-source on: SASS lines by warp-stall samples, with the stall reasons)
 """
 import collections
 import csv
@@ -95,9 +98,35 @@ def full(path, pattern=None):
                 print(f"  {m:85s} {r[idx[m]]:>18s} {units[idx[m]]}")
 
 
+def hotspots(path, top=40):
+    """SASS lines of a `--set full --import-source on` capture ordered by warp-stall samples."""
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    h0 = next(i for i, r in enumerate(rows) if any("Sampl" in c for c in r))
+    hdr = rows[h0]
+    key = next(i for i, c in enumerate(hdr) if "Sampl" in c)
+    src = hdr.index("Source") if "Source" in hdr else 1
+
+    def num(x):
+        try:
+            return float(x)
+        except ValueError:
+            return 0.0
+
+    body = [r for r in rows[h0 + 1:] if len(r) == len(hdr)]
+    tot = sum(num(r[key]) for r in body) or 1.0
+    print(f"# warp-stall sampling hot spots of {path}: % of samples, SASS, stall reasons (samples)")
+    for r in sorted(body, key=lambda r: -num(r[key]))[:top]:
+        why = " ".join(f"{h}={r[i]}" for i, h in enumerate(hdr)
+                       if h.startswith("stall") and "Not" not in h and num(r[i]) > 0)
+        print(f"{100 * num(r[key]) / tot:5.1f} {r[src][:90]} | {why[:200]}")
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "hotspots":
+        hotspots(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
     elif sys.argv[1] == "wide":
         wide(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:

@@ -5,25 +5,7 @@ T=/tmp/ncu_r2; mkdir -p $T
 A="tools/bench_c4.py --steps 1 --warmup 0 --no-kernel-timing"
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:cgs_update -s 80 -c 1 -o $T/cgs -f python $A > /dev/null 2>> gpurun_out/r2t.err
 python tools/ncu_summary.py wide $T/cgs.ncu-rep > gpurun_out/r2t_cgs.txt 2>> gpurun_out/r2t.err
-ncu -i $T/cgs.ncu-rep --page source --csv > $T/cgs_src.csv 2>> gpurun_out/r2t.err
-head -c 6000 $T/cgs_src.csv > gpurun_out/r2t_cgs_source_head.txt
-python - <<'PY' > gpurun_out/r2t_cgs_source.txt
-import csv
-rows=list(csv.reader(open("/tmp/ncu_r2/cgs_src.csv")))
-# the page starts with metadata rows; the table header is the first row naming a sampling column
-h0=next(i for i,r in enumerate(rows) if any("Sampl" in c for c in r))
-hdr=rows[h0]; idx={h:i for i,h in enumerate(hdr)}
-key=next(i for i,c in enumerate(hdr) if "Sampl" in c)
-def num(x):
-    try: return float(x)
-    except: return 0.0
-body=[r for r in rows[h0+1:] if len(r)==len(hdr)]
-tot=sum(num(r[key]) for r in body) or 1
-print(hdr)
-src=idx.get("Source", 1)
-for r in sorted(body,key=lambda r:-num(r[key]))[:60]:
-    print(round(100*num(r[key])/tot,1), r[src][:100], "|", " ".join(f"{h}={r[i]}" for i,h in enumerate(hdr) if h.startswith("stall") and num(r[i])>0)[:260])
-PY
+python tools/ncu_summary.py hotspots $T/cgs.ncu-rep > gpurun_out/r2t_cgs_source.txt 2>> gpurun_out/ncu_hotspots.err
 #false && timeout 600 ncu --set full --clock-control none -k regex:reorth_update_kernel -s 160 -c 1 -o $T/upd -f python $A > /dev/null 2>> gpurun_out/r2t.err
 #false && python tools/ncu_summary.py wide $T/upd.ncu-rep > gpurun_out/r2t_upd.txt 2>> gpurun_out/r2t.err
 for f in gpurun_out/r2t_cgs.txt gpurun_out/r2t_upd.txt; do echo == $f; grep -E "gpu__time_duration.sum|l1tex__data_pipe_lsu_wavefronts.avg.pct|l1tex__data_bank_conflicts|smsp__inst_executed.sum |dram__bytes_read.sum |dram__bytes_write.sum |dram__throughput.avg.pct|smsp__average_warps_issue_stalled_.*ratio|sm__warps_active.avg.pct|lts__t_sectors_srcunit_tex_op_read.sum |l1tex__throughput.avg.pct|launch__shared_mem_per_block_dynamic|launch__grid_size" $f | cut -c1-150; done

@@ -4,20 +4,6 @@ B="--steps 1 --warmup 1 --profile --no-e2e --no-cpu-baseline --no-extras --probe
 T=/tmp/ncu_r2; mkdir -p $T
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:spmm -s 6 -c 1 -o $T/spmm_2d_tma2 -f python bench.py $B > /dev/null 2>> gpurun_out/r2zf.err
 python tools/ncu_summary.py wide $T/spmm_2d_tma2.ncu-rep > gpurun_out/r2zf_spmm_2d_tma.txt 2>> gpurun_out/r2zf.err
-ncu -i $T/spmm_2d_tma2.ncu-rep --page source --csv > $T/src.csv 2>> gpurun_out/r2zf.err
-python - <<'PY' > gpurun_out/r2zf_spmm_2d_tma_hotspots.txt
-import csv
-rows=list(csv.reader(open("/tmp/ncu_r2/src.csv")))
-h0=next(i for i,r in enumerate(rows) if any("Sampl" in c for c in r))
-hdr=rows[h0]; key=next(i for i,c in enumerate(hdr) if "Sampl" in c)
-def num(x):
-    try: return float(x)
-    except: return 0.0
-body=[r for r in rows[h0+1:] if len(r)==len(hdr)]
-tot=sum(num(r[key]) for r in body) or 1
-src=hdr.index("Source") if "Source" in hdr else 1
-for r in sorted(body,key=lambda r:-num(r[key]))[:40]:
-    print(round(100*num(r[key])/tot,1), r[src][:90], "|", " ".join(f"{h}={r[i]}" for i,h in enumerate(hdr) if h.startswith("stall") and "Not" not in h and num(r[i])>0)[:200])
-PY
+python tools/ncu_summary.py hotspots $T/spmm_2d_tma2.ncu-rep > gpurun_out/r2zf_spmm_2d_tma_hotspots.txt 2>> gpurun_out/ncu_hotspots.err
 grep -E "gpu__time_duration.sum|l1tex__data_pipe_lsu_wavefronts.avg.pct|smsp__inst_executed.sum |dram__bytes_read.sum |dram__bytes_write.sum |lts__throughput.avg|smsp__average_warps_issue_stalled_(barrier|long|short|wait|mio|sleeping|selected|not_sel|branch|no_inst).*ratio|sm__warps_active.avg.pct|l1tex__m_xbar2l1tex_read_bytes.sum " gpurun_out/r2zf_spmm_2d_tma.txt | cut -c1-150
 head -30 gpurun_out/r2zf_spmm_2d_tma_hotspots.txt | cut -c1-300
