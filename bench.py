@@ -471,7 +471,7 @@ def run_ours(a, rank, local_rank, world):
     # profiles/r2zx_update_dram.txt, the strip-walk CSR product profiles/r2zf_spmm_2d_walk.txt, probe_gen
     # profiles/r1o_full.txt (unchanged kernel).  They equal the algorithmic bytes to 0.1 % / 0.2 %, i.e. no
     # wasted re-reads
-    ncu_traffic = {"lanczos_update": 51.54e9 + 17.15e9, "spmm_csr": 17.918636e9 + 17.137428e9,
+    ncu_traffic = {"lanczos_update": 51.54e9 + 17.15e9, "spmm_csr": 18.154080e9 + 17.133408e9,
                    "probe_gen": 0.003344e9 + 17.124462e9}
     traffic = ncu_traffic.get(top) if (a.workload == "c2" and a.grid == 4096 and tile == 256) else None
     roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top].get("achieved_gbs"),
